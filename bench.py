@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the Craft hot path (teacher action + features + step) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E] [--impl ours|reference]
+
+One "step" = one rollout tick of the whole batch: for every env the BFS teacher's action, the
+f32[404] feature vector and the state transition (with done / success / auto-reset), i.e. the body
+of trainers/imitation.py:42-73.  Workload at N=1: BASELINE.json configs[1] — craft_medium train
+tasks (17,600 instances, regenerated with the reference's make_data.py, committed as
+tests/golden/craft_medium_splits.npz) tiled to 65,536 envs; weak scaling for N>1 (same envs per
+GPU, no data-path collective; one NCCL all-reduce of the episode statistics after the timed
+region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/s (step+features+expert)"
+UNIT = "env-steps/s"
+# algorithmic bytes per env-step at craft_medium (DESIGN.md §"Rooflines")
+BYTES_FUSED = 1815
+BYTES_STEP, BYTES_FEATURES, BYTES_EXPERT = 198, 1712, 97
+
+
+def load_workload(n_envs, split="train"):
+    sp = np.load(os.path.join(ROOT, "tests", "golden", "craft_medium_splits.npz"))
+    n_inst = len(sp[split + "_inst_env"])
+    idx = np.arange(n_envs) % n_inst
+    return dict(grids=sp[split + "_grids"], env=sp[split + "_inst_env"][idx],
+                pos=sp[split + "_inst_pos"][idx], task=sp[split + "_inst_task"][idx],
+                n_instances=n_inst, raw=sp)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15] or self.rows
+        for _, line in rows:
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baselines
+def cpu_python_port(budget_s=20.0, procs=None, rounds=1, warm=0):
+    """The reference's Python loop, restated (oracle/craft_ref_port.py), one process per core on a
+    bounded sample of dev-split instances (BASELINE config 1).  Returns one dict per round."""
+    from oracle import craft_ref_port as port
+    procs = procs or os.cpu_count() or 1
+    sp = load_workload(1, "dev")["raw"]
+    # ~4.8k env-steps/s/core and ~10 env-steps per instance
+    n_inst = int(min(2200 * 8, max(procs * 20, budget_s * 450 * procs)))
+    idx = np.arange(n_inst) % 2200
+    runner = port.ParallelRunner("craft_medium", sp["dev_grids"], procs)
+    out = []
+    try:
+        for r in range(warm + rounds):
+            steps, secs = runner.run(sp["dev_inst_env"][idx], sp["dev_inst_pos"][idx],
+                                     sp["dev_inst_task"][idx], n_inst)
+            if r >= warm:
+                out.append({"value": steps / secs, "unit": UNIT, "cores": procs, "kind": "port",
+                            "sample": "%d dev-split instances (%d env-steps) through "
+                                      "oracle/craft_ref_port.py (pure-Python port of the reference "
+                                      "loop), %d processes, %.2f s" % (n_inst, steps, procs, secs),
+                            "seconds": secs})
+    finally:
+        runner.close()
+    return out
+
+
+def cpu_native_oracle(n_envs=65536, ticks=20):
+    """The C restatement (oracle/craft_oracle.c) with OpenMP on all cores — a much stronger CPU
+    baseline than the reference's Python, reported for context."""
+    from psketch_b200.tables import CraftTables
+    from oracle.craft_oracle import CraftOracle
+    tables = CraftTables()
+    o = CraftOracle(tables)
+    w = load_workload(n_envs)
+    init_grid = w["grids"][w["env"].astype(np.int64)]
+    state, _, _, _ = o.rollout(1, 40, init_grid, w["pos"].astype(np.int32), w["task"].astype(np.int32))
+    t0 = time.perf_counter()
+    state, stats, _, _ = o.rollout(ticks, 40, init_grid, w["pos"].astype(np.int32),
+                                   w["task"].astype(np.int32), state=state)
+    dt = time.perf_counter() - t0
+    return {"value": int(stats[2]) / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port-c",
+            "sample": "%d envs x %d ticks through oracle/craft_oracle.c (OpenMP), %.2f s" % (n_envs, ticks, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = cpu_python_port(budget_s=max(0.25, 60.0 / max(1, args.steps + args.warmup)),
+                               rounds=args.steps, warm=args.warmup)
+    base = per_step[-1]
+    value = float(np.mean([b["value"] for b in per_step]))
+    ms = float(np.mean([b["seconds"] for b in per_step])) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "craft_medium dev-split instances, teacher+features+step per env "
+                               "in a Python loop (pure-Python port of the reference, one process per core)"},
+        "cpu_baseline": dict(base, value=value),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def time_kernel(fn, iters, torch):
+    fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e-3
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from psketch_b200.tables import CraftTables
+    from psketch_b200.vec import VecCraft
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.envs_per_gpu
+    K, W = args.steps, args.warmup
+    tables = CraftTables()
+    wl = load_workload(n)
+    # each rank owns its own slice of the batch: rotate the instance tiling by rank
+    shift = (rank * n) % wl["n_instances"]
+    env = VecCraft.from_instances(tables, wl["grids"], np.roll(wl["env"], -shift),
+                                  np.roll(wl["pos"], -shift, axis=0), np.roll(wl["task"], -shift),
+                                  max_timesteps=40, device=dev)
+    nf = env.n_features
+    feat_bytes = n * nf * 4
+    ring = max(2, int(np.ceil(1.5 * 126e6 / feat_bytes)) + 1)     # ring of outputs > L2 (126 MB)
+    ring = min(ring, 64)
+    feats = [torch.empty((n, nf), dtype=torch.float32, device=dev) for _ in range(ring)]
+    outs = [dict() for _ in range(ring)]
+    fused = not args.unfused
+
+    def tick(i):
+        env.tick(features_out=feats[i % ring], fused=fused, out=outs[i % ring])
+
+    for i in range(ring):           # allocate output tensors outside the graph
+        tick(i)
+    torch.cuda.synchronize()
+    # CUDA graph of `ring` consecutive ticks (launch-bound otherwise: ~25 us of work per tick)
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(ring):
+                    tick(i)
+        torch.cuda.current_stream().wait_stream(side)
+
+    def run_steps(k):
+        done = 0
+        if graph is not None:
+            while k - done >= ring:
+                graph.replay()
+                done += ring
+        while done < k:
+            tick(done)
+            done += 1
+
+    run_steps(max(W, 3))
+    env.stats.zero_()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    start.record()
+    run_steps(K)
+    end.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    if distributed:
+        dist.barrier()
+    elapsed = start.elapsed_time(end) * 1e-3
+    el = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+    stats = env.stats.clone()
+    if distributed:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)       # the path's only collective
+    elapsed = float(el.item())
+    clocks = sampler.stop(t0, t1) if sampler else None
+    env.check_errors()
+    total_steps = n * K * world
+    value = total_steps / elapsed
+    st = stats.cpu().numpy()
+    assert int(st[2]) == total_steps, "kernel step counter disagrees with the host's"
+
+    # ---- end to end through the public API with host buffers (rank-local, then aggregated)
+    e2e = measure_e2e(torch, tables, wl, n, dev, args)
+    if distributed:
+        ev = torch.tensor([e2e["elapsed"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(ev, op=dist.ReduceOp.MAX)
+        e2e["elapsed"] = float(ev.item())
+    e2e_value = n * e2e["steps"] * world / e2e["elapsed"]
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    per_launch_s = elapsed / K
+    launches_per_step = 1 if fused else 3
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": per_launch_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {
+            "workload": "craft_medium train tasks (17,600 instances tiled), %d parallel envs per GPU, "
+                        "teacher BFS + f32[404] features + step/auto-reset per tick" % n,
+            "envs_per_gpu": n, "max_timesteps": 40, "kernel": "fused tick" if fused else "expert+features+advance",
+            "cuda_graph": graph is not None,
+            "l2": "feature outputs rotate through a ring of %d buffers (%.0f MB > 126 MB L2)"
+                  % (ring, ring * feat_bytes / 1e6),
+        },
+        "clocks": clocks,
+        "gpu_launches": K * launches_per_step,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"], "how": e2e["how"]},
+        "episodes": int(st[0]), "successes": int(st[1]),
+    }
+    # ---- roofline of the dominant kernel
+    if fused:
+        achieved = BYTES_FUSED * n / per_launch_s / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "craft_tick_kernel", "achieved": achieved,
+                            "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_env_step": BYTES_FUSED}
+    # per-kernel numbers (north star: step and features as a fraction of the HBM roofline)
+    kern = {}
+    it = 50
+    act = env.expert()
+    big = [torch.empty((n, nf), dtype=torch.float32, device=dev) for _ in range(min(ring, 8))]
+    cnt = [0]
+
+    def f_feat(impl):
+        def g():
+            env.features(out=big[cnt[0] % len(big)], impl=impl)
+            cnt[0] += 1
+        return g
+
+    snap = env.snapshot()
+    for name, fn, b in (("features_tma", f_feat(0), BYTES_FEATURES), ("features_plain", f_feat(1), BYTES_FEATURES),
+                        ("expert", lambda: env.expert(out=act), BYTES_EXPERT),
+                        ("step", lambda: env.step(act), BYTES_STEP)):
+        dt = time_kernel(fn, it, torch)
+        kern[name] = {"us": dt * 1e6, "GBps": b * n / dt / 1e9, "frac": b * n / dt / 1e9 / peak,
+                      "env_per_s": n / dt}
+    env.restore(snap)
+    if not fused:
+        k = kern["features_tma"]
+        line["roofline"] = {"bound": "hbm", "kernel": "craft_features_kernel", "achieved": k["GBps"],
+                            "peak": peak, "unit": "GB/s", "frac": k["frac"], "traffic": None,
+                            "peak_source": peak_src, "algorithmic_bytes_per_env_step": BYTES_FEATURES}
+    line["kernels"] = kern
+    # ---- CPU baselines on this box's host cores (bounded samples)
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_python_port(budget_s=12.0)[0]
+        try:
+            line["cpu_baseline_native"] = cpu_native_oracle()
+        except Exception as ex:  # noqa: BLE001
+            line["cpu_baseline_native"] = {"error": str(ex)}
+    print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def measure_e2e(torch, tables, wl, n, dev, args):
+    """Same tick through the public API with HOST buffers: every step copies the states in from
+    pinned host memory, runs the fused tick and reads features, teacher actions, done/success and
+    the new states back to pinned host memory."""
+    from psketch_b200.vec import VecCraft
+    env = VecCraft.from_instances(tables, wl["grids"], wl["env"], wl["pos"], wl["task"],
+                                  max_timesteps=40, device=dev)
+    nf = env.n_features
+    h_grid = env.grid.cpu().pin_memory()
+    h_agent = env.agent.cpu().pin_memory()
+    h_feat = torch.empty((n, nf), dtype=torch.float32).pin_memory()
+    h_small = torch.empty((3, n), dtype=torch.uint8).pin_memory()
+    d_feat = torch.empty((n, nf), dtype=torch.float32, device=dev)
+    out = {}
+    steps = max(3, min(args.steps, 20))
+
+    def one():
+        env.grid.copy_(h_grid, non_blocking=True)
+        env.agent.copy_(h_agent, non_blocking=True)
+        env.tick(features_out=d_feat, fused=not args.unfused, out=out)
+        h_feat.copy_(d_feat, non_blocking=True)
+        h_small[0].copy_(out["expert"], non_blocking=True)
+        h_small[1].copy_(out["done"], non_blocking=True)
+        h_small[2].copy_(out["success"], non_blocking=True)
+        h_grid.copy_(env.grid, non_blocking=True)
+        h_agent.copy_(env.agent, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        one()
+    e.record()
+    torch.cuda.synchronize()
+    state_bytes = n * (env.cell_stride + 32)
+    return {"elapsed": s.elapsed_time(e) * 1e-3, "steps": steps, "h2d": state_bytes,
+            "d2h": n * nf * 4 + 3 * n + state_bytes,
+            "how": "VecCraft.tick with pinned host buffers: H2D states, fused tick, D2H features+actions+flags+states, sync per step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--unfused", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

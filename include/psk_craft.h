@@ -1,0 +1,148 @@
+/*
+ * psk_craft.h — C ABI of the B200-native batched Craft environment + BFS teacher.
+ *
+ * The reference (khanhptnk/psketch) has no FFI: its boundary for this path is the duck-typed
+ * Python object API of worlds/craft.py and teachers/*.py.  Every entry point below replaces
+ * one reference method, applied to a whole batch of environments whose state lives in HBM as
+ * structure-of-arrays tensors; psketch_b200/worlds/craft.py and psketch_b200/teachers/ are the
+ * Python-side mirror that binds them (ctypes) and INTEGRATION.md shows the binding a reference
+ * maintainer would add.
+ *
+ * Conventions: every function returns PSK_OK (0) or a PSK_ERR_* code and never throws; all
+ * `uint8_t*`/`float*`/... arguments are DEVICE pointers unless the name starts with `host_`;
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); launches are
+ * asynchronous on that stream.  Kernel-detected conditions that make the reference raise are
+ * OR-ed into `*err_flags` (device int32, may be NULL) as PSK_FLAG_* bits.
+ *
+ * Device state layout (one env = one row in each array):
+ *   grid  u8[n][cell_stride]   kind id per cell, 0 = free, cell (x, y) at x*height + y
+ *                              (the reference's one-hot float64 grid[x, y, kind], craft.py:275-283);
+ *                              cell_stride = width*height rounded up to a multiple of 64.
+ *   agent u8[n][32]            bytes 0..23 inventory counts by kind id (reference: float64[K]),
+ *                              24 x, 25 y, 26 dir, 27 task id, 28 timer, 29..31 reserved.
+ */
+#ifndef PSK_CRAFT_H
+#define PSK_CRAFT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSK_OK 0
+#define PSK_ERR_UNSUPPORTED 1 /* (width, height, window) combination not built */
+#define PSK_ERR_BADARG 2
+#define PSK_ERR_CUDA 3
+
+#define PSK_FLAG_BAD_ACTION 1   /* step(): "Unexpected action" exception, worlds/craft.py:415-416 */
+#define PSK_FLAG_INV_OVERFLOW 2 /* an inventory count would exceed 255 (u8 storage) */
+#define PSK_FLAG_BAD_LEAF 4     /* teacher: leaf is neither 'use' nor 'go', demonstration.py:18 */
+#define PSK_FLAG_OFF_GRID 8     /* agent position outside the grid */
+
+#define PSK_AGENT_BYTES 32
+#define PSK_AG_X 24
+#define PSK_AG_Y 25
+#define PSK_AG_DIR 26
+#define PSK_AG_TASK 27
+#define PSK_AG_TIMER 28
+
+#define PSK_MAX_INV 24
+#define PSK_MAX_KINDS 32
+#define PSK_MAX_RECIPES 16
+#define PSK_MAX_TASKS 32
+#define PSK_MAX_TASK_NODES 16
+
+#define PSK_ACT_DOWN 0
+#define PSK_ACT_UP 1
+#define PSK_ACT_LEFT 2
+#define PSK_ACT_RIGHT 3
+#define PSK_ACT_USE 4
+#define PSK_ACT_STOP 5
+#define PSK_ACT_INVALID 255 /* expert output where the reference asserts */
+
+/* Domain tables (host struct, passed by pointer and copied into kernel parameters).
+ * Replaces: Cookbook (worlds/cookbook.py:7-26), the kind sets of CraftWorld.__init__
+ * (worlds/craft.py:101-107) and the hint tree of TaskManager (data/task.py:34-59).
+ * Built by psketch_b200/tables.py:CraftTables. */
+typedef struct psk_craft_tables {
+    int32_t width, height, n_kinds, window_w, window_h;
+    int32_t n_recipes, n_tasks;
+    int32_t water_kind, stone_kind, bridge_kind, axe_kind;
+    int32_t reserved;
+    uint8_t kind_class[PSK_MAX_KINDS];                       /* 0 free,1 inert,2 workshop,3 water,4 stone,5 grabbable */
+    uint8_t recipes[PSK_MAX_RECIPES][8];                     /* out, workshop, n_in, in0, cnt0, in1, cnt1, yield — firing order */
+    uint8_t task_len[PSK_MAX_TASKS];                         /* nodes in the pre-order flattening of each task's hint tree */
+    uint8_t task_nodes[PSK_MAX_TASKS][PSK_MAX_TASK_NODES][4]; /* sat class, arg kind, leaf kind, skip_to */
+} psk_craft_tables;
+
+typedef struct psk_craft_state {
+    uint8_t *grid;  /* [n][cell_stride] */
+    uint8_t *agent; /* [n][PSK_AGENT_BYTES] */
+    int64_t n;
+    int32_t cell_stride;
+    int32_t reserved;
+} psk_craft_state;
+
+/* Where a finished episode restarts from (CraftScenario.init, worlds/craft.py:270-273). */
+typedef struct psk_craft_episodes {
+    const uint8_t *scen_grid;  /* [n_scen][cell_stride] initial grids (shared between envs) */
+    const int32_t *scen_idx;   /* [n] scenario of each env */
+    const uint8_t *init_agent; /* [n][32] initial agent record (empty inventory, pos, dir, task, timer) */
+} psk_craft_episodes;
+
+/* library / build info: "psketch_b200 <version> sm_100a" */
+const char *psk_version(void);
+/* number of bytes of one feature row, or -1 when the configuration is unsupported */
+int psk_craft_n_features(const psk_craft_tables *t);
+int psk_craft_supported(const psk_craft_tables *t);
+
+/* CraftState.step (worlds/craft.py:332-424), in place.  reward (may be NULL) receives 0.0 per
+ * env; active (may be NULL) masks envs that must not move (the trainers' `if not done[i]`,
+ * trainers/imitation.py:68-72). */
+int psk_craft_step(const psk_craft_tables *t, psk_craft_state s, const uint8_t *action,
+                   const uint8_t *active, float *reward, int32_t *err_flags, void *stream);
+
+/* CraftState.features (worlds/craft.py:296-330) as float32 (students/imitation.py:72-73):
+ * out f32[n][n_features].  impl: 0 = default (TMA bulk-store tiles), 1 = plain vector stores. */
+int psk_craft_features(const psk_craft_tables *t, psk_craft_state s, float *out, int impl,
+                       void *stream);
+
+/* CraftState.satisfies (worlds/craft.py:285-294): out[i] = 1 True, 0 False, 2 None.
+ * task (may be NULL) overrides the task id stored in the agent record. */
+int psk_craft_satisfies(const psk_craft_tables *t, psk_craft_state s, const uint8_t *task,
+                        uint8_t *out, void *stream);
+
+/* DemonstrationTeacher.__call__ (teachers/demonstration.py:9-30, teachers/base.py:10-87):
+ * action u8[n]; dist (may be NULL) i16[n] = BFS path length when a go[...] leaf was searched,
+ * else -1. */
+int psk_craft_expert(const psk_craft_tables *t, psk_craft_state s, const uint8_t *task,
+                     uint8_t *action, int16_t *dist, int32_t *err_flags, void *stream);
+
+/* BaseTeacher.find_closest_resources (teachers/base.py:27-34) for kind[i] (u8[n]):
+ * goal u8[n][2] (255,255 if the kind is absent), length i16[n] (-1 = unreachable/None),
+ * seq (may be NULL) u8[n][seq_cap] the action sequence padded with 255. */
+int psk_craft_find_closest(const psk_craft_tables *t, psk_craft_state s, const uint8_t *kind,
+                           uint8_t *goal, int16_t *length, uint8_t *seq, int32_t seq_cap,
+                           void *stream);
+
+/* CraftWorld.init_state for every env (worlds/craft.py:258-259): working state <- episode start. */
+int psk_craft_reset(psk_craft_state s, psk_craft_episodes ep, const uint8_t *mask, void *stream);
+
+/* One rollout tick for every env — the body of trainers/imitation.py:42-73:
+ *     ref = teacher(task, s); f = s.features(); a = action_in ? action_in[i] : ref
+ *     timer -= 1; done = (a == STOP) or timer <= 0
+ *     done  -> success = s.satisfies(task); s <- episode start (auto-reset)
+ *     !done -> s = s.step(a)
+ * features_out f32[n][n_features] (may be NULL), expert_out u8[n], done_out/success_out u8[n]
+ * (may be NULL), stats u64[4] device accumulators {episodes, successes, env_steps, reserved}
+ * (may be NULL).  fused != 0 selects the single fused kernel, 0 the three-kernel pipeline. */
+int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
+                   const uint8_t *action_in, float *features_out, uint8_t *expert_out,
+                   uint8_t *done_out, uint8_t *success_out, unsigned long long *stats,
+                   int32_t *err_flags, int fused, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSK_CRAFT_H */

@@ -1,0 +1,108 @@
+"""ctypes binding of libpsk_b200.so (include/psk_craft.h).  There is no CPU fallback: if the
+shared library is missing or a CUDA device is absent, the ops raise."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import tables as _tables
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpsk_b200.so")
+
+PSK_OK, PSK_ERR_UNSUPPORTED, PSK_ERR_BADARG, PSK_ERR_CUDA = 0, 1, 2, 3
+FLAG_BAD_ACTION, FLAG_INV_OVERFLOW, FLAG_BAD_LEAF, FLAG_OFF_GRID = 1, 2, 4, 8
+AGENT_BYTES = 32
+AG_X, AG_Y, AG_DIR, AG_TASK, AG_TIMER = 24, 25, 26, 27, 28
+MAX_INV = 24
+
+CRAFT_EXPORTS = (
+    "psk_version", "psk_craft_n_features", "psk_craft_supported", "psk_craft_step",
+    "psk_craft_features", "psk_craft_satisfies", "psk_craft_expert", "psk_craft_find_closest",
+    "psk_craft_reset", "psk_craft_tick",
+)
+
+
+class CraftTablesC(ctypes.Structure):
+    """Mirror of ``psk_craft_tables`` (include/psk_craft.h)."""
+    _fields_ = [
+        ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("n_kinds", ctypes.c_int32),
+        ("window_w", ctypes.c_int32), ("window_h", ctypes.c_int32),
+        ("n_recipes", ctypes.c_int32), ("n_tasks", ctypes.c_int32),
+        ("water_kind", ctypes.c_int32), ("stone_kind", ctypes.c_int32),
+        ("bridge_kind", ctypes.c_int32), ("axe_kind", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("kind_class", ctypes.c_uint8 * 32),
+        ("recipes", ctypes.c_uint8 * (16 * 8)),
+        ("task_len", ctypes.c_uint8 * 32),
+        ("task_nodes", ctypes.c_uint8 * (32 * 16 * 4)),
+    ]
+
+
+class CraftStateC(ctypes.Structure):
+    _fields_ = [("grid", ctypes.c_void_p), ("agent", ctypes.c_void_p), ("n", ctypes.c_int64),
+                ("cell_stride", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class CraftEpisodesC(ctypes.Structure):
+    _fields_ = [("scen_grid", ctypes.c_void_p), ("scen_idx", ctypes.c_void_p),
+                ("init_agent", ctypes.c_void_p)]
+
+
+class PskError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (building nothing: ``__graft_entry__.build()`` does that)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PskError("%s not found — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.psk_version.restype = ctypes.c_char_p
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    tp = ctypes.POINTER(CraftTablesC)
+    lib.psk_craft_n_features.argtypes = [tp]
+    lib.psk_craft_supported.argtypes = [tp]
+    lib.psk_craft_step.argtypes = [tp, CraftStateC, vp, vp, vp, vp, vp]
+    lib.psk_craft_features.argtypes = [tp, CraftStateC, vp, i32, vp]
+    lib.psk_craft_satisfies.argtypes = [tp, CraftStateC, vp, vp, vp]
+    lib.psk_craft_expert.argtypes = [tp, CraftStateC, vp, vp, vp, vp, vp]
+    lib.psk_craft_find_closest.argtypes = [tp, CraftStateC, vp, vp, vp, vp, i32, vp]
+    lib.psk_craft_reset.argtypes = [CraftStateC, CraftEpisodesC, vp, vp]
+    lib.psk_craft_tick.argtypes = [tp, CraftStateC, CraftEpisodesC, vp, vp, vp, vp, vp, vp, vp,
+                                   i32, vp]
+    for name in CRAFT_EXPORTS[1:]:
+        getattr(lib, name).restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc == PSK_OK:
+        return
+    msg = {PSK_ERR_UNSUPPORTED: "unsupported world geometry", PSK_ERR_BADARG: "bad argument",
+           PSK_ERR_CUDA: "CUDA launch failed"}.get(rc, "error %d" % rc)
+    raise PskError("%s: %s" % (what, msg))
+
+
+def make_tables(t):
+    """psketch_b200.tables.CraftTables -> CraftTablesC."""
+    c = CraftTablesC()
+    c.width, c.height, c.n_kinds = t.W, t.H, t.K
+    c.window_w, c.window_h = t.win_w, t.win_h
+    c.n_recipes, c.n_tasks = t.n_recipes, t.n_tasks
+    c.water_kind, c.stone_kind = t.water_kind, t.stone_kind
+    c.bridge_kind, c.axe_kind = t.bridge_kind, t.axe_kind
+    ctypes.memmove(c.kind_class, np.ascontiguousarray(t.kind_class[:32]).ctypes.data, 32)
+    ctypes.memmove(c.recipes, np.ascontiguousarray(t.recipes).ctypes.data, 16 * 8)
+    ctypes.memmove(c.task_len, np.ascontiguousarray(t.task_len[:32]).ctypes.data, 32)
+    ctypes.memmove(c.task_nodes, np.ascontiguousarray(t.task_nodes[:32]).ctypes.data, 32 * 16 * 4)
+    assert _tables.MAX_TASKS == 32 and _tables.MAX_TASK_NODES == 16
+    return c

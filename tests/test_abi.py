@@ -1,0 +1,95 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and
+exports every symbol that include/*.h declares; the host tables match the reference's ids."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    import __graft_entry__ as g
+    return g.build()
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(psk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    headers = [h for h in os.listdir(os.path.join(ROOT, "include")) if h.endswith(".h")]
+    assert "psk_craft.h" in headers
+    n = 0
+    for h in headers:
+        for sym in _declared(h):
+            assert hasattr(lib, sym), "%s declared in %s but not exported" % (sym, h)
+            n += 1
+    assert n >= 10
+    lib.psk_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.psk_version()
+
+
+def test_library_has_sm100a_sass_with_tma(lib_path):
+    out = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out          # TMA bulk store of feature tiles
+    assert ".256" in out            # 256-bit agent-record loads/stores
+
+
+def test_struct_sizes_match_header():
+    from psketch_b200 import _lib
+    assert ctypes.sizeof(_lib.CraftTablesC) == 12 * 4 + 32 + 128 + 32 + 2048
+    assert ctypes.sizeof(_lib.CraftStateC) == 32
+    assert ctypes.sizeof(_lib.CraftEpisodesC) == 24
+
+
+def test_ops_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from psketch_b200 import _lib
+    from psketch_b200.vec import VecCraft
+    with pytest.raises(_lib.PskError):
+        VecCraft(None, 4)
+
+
+def test_tables_match_reference_ids(medium_tables):
+    """Kind ids / classes and task ids (Appendix B)."""
+    cb = medium_tables.cookbook
+    names = ["boundary", "workshop0", "workshop1", "workshop2", "water", "stone", "iron", "grass",
+             "wood", "gold", "gem", "plank", "stick", "axe", "rope", "bed", "shears", "cloth",
+             "bridge", "ladder"]
+    assert [cb.index[n] for n in names] == list(range(1, 21))
+    assert cb.n_kinds == 21 and medium_tables.n_features == 404
+    assert cb.index["none"] is None
+    assert medium_tables.kind_class[:21].tolist() == [0, 1, 2, 2, 2, 3, 4] + [5] * 14
+    rec = medium_tables.recipes[:9]
+    assert rec[:, 0].tolist() == [12, 14, 15, 13, 16, 17, 18, 19, 20]
+    assert rec[:, 1].tolist() == [2, 2, 2, 3, 3, 3, 4, 4, 4]
+    tm = medium_tables.task_manager
+    assert tm["get[wood]"].task_id == 13 and tm["make[shears]"].task_id == 26
+    assert tm["make[bed]"].encoding == [19, 25] and tm["get[iron]"].encoding == [17, 12]
+    assert len(tm.vocab) - 1 == 27
+    # make[bed] flattens to 14 pre-order nodes
+    assert medium_tables.task_len[24] == 14
+
+
+def test_tables_from_reference_yaml_if_present(medium_tables):
+    ref = "/root/reference/resources/craft"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present")
+    from psketch_b200.tables import Cookbook, CraftTables, TaskManager
+    t2 = CraftTables(Cookbook(os.path.join(ref, "recipes.yaml")),
+                     TaskManager(os.path.join(ref, "hints.hierarchy.yaml")))
+    assert np.array_equal(t2.kind_class, medium_tables.kind_class)
+    assert np.array_equal(t2.recipes, medium_tables.recipes)
+    assert np.array_equal(t2.task_nodes, medium_tables.task_nodes)
+    assert np.array_equal(t2.task_len, medium_tables.task_len)

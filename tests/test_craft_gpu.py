@@ -1,0 +1,252 @@
+"""Parity of the CUDA path (through the C ABI of include/psk_craft.h) against the golden
+fixtures exported from the reference and against the CPU oracle.  Bit-exact everywhere:
+features hold small exact integers in f32, everything else is integer/byte state."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+ERR_TYPE = 254
+
+
+def _env_from_states(tables, S, task=None):
+    from psketch_b200.vec import VecCraft
+    return VecCraft.from_states(tables, S["grid"], S["inv"], S["pos"], S["dir"], task=task)
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def _check_states(tables, oracle, S):
+    n = len(S["grid"])
+    C, K = tables.W * tables.H, tables.K
+    env = _env_from_states(tables, S)
+    # ---- features, both store paths
+    ref_f = S["features"].astype(np.float32)
+    for impl in (0, 1):
+        f = env.features(impl=impl)
+        assert f.dtype == torch.float32 and tuple(f.shape) == (n, tables.n_features)
+        assert np.array_equal(_np(f), ref_f), "features impl %d" % impl
+    # ---- step, all six actions
+    snap = env.snapshot()
+    for a in range(6):
+        env.restore(snap)
+        r = env.step(torch.full((n,), a, dtype=torch.uint8))
+        assert float(r.abs().sum()) == 0.0
+        assert np.array_equal(_np(env.cells), S["step_grid"][:, a]), a
+        assert np.array_equal(_np(env.inventory), S["step_inv"][:, a]), a
+        assert np.array_equal(_np(env.pos), S["step_pos"][:, a]), a
+        assert np.array_equal(_np(env.dir), S["step_dir"][:, a]), a
+    env.check_errors()
+    env.restore(snap)
+    # ---- satisfies + expert, every task id
+    inv32 = S["inv"].astype(np.int32)
+    pos32, dir32 = S["pos"].astype(np.int32), S["dir"].astype(np.int32)
+    for tid in range(1, S["satisfies"].shape[1]):
+        tk = torch.full((n,), tid, dtype=torch.uint8)
+        assert np.array_equal(_np(env.satisfies(tk)), S["satisfies"][:, tid]), tid
+        act, dist = env.expert(tk, want_dist=True)
+        act = _np(act)
+        ref = S["expert"][:, tid]
+        raised = ref == ERR_TYPE       # reference: TypeError; defined here as the oracle's answer
+        o_act, o_dist, _ = oracle.expert(S["grid"], inv32, pos32, dir32, np.full(n, tid))
+        assert np.array_equal(act[~raised], ref[~raised]), tid
+        assert np.array_equal(act, o_act.astype(np.uint8)), tid
+        assert np.array_equal(_np(dist).astype(np.int32), o_dist), tid
+    # leaf tasks that are neither use nor go make the reference assert
+    with pytest.raises(AssertionError):
+        env.expert(torch.full((n,), 1, dtype=torch.uint8))
+        env.check_errors()
+    # ---- find_closest_resources
+    for j, kind in enumerate(S["go_kinds"]):
+        goal, length, seq = env.find_closest(torch.full((n,), int(kind), dtype=torch.uint8),
+                                             seq_cap=48)
+        goal, length, seq = _np(goal), _np(length), _np(seq)
+        rst = S["closest_status"][:, j]
+        ok = rst == 0
+        assert np.array_equal(length[ok], S["closest_len"][ok, j])
+        assert np.array_equal(goal[ok], S["closest_goal"][ok, j])
+        assert np.array_equal(seq[ok], S["closest_seq"][ok, j])
+        none = rst == 1
+        assert (length[none] == -1).all()
+        assert np.array_equal(goal[none], S["closest_goal"][none, j])
+        o_goal, o_len, o_st, o_seq = oracle.find_closest(S["grid"], pos32, dir32,
+                                                         np.full(n, kind), seq_cap=48)
+        assert np.array_equal(length.astype(np.int32), o_len)
+        found = o_len >= 0
+        assert np.array_equal(goal[found], o_goal[found].astype(np.uint8))
+        assert np.array_equal(seq[found], o_seq[found])
+
+
+def test_states_medium(medium_tables, medium_oracle, medium_states):
+    _check_states(medium_tables, medium_oracle, medium_states)
+
+
+def test_states_large(large_tables, large_oracle, large_states):
+    _check_states(large_tables, large_oracle, large_states)
+
+
+@pytest.mark.parametrize("split", ["dev", "test", "train"])
+def test_golden_trajectories(split, splits, medium_tables):
+    """Every ref_actions sequence of the reference's dataset, replayed teacher -> step on the
+    GPU for all instances at once (make_data.py:146-152)."""
+    from psketch_b200.vec import VecCraft
+    ref = splits[split + "_ref_actions"]
+    n = len(ref)
+    env = VecCraft.from_instances(medium_tables, splits[split + "_grids"],
+                                  splits[split + "_inst_env"], splits[split + "_inst_pos"],
+                                  splits[split + "_inst_task"])
+    alive = torch.ones(n, dtype=torch.uint8, device=env.device)
+    mism = 0
+    for t in range(ref.shape[1]):
+        act = env.expert()
+        want = torch.from_numpy(ref[:, t]).to(env.device)
+        live = alive.bool()
+        mism += int((act[live] != want[live]).sum())
+        stop = (act == 5) & live
+        if bool(stop.any()):
+            assert bool((env.satisfies()[stop] == 1).all())     # make_data.py:151
+        alive = (live & ~stop).to(torch.uint8)
+        env.step(act, active=alive)
+    assert mism == 0
+    assert int(alive.sum()) == 0
+    env.check_errors()
+
+
+def _oracle_state(env_np, K):
+    return dict(grid=env_np[0], inv=env_np[1], pos=env_np[2], dir=env_np[3], timer=env_np[4])
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_tick_matches_oracle_rollout(fused, splits, medium_tables, medium_oracle):
+    """The rollout tick (trainers/imitation.py:42-73 with auto-reset) against orc_rollout, tick by
+    tick, on the dev split tiled to a size that is not a multiple of any tile."""
+    from psketch_b200.vec import VecCraft
+    reps = 3
+    idx = np.concatenate([np.arange(2200)] * reps)[:6007]
+    grids = splits["dev_grids"]
+    ienv = splits["dev_inst_env"][idx]
+    ipos = splits["dev_inst_pos"][idx]
+    itask = splits["dev_inst_task"][idx]
+    T = 12                                   # short timer so that time-outs occur too
+    env = VecCraft.from_instances(medium_tables, grids, ienv, ipos, itask, max_timesteps=T)
+    init_grid = grids[ienv.astype(np.int64)]
+    state = None
+    tot = np.zeros(4, np.int64)
+    for t in range(45):
+        out = env.tick(fused=fused)
+        state, stats, feats, act = medium_oracle.rollout(
+            1, T, init_grid, ipos.astype(np.int32), itask.astype(np.int32), state=state,
+            want_features=True)
+        tot += stats
+        assert np.array_equal(_np(out["expert"]).astype(np.int32), act), t
+        assert np.array_equal(_np(out["features"]), feats), t
+        assert np.array_equal(_np(env.cells), state["grid"]), t
+        assert np.array_equal(_np(env.inventory).astype(np.int32), state["inv"]), t
+        assert np.array_equal(_np(env.pos).astype(np.int32), state["pos"]), t
+        assert np.array_equal(_np(env.dir).astype(np.int32), state["dir"]), t
+        assert np.array_equal(_np(env.timer).astype(np.int32), state["timer"]), t
+    st = _np(env.stats)
+    assert st[0] == tot[0] and st[1] == tot[1] and st[2] == tot[2]
+    assert st[0] > 0 and st[1] > 0 and st[1] < st[0] or T >= 30
+    env.check_errors()
+
+
+def test_tick_with_student_actions(splits, medium_tables, medium_oracle):
+    """Externally supplied (random) actions instead of the teacher's: DAgger-style rollout."""
+    from psketch_b200.vec import VecCraft
+    n = 4099
+    rng = np.random.RandomState(5)
+    idx = rng.randint(0, 2200, size=n)
+    grids = splits["test_grids"]
+    ienv, ipos, itask = (splits["test_inst_env"][idx], splits["test_inst_pos"][idx],
+                         splits["test_inst_task"][idx])
+    env = VecCraft.from_instances(medium_tables, grids, ienv, ipos, itask, max_timesteps=40)
+    o = medium_oracle
+    grid = grids[ienv.astype(np.int64)].copy()
+    init_grid = grid.copy()
+    inv = np.zeros((n, 21), np.int32)
+    pos = ipos.astype(np.int32).copy()
+    dirs = np.zeros(n, np.int32)
+    timer = np.full(n, 40, np.int32)
+    task = itask.astype(np.int32)
+    for t in range(60):
+        a = rng.choice(6, size=n, p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8)
+        out = env.tick(actions=torch.from_numpy(a), fused=bool(t % 2))
+        ref_act, _, _ = o.expert(grid, inv, pos, dirs, task)
+        assert np.array_equal(_np(out["expert"]).astype(np.int32), ref_act)
+        assert np.array_equal(_np(out["features"]), o.features(grid, inv, pos, dirs))
+        timer -= 1
+        done = (a == 5) | (timer <= 0)
+        succ = (o.satisfies(grid, inv, pos, dirs, task) == 1) & done
+        g2, i2, p2, d2, _ = o.step(grid, inv, pos, dirs, a.astype(np.int32))
+        grid = np.where(done[:, None], init_grid, g2)
+        inv = np.where(done[:, None], 0, i2)
+        pos = np.where(done[:, None], ipos.astype(np.int32), p2)
+        dirs = np.where(done, 0, d2)
+        timer = np.where(done, 40, timer)
+        assert np.array_equal(_np(out["done"]).astype(bool), done)
+        assert np.array_equal(_np(out["success"]).astype(bool), succ)
+        assert np.array_equal(_np(env.cells), grid)
+        assert np.array_equal(_np(env.inventory).astype(np.int32), inv)
+        assert np.array_equal(_np(env.pos).astype(np.int32), pos)
+    env.check_errors()
+
+
+def test_bad_action_raises(medium_tables, medium_states):
+    S = {k: medium_states[k][:64] for k in ("grid", "inv", "pos", "dir")}
+    env = _env_from_states(medium_tables, S)
+    before = env.snapshot()
+    env.step(torch.full((64,), 6, dtype=torch.uint8))
+    with pytest.raises(Exception, match="Unexpected action"):
+        env.check_errors()
+    assert torch.equal(env.grid, before[0]) and torch.equal(env.agent, before[1])
+
+
+@pytest.mark.parametrize("n", [0, 1, 15, 17, 129])
+def test_ragged_sizes(n, medium_tables, medium_oracle, medium_states):
+    S = {k: medium_states[k][:n] for k in ("grid", "inv", "pos", "dir", "features")}
+    env = _env_from_states(medium_tables, S)
+    f = env.features()
+    assert tuple(f.shape) == (n, 404)
+    assert np.array_equal(_np(f), S["features"].astype(np.float32))
+    if n:
+        a = env.expert(torch.full((n,), 24, dtype=torch.uint8))
+        o, _, _ = medium_oracle.expert(S["grid"], S["inv"].astype(np.int32),
+                                       S["pos"].astype(np.int32), S["dir"].astype(np.int32),
+                                       np.full(n, 24))
+        assert np.array_equal(_np(a).astype(np.int32), o)
+
+
+def test_full_size_properties(splits, medium_tables, medium_oracle):
+    """BASELINE config 2 size (65,536 envs from the train split): the whole batch against the
+    oracle for a few ticks, then size-independent properties over a long rollout: every
+    teacher-driven episode succeeds, and the episode/step counters add up."""
+    from psketch_b200.vec import VecCraft
+    n = 65536
+    idx = np.arange(n) % 17600
+    grids = splits["train_grids"]
+    ienv, ipos, itask = (splits["train_inst_env"][idx], splits["train_inst_pos"][idx],
+                         splits["train_inst_task"][idx])
+    env = VecCraft.from_instances(medium_tables, grids, ienv, ipos, itask, max_timesteps=40)
+    init_grid = grids[ienv.astype(np.int64)]
+    state = None
+    for t in range(6):
+        out = env.tick(fused=True)
+        state, _, feats, act = medium_oracle.rollout(1, 40, init_grid, ipos.astype(np.int32),
+                                                     itask.astype(np.int32), state=state,
+                                                     want_features=True)
+        assert np.array_equal(_np(out["expert"]).astype(np.int32), act)
+        assert np.array_equal(_np(out["features"]), feats)
+    for t in range(94):
+        env.tick(fused=True, want_features=False)
+    st = _np(env.stats)
+    assert st[2] == 100 * n
+    assert st[0] == st[1] and st[0] > 0          # teacher rollouts always succeed
+    # expected number of finished episodes: ticks / golden length per instance
+    ref_len = splits["train_ref_len"][idx].astype(np.int64)
+    assert st[0] == int((100 // ref_len).sum())
+    env.check_errors()
