@@ -326,7 +326,7 @@ def run_ours(args):
         return g
 
     snap = env.snapshot()
-    for name, fn, b in (("features_tma", f_feat(0), BYTES_FEATURES), ("features_plain", f_feat(1), BYTES_FEATURES),
+    for name, fn, b in (("features_tma", f_feat(2), BYTES_FEATURES), ("features_plain", f_feat(1), BYTES_FEATURES),
                         ("expert", lambda: env.expert(out=act), BYTES_EXPERT),
                         ("step", lambda: env.step(act), BYTES_STEP)):
         dt = time_kernel(fn, it, torch)

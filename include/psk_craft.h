@@ -104,7 +104,8 @@ int psk_craft_step(const psk_craft_tables *t, psk_craft_state s, const uint8_t *
                    const uint8_t *active, float *reward, int32_t *err_flags, void *stream);
 
 /* CraftState.features (worlds/craft.py:296-330) as float32 (students/imitation.py:72-73):
- * out f32[n][n_features].  impl: 0 = default (TMA bulk-store tiles), 1 = plain vector stores. */
+ * out f32[n][n_features].  impl: 0 = default, 1 = shared-memory tile + 128-bit vector stores,
+ * 2 = shared-memory tile + TMA bulk stores (cp.async.bulk). */
 int psk_craft_features(const psk_craft_tables *t, psk_craft_state s, float *out, int impl,
                        void *stream);
 

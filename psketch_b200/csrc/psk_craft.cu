@@ -12,6 +12,7 @@
 //   craft_advance_kernel   rollout bookkeeping (timer / done / success / auto-reset) + step.
 //   craft_tick_kernel      expert + features + advance fused: state read once per tick.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "psk_common.cuh"
@@ -21,16 +22,17 @@ namespace psk {
 // =============================================================================================
 // step  (worlds/craft.py:332-424)
 // =============================================================================================
-// Applies `act` to the agent record `a` and the env's grid row (global or shared memory).
-// Returns true when the grid row was modified.  flags collects PSK_FLAG_* bits.
+// Applies `act` to the agent record `a` and the env's grid row.  Cells are read through `rd`
+// (global memory, or a shared-memory copy of the row) and cleared through `row` (global).
+// flags collects PSK_FLAG_* bits.
 template <int W, int H>
-__device__ __forceinline__ void step_env(const SharedTables &st, Agent &a, uint8_t *row, int act,
-                                         uint32_t &flags) {
+__device__ __forceinline__ void step_env(const SharedTables &st, Agent &a, uint8_t *row,
+                                         const uint8_t *rd, int act, uint32_t &flags) {
     int x = a.x(), y = a.y(), dir = a.dir();
     if (act < 4) {  // craft.py:341-352 + 418-421: turn always, move iff the target cell is free
         dir = act;
         const int tx = x + dx_of(act), ty = y + dy_of(act);
-        if (tx >= 0 && ty >= 0 && tx < W && ty < H && row[tx * H + ty] == 0) {
+        if (tx >= 0 && ty >= 0 && tx < W && ty < H && rd[tx * H + ty] == 0) {
             x = tx;
             y = ty;
         }
@@ -38,7 +40,7 @@ __device__ __forceinline__ void step_env(const SharedTables &st, Agent &a, uint8
     } else if (act == PSK_ACT_USE) {  // craft.py:356-412
         const int fx = x + dx_of(dir), fy = y + dy_of(dir);
         if (fx >= 0 && fy >= 0 && fx < W && fy < H) {  // neighbors(), craft.py:426-437
-            const int thing = row[fx * H + fy];
+            const int thing = rd[fx * H + fy];
             const int cls = st.kind_class(thing);
             const psk_craft_tables &T = st.t();
             if (cls == KC_GRAB) {  // craft.py:383-386
@@ -90,7 +92,7 @@ craft_step_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__restric
         if (active && !active[e]) continue;
         Agent a = load_agent(agent, e);
         const Agent before = a;
-        step_env<W, H>(st, a, grid + e * cell_stride, action[e], flags);
+        step_env<W, H>(st, a, grid + e * cell_stride, grid + e * cell_stride, action[e], flags);
         bool changed = false;
 #pragma unroll
         for (int i = 0; i < 8; i++) changed |= a.w[i] != before.w[i];
@@ -116,18 +118,23 @@ __device__ __forceinline__ int node_satisfied(uint32_t nd, const Agent &a, int f
     return 2;  // None
 }
 
-// first incomplete leaf of `task` (node word), or 0 when there is none (-> STOP)
+// first incomplete leaf of `task` (node word), or 0 when there is none (-> STOP).
+// WARP-CONVERGENT: all 32 lanes call it together; the loop runs in lock-step (vote) so that the
+// lanes are converged again when it ends, whatever their individual trip counts were.
 __device__ __forceinline__ uint32_t find_incomplete(const SharedTables &st, int task,
                                                     const Agent &a, int facing) {
     const int n = st.task_len(task);
     int i = 0;
-    while (i < n) {
-        const uint32_t nd = st.node(task, i);
-        if (node_satisfied(nd, a, facing) == 1) i = nd >> 24;
-        else if ((nd >> 16) & 0xFF) return nd | 0x80000000u;  // leaf (bit 31 marks "found")
-        else i++;
+    uint32_t leaf = 0;
+    while (__any_sync(0xffffffffu, i < n && !leaf)) {
+        if (i < n && !leaf) {
+            const uint32_t nd = st.node(task, i);
+            if (node_satisfied(nd, a, facing) == 1) i = nd >> 24;
+            else if ((nd >> 16) & 0xFF) leaf = nd | 0x80000000u;  // bit 31 marks "found"
+            else i++;
+        }
     }
-    return 0;
+    return leaf;
 }
 
 template <int W, int H>
@@ -152,101 +159,116 @@ craft_satisfies_kernel(const __grid_constant__ psk_craft_tables T,
 // =============================================================================================
 // The reference runs one FIFO BFS per goal cell over states (pos, dir), expanding DOWN, UP,
 // LEFT, RIGHT, keeps the strictly shortest path (first goal cell in x-major order wins ties) and
-// returns its first action.  Because the successor of (p, d) under action a is (p', a) with p'
-// independent of d, and because the FIFO tree path of a node is the lexicographically smallest
-// shortest path to it, the answer has an order-independent form that maps onto bitboards:
-//   * one level-synchronous BFS; V[a] = visited positions with dir a;
-//   * P[f] = frontier positions that some shortest path starting with action f reaches;
-//   * the first level L at which a new state faces a goal cell gives the distance; the goal is
-//     the lowest-index goal cell hit at L; the action is the smallest f whose colour faces it.
+// returns its first action.  Order-independent form used here (proved in DESIGN.md §BFS, checked
+// against the literal queue of oracle/craft_oracle.c on every golden state):
+//   * the successor of (p, d) under action a is (p', a), p' independent of d, so every state on
+//     a shortest path except the last is entered by a successful move: its depth is the plain
+//     4-neighbour distance dpos() of its position;
+//   * a state facing goal cell g with direction d is entered either by turning in place at
+//     q = g - delta(d) (action d is blocked by g) or by moving from q = g - 2*delta(d) into
+//     g - delta(d); both cost dpos(q) + 1.  Call such q a "source" of g for direction d;
+//   * the FIFO tree path of a node is the lexicographically smallest shortest path to it, so
+//     the teacher's action is the smallest first action over all shortest paths to sources of
+//     the chosen goal cell.
+// So: a colourless forward flood from the agent until the flooded set touches a source gives
+// the length D and (lowest bit) the goal cell; a backward flood of D-2 levels from that cell's
+// sources tells which neighbours of the agent lie on a shortest path; the action is the
+// smallest such direction.  Two floods of ~20 instructions per level on 64/128-bit boards.
 // Returns the path length (-1: unreachable); first (0..3) is valid when the length is > 0.
 template <int W, int H>
-__device__ __forceinline__ int bfs_first_action(typename Board<W, H>::BT occ,
+__device__ __forceinline__ typename Board<W, H>::BT spread(typename Board<W, H>::BT v) {
+    using B = Board<W, H>;
+    return B::template shift<0>(v) | B::template shift<1>(v) | B::template shift<2>(v) |
+           B::template shift<3>(v);
+}
+
+// WARP-CONVERGENT: all 32 lanes call it together (lanes without a search pass need = false).
+// Both floods run in lock-step under a warp vote, so the straight-line code after each loop is
+// executed once per warp instead of once per distinct trip count.
+template <int W, int H>
+__device__ __forceinline__ int bfs_first_action(bool need, typename Board<W, H>::BT occ,
                                                 typename Board<W, H>::BT goal, int x, int y,
                                                 int d0, int &first, int &goal_idx) {
     using B = Board<W, H>;
     using BT = typename B::BT;
+    constexpr unsigned FULL = 0xffffffffu;
     const BT freeb = ~occ & B::all();
-    // cm[a]: positions whose a-neighbour is on the grid and free (the agent moves);
-    // T[a]:  positions whose a-neighbour is a goal cell (facing the goal with dir a).
-    const BT cm[4] = {B::template unshift<0>(freeb), B::template unshift<1>(freeb),
-                      B::template unshift<2>(freeb), B::template unshift<3>(freeb)};
-    const BT Tg[4] = {B::template unshift<0>(goal), B::template unshift<1>(goal),
-                      B::template unshift<2>(goal), B::template unshift<3>(goal)};
     const BT root = B::bit(x * H + y);
-    BT V[4];
-#pragma unroll
-    for (int a = 0; a < 4; a++) V[a] = (a == d0) ? root : BT(0);
     first = -1;
     goal_idx = -1;
-    {  // level 0: already facing a goal cell (teachers/base.py:57-66 on the first dequeue)
-        BT t = 0;
-#pragma unroll
-        for (int a = 0; a < 4; a++) t |= (a == d0) ? (Tg[a] & root) : BT(0);
-        if (t) {
-            goal_idx = (x + dx_of(d0)) * H + (y + dy_of(d0));
-            return 0;
+    bool face0 = false;
+    {  // depth 0: already facing a goal cell (teachers/base.py:57-66 on the first dequeue)
+        const int fx = x + dx_of(d0), fy = y + dy_of(d0);
+        if (need && fx >= 0 && fy >= 0 && fx < W && fy < H && ((goal >> (fx * H + fy)) & 1)) {
+            face0 = true;
+            goal_idx = fx * H + fy;
         }
     }
-    BT P[4] = {root, root, root, root};
-    bool first_level = true;
-    for (int level = 1; level <= 4 * W * H + 1; level++) {
-        BT nP[4] = {0, 0, 0, 0}, nV[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int f = 0; f < 4; f++) {
-            const BT p = P[f];
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                BT c;
-                if (a == 0) c = B::template shift<0>(p & cm[0]) | (p & ~cm[0]);
-                else if (a == 1) c = B::template shift<1>(p & cm[1]) | (p & ~cm[1]);
-                else if (a == 2) c = B::template shift<2>(p & cm[2]) | (p & ~cm[2]);
-                else c = B::template shift<3>(p & cm[3]) | (p & ~cm[3]);
-                BT nw = c & ~V[a];
-                if (first_level && a != f) nw = 0;  // at depth 1 colour f is exactly action f
-                nP[f] |= nw;
-                nV[a] |= nw;
-            }
+    // T[d]: positions whose d-neighbour is a goal cell
+    const BT T0 = B::template unshift<0>(goal), T1 = B::template unshift<1>(goal),
+             T2 = B::template unshift<2>(goal), T3 = B::template unshift<3>(goal);
+    const BT src_all = T0 | T1 | T2 | T3 |
+                       (B::template unshift<0>(freeb & T0)) | (B::template unshift<1>(freeb & T1)) |
+                       (B::template unshift<2>(freeb & T2)) | (B::template unshift<3>(freeb & T3));
+    // forward flood: VF = positions within k moves of the agent
+    const bool run = need && !face0 && goal != 0;
+    BT VF = root;
+    int k = 0;
+    bool h;
+    while (true) {
+        h = (VF & src_all) != 0;
+        const BT nv = VF | (spread<W, H>(VF) & freeb);
+        const bool go = run && !h && nv != VF && k < W * H;  // nv == VF: queue drained (base.py:87)
+        if (!__any_sync(FULL, go)) break;
+        if (go) {
+            VF = nv;
+            k++;
         }
-        // goal cells faced by a new state of this level
-        const BT hit = B::template shift<0>(nV[0] & Tg[0]) | B::template shift<1>(nV[1] & Tg[1]) |
-                       B::template shift<2>(nV[2] & Tg[2]) | B::template shift<3>(nV[3] & Tg[3]);
-        if (hit) {
-            goal_idx = B::lowest(hit);
-            const BT g = B::bit(goal_idx);
-            const BT tg[4] = {B::template unshift<0>(g), B::template unshift<1>(g),
-                              B::template unshift<2>(g), B::template unshift<3>(g)};
-#pragma unroll
-            for (int f = 3; f >= 0; f--) {  // descending, so the smallest f is written last
-                const BT p = P[f];
-                BT faced = 0;
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    BT c;
-                    if (a == 0) c = B::template shift<0>(p & cm[0]) | (p & ~cm[0]);
-                    else if (a == 1) c = B::template shift<1>(p & cm[1]) | (p & ~cm[1]);
-                    else if (a == 2) c = B::template shift<2>(p & cm[2]) | (p & ~cm[2]);
-                    else c = B::template shift<3>(p & cm[3]) | (p & ~cm[3]);
-                    BT nw = c & ~V[a];
-                    if (first_level && a != f) nw = 0;
-                    faced |= nw & tg[a];
-                }
-                if (faced) first = f;
-            }
-            return level;
-        }
-        if (!(nV[0] | nV[1] | nV[2] | nV[3])) return -1;  // queue drained (base.py:87)
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            V[a] |= nV[a];
-            P[a] = nP[a];
-        }
-        first_level = false;
     }
-    return -1;
+    const bool reached = run && h;
+    // goal cells faced at depth k+1: by a turn at a flooded cell, or one move further
+    const BT hit = B::template shift<0>(VF & T0) | B::template shift<1>(VF & T1) |
+                   B::template shift<2>(VF & T2) | B::template shift<3>(VF & T3) |
+                   B::template shift<0>(B::template shift<0>(VF) & freeb & T0) |
+                   B::template shift<1>(B::template shift<1>(VF) & freeb & T1) |
+                   B::template shift<2>(B::template shift<2>(VF) & freeb & T2) |
+                   B::template shift<3>(B::template shift<3>(VF) & freeb & T3);
+    const BT hg = hit & goal;
+    const int gi = hg ? B::lowest(hg) : 0;
+    const BT g = B::bit(gi);
+    // sources of the chosen goal cell, per final action d
+    const BT g0 = B::template unshift<0>(g), g1 = B::template unshift<1>(g),
+             g2 = B::template unshift<2>(g), g3 = B::template unshift<3>(g);
+    const BT s0 = g0 | B::template unshift<0>(freeb & g0), s1 = g1 | B::template unshift<1>(freeb & g1),
+             s2 = g2 | B::template unshift<2>(freeb & g2), s3 = g3 | B::template unshift<3>(freeb & g3);
+    // backward flood over free cells: VB = cells within k-1 moves of a source (sources lie at
+    // forward depth exactly k, otherwise the forward flood had stopped earlier)
+    BT VB = (s0 | s1 | s2 | s3) & VF;
+    const int kmax = __reduce_max_sync(FULL, reached ? k : 0);
+    for (int j = 1; j < kmax; j++) {
+        const BT nb = VB | (spread<W, H>(VB) & freeb);
+        if (j < k) VB = nb;
+    }
+    if (face0) return 0;
+    if (!reached) return -1;
+    goal_idx = gi;
+    if (k == 0) {  // the agent's own cell is the source: one action
+        first = (root & s0) ? 0 : (root & s1) ? 1 : (root & s2) ? 2 : 3;
+        return 1;
+    }
+    const BT ok = VB & freeb;
+    first = (B::template shift<0>(root) & ok) ? 0
+          : (B::template shift<1>(root) & ok) ? 1
+          : (B::template shift<2>(root) & ok) ? 2 : 3;
+    return k + 1;
 }
 
-// occupancy / goal bitboards from one env's grid row (any address space), CP = padded cells
+// occupancy / goal bitboards from one env's grid row held in registers.
+// Per 4-cell word: bit 7 of every non-zero byte via ((w & 0x7f..) + 0x7f..) | w, the four flag
+// bits gathered into a nibble by one multiply (0x00204081 moves bits 7,15,23,31 to 28..31).
+__device__ __forceinline__ uint32_t nonzero_flags(uint32_t w) {
+    return (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+}
 template <int W, int H>
 __device__ __forceinline__ void build_boards(const uint32_t *row_words, int goal_kind,
                                              typename Board<W, H>::BT &occ,
@@ -254,13 +276,24 @@ __device__ __forceinline__ void build_boards(const uint32_t *row_words, int goal
     using BT = typename Board<W, H>::BT;
     constexpr int NW = (W * H + 3) / 4;
     const uint32_t gk = uint32_t(goal_kind) * 0x01010101u;
-    occ = 0;
-    goal = 0;
+    uint32_t o[(NW + 7) / 8], q[(NW + 7) / 8];
+#pragma unroll
+    for (int i = 0; i < (NW + 7) / 8; i++) o[i] = q[i] = 0;
 #pragma unroll
     for (int i = 0; i < NW; i++) {
         const uint32_t w = row_words[i];
-        occ |= BT(mask_nibble(__vcmpne4(w, 0u))) << (4 * i);
-        goal |= BT(mask_nibble(__vcmpeq4(w, gk))) << (4 * i);
+        const uint32_t nz = nonzero_flags(w);
+        const uint32_t eq = nonzero_flags(w ^ gk) ^ 0x80808080u;
+        const int sh = 4 * (i & 7);
+        o[i >> 3] |= ((nz * 0x00204081u) >> 28) << sh;
+        q[i >> 3] |= ((eq * 0x00204081u) >> 28) << sh;
+    }
+    occ = 0;
+    goal = 0;
+#pragma unroll
+    for (int i = 0; i < (NW + 7) / 8; i++) {
+        occ |= BT(o[i]) << (32 * i);
+        goal |= BT(q[i]) << (32 * i);
     }
     occ &= Board<W, H>::all();
     goal &= Board<W, H>::all();
@@ -281,24 +314,26 @@ __device__ __forceinline__ void load_row(const uint8_t *row, uint32_t *words) {
 }
 
 // Teacher action for one env.  row_words: the env's grid row in registers.
+// WARP-CONVERGENT (see find_incomplete / bfs_first_action): called by all 32 lanes.
 template <int W, int H>
 __device__ __forceinline__ int expert_env(const SharedTables &st, const Agent &a, int task,
                                           const uint32_t *row_words, int facing, int &dist,
                                           uint32_t &flags) {
-    dist = -1;
     const uint32_t leaf = find_incomplete(st, task, a, facing);
-    if (!leaf) return PSK_ACT_STOP;                         // demonstration.py:15-16
     const int kind = (leaf >> 16) & 0x7F;
+    const bool need = leaf && kind == LEAF_GO;
+    typename Board<W, H>::BT occ, goal;
+    build_boards<W, H>(row_words, need ? (leaf >> 8) & 0xFF : 0, occ, goal);
+    int first, gidx;
+    const int d = bfs_first_action<W, H>(need, occ, goal, a.x(), a.y(), a.dir(), first, gidx);
+    dist = need ? d : -1;
+    if (!leaf) return PSK_ACT_STOP;                         // demonstration.py:15-16
     if (kind == LEAF_USE) return PSK_ACT_USE;               // demonstration.py:20-21
     if (kind != LEAF_GO) {                                  // demonstration.py:18 (assert)
         flags |= PSK_FLAG_BAD_LEAF;
         return PSK_ACT_INVALID;
     }
-    typename Board<W, H>::BT occ, goal;
-    build_boards<W, H>(row_words, (leaf >> 8) & 0xFF, occ, goal);
-    int first, gidx;
-    dist = bfs_first_action<W, H>(occ, goal, a.x(), a.y(), a.dir(), first, gidx);
-    if (dist < 0) return PSK_ACT_STOP;                      // demonstration.py:25-26
+    if (d < 0) return PSK_ACT_STOP;                         // demonstration.py:25-26
     return first >= 0 ? first : PSK_ACT_INVALID;
 }
 
@@ -312,8 +347,12 @@ craft_expert_kernel(const __grid_constant__ psk_craft_tables T, const uint8_t *_
     stage_tables(st, T);
     constexpr int NW4 = (W * H + 15) / 16;
     uint32_t flags = 0;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
-         e += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    // whole warps iterate (base is warp-uniform); lanes past the end replay env n-1, unsaved
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < n;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const bool valid = base + lane < n;
+        const int64_t e = valid ? base + lane : n - 1;
         const Agent a = load_agent_ro(agent, e);
         const uint8_t *row = grid + e * cell_stride;
         uint32_t words[NW4 * 4];
@@ -321,9 +360,13 @@ craft_expert_kernel(const __grid_constant__ psk_craft_tables T, const uint8_t *_
         const int tk = task ? task[e] : a.task();
         const int facing = facing_kind<W, H>(a, row);
         int dist;
-        const int act = expert_env<W, H>(st, a, tk, words, facing, dist, flags);
-        action[e] = (uint8_t)act;
-        if (dist_out) dist_out[e] = (int16_t)dist;
+        uint32_t fl = 0;
+        const int act = expert_env<W, H>(st, a, tk, words, facing, dist, fl);
+        if (valid) {
+            flags |= fl;
+            action[e] = (uint8_t)act;
+            if (dist_out) dist_out[e] = (int16_t)dist;
+        }
     }
     if (flags && err_flags) atomicOr(err_flags, (int)flags);
 }
@@ -341,8 +384,11 @@ craft_find_closest_kernel(const __grid_constant__ psk_craft_tables T,
     using B = Board<W, H>;
     using BT = typename B::BT;
     constexpr int NW4 = (W * H + 15) / 16;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
-         e += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < n;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const bool valid = base + lane < n;
+        const int64_t e = valid ? base + lane : n - 1;
         const Agent a = load_agent_ro(agent, e);
         uint32_t words[NW4 * 4];
         load_row<NW4>(grid + e * cell_stride, words);
@@ -350,41 +396,43 @@ craft_find_closest_kernel(const __grid_constant__ psk_craft_tables T,
         build_boards<W, H>(words, kind[e], occ, goal);
         int first, gidx;
         int x = a.x(), y = a.y(), d = a.dir();
-        const int len = bfs_first_action<W, H>(occ, goal, x, y, d, first, gidx);
-        len_out[e] = (int16_t)len;
-        if (len < 0) {
-            // best_goal keeps the LAST goal cell scanned when none is reachable (base.py:31)
-            int last = -1;
-            if (goal) {
+        const int len = bfs_first_action<W, H>(true, occ, goal, x, y, d, first, gidx);
+        if (valid) {
+            len_out[e] = (int16_t)len;
+            if (len < 0) {
+                // best_goal keeps the LAST goal cell scanned when none is reachable (base.py:31)
+                int last = -1;
                 BT g = goal;
                 while (g) { last = B::lowest(g); g &= g - 1; }
+                goal_out[2 * e] = last < 0 ? 255 : last / H;
+                goal_out[2 * e + 1] = last < 0 ? 255 : last % H;
+            } else {
+                goal_out[2 * e] = gidx / H;
+                goal_out[2 * e + 1] = gidx % H;
             }
-            goal_out[2 * e] = last < 0 ? 255 : last / H;
-            goal_out[2 * e + 1] = last < 0 ? 255 : last % H;
-        } else {
-            goal_out[2 * e] = gidx / H;
-            goal_out[2 * e + 1] = gidx % H;
         }
         if (seq) {
+            // replay: apply the action, search again towards the chosen cell (lock-step)
             uint8_t *sq = seq + e * (int64_t)seq_cap;
-            int k = 0;
-            if (len > 0) {
-                const BT g1 = B::bit(gidx);
-                int f = first;
-                for (; k < len && k < seq_cap; k++) {
-                    sq[k] = (uint8_t)f;
+            const BT g1 = len > 0 ? B::bit(gidx) : BT(0);
+            const int lmax = __reduce_max_sync(0xffffffffu, len > 0 ? len : 0);
+            int f = first;
+            for (int k = 0; k < lmax; k++) {
+                const bool on = k < len;
+                if (on) {
+                    if (valid && k < seq_cap) sq[k] = (uint8_t)f;
                     const int tx = x + dx_of(f), ty = y + dy_of(f);
                     const bool can = tx >= 0 && ty >= 0 && tx < W && ty < H &&
                                      !((occ >> (tx * H + ty)) & 1);
                     if (can) { x = tx; y = ty; }
                     d = f;
-                    if (k + 1 < len) {
-                        int g2;
-                        bfs_first_action<W, H>(occ, g1, x, y, d, f, g2);
-                    }
                 }
+                int f2, g2;
+                bfs_first_action<W, H>(on && k + 1 < len, occ, g1, x, y, d, f2, g2);
+                if (on && k + 1 < len) f = f2;
             }
-            for (; k < seq_cap; k++) sq[k] = 255;
+            if (valid)
+                for (int k = len > 0 ? len : 0; k < seq_cap; k++) sq[k] = 255;
         }
     }
 }
@@ -392,51 +440,99 @@ craft_find_closest_kernel(const __grid_constant__ psk_craft_tables T,
 // =============================================================================================
 // features  (worlds/craft.py:296-330)
 // =============================================================================================
-// Scatter of one env's non-zero features into its f32 row `frow` (shared memory), done by the
-// TPE threads of the env; thread `j` owns cells [j*CPT, (j+1)*CPT) of the padded grid row.
+// Shared-space stores by 32-bit address (no generic-address conversion in the hot loop).
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_zero16(uint32_t addr) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0) : "memory");
+}
+
+// The grid-row bytes one feature thread owns: NCH chunks of 8 consecutive cells.
+template <int W, int H, int TPE> struct RowChunks {
+    static constexpr int CP = ((W * H + 63) / 64) * 64;
+    static constexpr int NCH = CP / (8 * TPE);
+    uint2 v[NCH];
+    // thread j of the env reads cells [j*NCH*8, (j+1)*NCH*8) (global or shared, 8-byte aligned)
+    __device__ __forceinline__ void load(const uint8_t *row, int j) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+            v[c] = *reinterpret_cast<const uint2 *>(row + (j * NCH + c) * 8);
+    }
+};
+
+// Scatter of one env's non-zero features into its f32 row at shared address `frow_s`, done by
+// the TPE threads of the env; thread j owns the cells in `cells`.  K is the number of kinds.
+// The centre block of the pooled WIN^2 x WIN^2 window is exactly the local WIN x WIN window
+// (bhw = hw*WIN + hw), so one pass over the cells writes both feature groups.
 template <int W, int H, int WIN, int TPE>
-__device__ __forceinline__ void scatter_features(float *frow, const uint8_t *row, int cell_stride,
+__device__ __forceinline__ void scatter_features(uint32_t frow_s, const RowChunks<W, H, TPE> &cells,
                                                  const Agent &a, int K, int j) {
     constexpr int HW = WIN / 2, BHW = (WIN * WIN) / 2;  // craft.py:299-302
+    constexpr int WW = WIN * WIN;
+    constexpr int NCH = RowChunks<W, H, TPE>::NCH;
     const int px = a.x(), py = a.y();
-    const int cpt = cell_stride / TPE;                  // multiple of 8 (cell_stride % 64 == 0)
-    const int c0 = j * cpt;
-    for (int cb = 0; cb < cpt; cb += 8) {
-        const uint2 v = *reinterpret_cast<const uint2 *>(row + c0 + cb);
-        if ((v.x | v.y) == 0) continue;
+    const int K4 = K * 4;
+    const uint32_t big_s = frow_s + WW * K4;
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
-            const int k = ((b < 4 ? v.x : v.y) >> ((b & 3) * 8)) & 0xFF;
-            const int c = c0 + cb + b;
-            if (k == 0 || c >= W * H) continue;
-            const int dx = c / H - px, dy = c % H - py;
-            // local window, ravel order (dx, dy, kind)  (craft.py:304-305)
-            if (dx >= -HW && dx <= HW && dy >= -HW && dy <= HW)
-                frow[((dx + HW) * WIN + (dy + HW)) * K + k] = 1.0f;
-            // WIN^2 x WIN^2 window max-pooled in WIN x WIN blocks  (craft.py:306-310)
-            const int bx = dx + BHW, by = dy + BHW;
-            if (bx >= 0 && bx < WIN * WIN && by >= 0 && by < WIN * WIN)
-                frow[WIN * WIN * K + ((bx / WIN) * WIN + (by / WIN)) * K + k] = 1.0f;
+    for (int ch = 0; ch < NCH; ch++) {
+        const int cc = (j * NCH + ch) * 8;
+        const uint2 v = cells.v[ch];
+        if (cc >= W * H || (v.x | v.y) == 0) continue;
+        if (H % 8 == 0) {
+            // the 8 cells share one column x; y = y0 + b
+            const int x = cc / H, y0 = cc % H;
+            const int bx = x - px + BHW;
+            const bool bx_ok = (unsigned)bx < (unsigned)WW;
+            const int bi = bx / WIN;
+            const uint32_t big_col = big_s + bi * (WIN * K4);
+            const bool centre_col = bi == HW;
+            const uint32_t loc_col = frow_s + (bx - HW * WIN) * (WIN * K4) - HW * WIN * K4;
+            const int by0 = y0 - py + BHW;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const int k = ((b < 4 ? v.x : v.y) >> ((b & 3) * 8)) & 0xFF;
+                const int by = by0 + b;
+                const bool ok = bx_ok && (unsigned)by < (unsigned)WW && k != 0;
+                const int bj = by / WIN;
+                // pooled window, block (bi, bj)  (craft.py:306-310)
+                if (ok) sts_f32(big_col + bj * K4 + k * 4, 1.0f);
+                // local window, ravel order (dx, dy, kind)  (craft.py:304-305)
+                if (ok && centre_col && bj == HW) sts_f32(loc_col + by * K4 + k * 4, 1.0f);
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const int k = ((b < 4 ? v.x : v.y) >> ((b & 3) * 8)) & 0xFF;
+                const int c = cc + b;
+                if (k == 0 || c >= W * H) continue;
+                const int dx = c / H - px, dy = c % H - py;
+                if ((unsigned)(dx + HW) < (unsigned)WIN && (unsigned)(dy + HW) < (unsigned)WIN)
+                    sts_f32(frow_s + (((dx + HW) * WIN + (dy + HW)) * K + k) * 4, 1.0f);
+                const int bx = dx + BHW, by = dy + BHW;
+                if ((unsigned)bx < (unsigned)WW && (unsigned)by < (unsigned)WW)
+                    sts_f32(big_s + (((bx / WIN) * WIN + (by / WIN)) * K + k) * 4, 1.0f);
+            }
         }
     }
     // inventory counts (craft.py:325): thread j converts inventory word j (4 kinds)
-    float *tail = frow + 2 * WIN * WIN * K;
+    const uint32_t tail_s = frow_s + 2 * WW * K4;
     for (int wi = j; wi < 6; wi += TPE) {
         const uint32_t w = a.inv_word(wi);
         if (w == 0) continue;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int cnt = (w >> (8 * b)) & 0xFF;
-            if (cnt && wi * 4 + b < K) tail[wi * 4 + b] = (float)cnt;
+            if (cnt && wi * 4 + b < K) sts_f32(tail_s + (wi * 4 + b) * 4, (float)cnt);
         }
     }
-    if (j == TPE - 1) tail[K + a.dir()] = 1.0f;  // craft.py:321-322; the final element stays 0
+    if (j == TPE - 1) sts_f32(tail_s + (K + a.dir()) * 4, 1.0f);  // craft.py:321-322; last stays 0
 }
 
 // TMA helpers (cp.async.bulk, shared::cta -> global)
-__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-                 "r"(smem_u32(ssrc)), "r"(bytes)
+                 "r"(ssrc), "r"(bytes)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -447,59 +543,104 @@ __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// E envs per tile, TPE threads per env, CTA = E*TPE threads, two f32 tile buffers in dynamic smem.
-template <int W, int H, int WIN, int E, int TPE, bool USE_TMA>
-__global__ void __launch_bounds__(E *TPE)
+// One warp builds the feature rows of up to EPW = 32/TPE consecutive envs in its own pair of
+// shared-memory buffers and hands each finished chunk to the TMA with one bulk store; lane 0
+// owns the warp's bulk groups.  No CTA-level barrier is involved: warps are autonomous pipelines.
+//   wbuf_s  shared address of this warp's two buffers; it = this warp's chunk counter (parity)
+//   gdst    where the chunk's rows go; ne = live envs in the chunk (<= EPW)
+//   cells/a the lane's share of its env's grid row and the env's agent record
+// KC > 0 fixes the number of kinds at compile time (KC == K) so that the zero-fill unrolls.
+template <int W, int H, int WIN, int TPE, int KC, bool USE_TMA>
+__device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, float *gdst, int ne,
+                                                   const RowChunks<W, H, TPE> &cells,
+                                                   const Agent &a, int K, int nf) {
+    constexpr int EPW = 32 / TPE;
+    if (KC > 0) {
+        K = KC;
+        nf = 2 * WIN * WIN * KC + KC + 5;
+    }
+    const int lane = threadIdx.x & 31;
+    const int le = lane / TPE, j = lane % TPE;
+    const uint32_t buf_s = wbuf_s + (USE_TMA ? (uint32_t)(it & 1) * EPW * nf * 4 : 0u);
+    // the buffer was handed to the TMA two chunks ago: wait until it has been read
+    if (USE_TMA && lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+    if ((nf & 3) == 0) {
+        const int n16 = EPW * nf / 4;
+        if (KC > 0) {
+#pragma unroll
+            for (int i = 0; i < (n16 + 31) / 32; i++)
+                if (i * 32 + lane < n16) sts_zero16(buf_s + (i * 32 + lane) * 16);
+        } else {
+            for (int i = lane; i < n16; i += 32) sts_zero16(buf_s + i * 16);
+        }
+    } else {
+        for (int i = lane; i < EPW * nf; i += 32) sts_f32(buf_s + i * 4, 0.f);
+    }
+    __syncwarp();
+    if (le < ne) scatter_features<W, H, WIN, TPE>(buf_s + le * nf * 4, cells, a, K, j);
+    const uint32_t bytes = (uint32_t)ne * (uint32_t)nf * 4u;
+    if (USE_TMA && (bytes & 15u) == 0) {
+        fence_async_smem();  // generic-proxy writes -> visible to the async proxy
+        __syncwarp();
+        if (lane == 0) bulk_store(gdst, buf_s, bytes);
+    } else {
+        __syncwarp();
+        if ((bytes & 15u) == 0) {
+            float4 *g4 = reinterpret_cast<float4 *>(gdst);
+            for (int i = lane; i < (int)(bytes / 16); i += 32) {
+                float4 t;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                             : "r"(buf_s + i * 16));
+                __stcs(g4 + i, t);
+            }
+        } else {
+            for (int i = lane; i < ne * nf; i += 32) {
+                float t;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(buf_s + i * 4));
+                gdst[i] = t;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// WPB autonomous warps per CTA; warp w of CTA b takes chunks (b*WPB + w) + k*gridDim.x*WPB.
+// The inputs of the next chunk are fetched before the current one is built (software prefetch).
+template <int W, int H, int WIN, int WPB, int TPE, int KC, bool USE_TMA>
+__global__ void __launch_bounds__(WPB * 32)
 craft_features_kernel(const uint8_t *__restrict__ grid, const uint8_t *__restrict__ agent,
                       float *__restrict__ out, int64_t n, int cell_stride, int K, int nf) {
+    constexpr int EPW = 32 / TPE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *tile[2] = {reinterpret_cast<float *>(smem_raw),
-                      reinterpret_cast<float *>(smem_raw) + (size_t)E * nf};
-    const int tid = threadIdx.x;
-    const int le = tid / TPE, j = tid % TPE;
-    const int64_t n_tiles = (n + E - 1) / E;
-    const int tile_f4 = E * nf / 4;  // E % 4 == 0, so the tile is a whole number of float4
-    int it = 0;
-    for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x, it++) {
-        float *buf = tile[it & 1];
-        const int64_t e = tile_id * E + le;
-        const bool live = e < n;
-        // inputs first, so the loads are in flight while the buffer is recycled
-        Agent a;
-        if (live) a = load_agent_ro(agent, e);
-        if (USE_TMA) {
-            // buffer `it&1` was handed to the TMA two iterations ago: wait until it was read
-            if (tid == 0) bulk_wait_read<1>();
-            __syncthreads();
-        }
-        float4 *b4 = reinterpret_cast<float4 *>(buf);
-        for (int i = tid; i < tile_f4; i += E * TPE) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncthreads();
-        if (live)
-            scatter_features<W, H, WIN, TPE>(buf + (size_t)le * nf, grid + e * cell_stride,
-                                             cell_stride, a, K, j);
-        const int64_t e0 = tile_id * E;
-        const int ne = (int)((n - e0) < E ? (n - e0) : E);
-        const uint32_t bytes = (uint32_t)ne * (uint32_t)nf * 4u;
-        float *gdst = out + e0 * nf;
-        if (USE_TMA && (bytes & 15u) == 0) {
-            fence_async_smem();  // generic-proxy writes -> visible to the async proxy
-            __syncthreads();
-            if (tid == 0) bulk_store(gdst, buf, bytes);
-        } else {
-            __syncthreads();
-            if ((bytes & 15u) == 0) {
-                float4 *g4 = reinterpret_cast<float4 *>(gdst);
-                for (int i = tid; i < (int)(bytes / 16); i += E * TPE) __stcs(g4 + i, b4[i]);
-            } else {
-                for (int i = tid; i < ne * nf; i += E * TPE) gdst[i] = buf[i];
-            }
-            __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int le = lane / TPE, j = lane % TPE;
+    const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)warp * (USE_TMA ? 2 : 1) * EPW * nf * 4;
+    const int64_t n_chunks = (n + EPW - 1) / EPW;
+    const int64_t stride = (int64_t)gridDim.x * WPB;
+    int64_t ch = (int64_t)blockIdx.x * WPB + warp;
+    Agent a, a_next;
+    RowChunks<W, H, TPE> cells, cells_next;
+    auto fetch = [&](int64_t c, Agent &ag, RowChunks<W, H, TPE> &rc) {
+        int64_t e = c * EPW + le;
+        if (e >= n) e = n - 1;
+        ag = load_agent_ro(agent, e);
+        rc.load(grid + e * cell_stride, j);
+    };
+    if (ch < n_chunks) fetch(ch, a, cells);
+    for (int it = 0; ch < n_chunks; ch += stride, it++) {
+        const bool more = ch + stride < n_chunks;
+        if (more) fetch(ch + stride, a_next, cells_next);
+        const int64_t e0 = ch * EPW;
+        const int ne = (int)((n - e0) < EPW ? (n - e0) : EPW);
+        warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA>(wbuf_s, it, out + e0 * nf, ne, cells, a, K, nf);
+        if (more) {
+            a = a_next;
+            cells = cells_next;
         }
     }
-    if (USE_TMA) {
-        if (tid == 0) bulk_wait_read<0>();  // smem must outlive the last bulk store's read
-    }
+    if (USE_TMA && lane == 0) bulk_wait_read<0>();  // smem must outlive the last store's read
 }
 
 // =============================================================================================
@@ -530,16 +671,17 @@ craft_reset_kernel(uint8_t *__restrict__ grid, uint8_t *__restrict__ agent,
     }
 }
 
-// Per-env end of a rollout tick.  Returns true when the episode ended (state was reset).
+// Per-env end of a rollout tick.  Cells are read through `rd` (global row or its shared copy) and
+// written through `row` (global).  Returns true when the episode ended (state was reset).
 template <int W, int H>
 __device__ __forceinline__ bool advance_env(const SharedTables &st, Agent &a, uint8_t *row,
-                                            int act, const uint8_t *scen_row,
+                                            const uint8_t *rd, int act, const uint8_t *scen_row,
                                             const uint8_t *init_agent_row, int cell_stride,
                                             bool &success, uint32_t &flags) {
     const int timer = a.timer() - 1;                          // imitation.py:63
     const bool done = (act == PSK_ACT_STOP) || timer <= 0;    // imitation.py:64-65
     if (done) {
-        const int facing = facing_kind<W, H>(a, row);
+        const int facing = facing_kind<W, H>(a, rd);
         success = st.task_len(a.task())
                       ? node_satisfied(st.node(a.task(), 0), a, facing) == 1
                       : false;                                // imitation.py:69
@@ -552,7 +694,7 @@ __device__ __forceinline__ bool advance_env(const SharedTables &st, Agent &a, ui
         a.w[4] = hi.x; a.w[5] = hi.y; a.w[6] = hi.z; a.w[7] = hi.w;
     } else {
         success = false;
-        step_env<W, H>(st, a, row, act, flags);               // imitation.py:72
+        step_env<W, H>(st, a, row, rd, act, flags);           // imitation.py:72
         a.set_timer(timer);
     }
     return done;
@@ -587,7 +729,8 @@ craft_advance_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__rest
          e += (int64_t)gridDim.x * blockDim.x) {
         Agent a = load_agent(agent, e);
         bool success;
-        const bool done = advance_env<W, H>(st, a, grid + e * cell_stride, action[e],
+        const bool done = advance_env<W, H>(st, a, grid + e * cell_stride,
+                                            grid + e * cell_stride, action[e],
                                             scen_grid + (int64_t)scen_idx[e] * cell_stride,
                                             init_agent + e * PSK_AGENT_BYTES, cell_stride,
                                             success, flags);
@@ -602,15 +745,17 @@ craft_advance_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__rest
 // =============================================================================================
 // fused tick: expert + features + advance, state read once
 // =============================================================================================
-// CTA = 128 threads = one super-tile of 128 envs.
-//   phase A (thread per env): agent -> registers, grid row -> registers + shared copy,
-//                             teacher action (bitboard BFS).
-//   phase B (all threads):    features of the 128 envs in 128/E sub-tiles, each built in a
-//                             double-buffered f32 smem tile and TMA-bulk-stored.
-//   phase C (thread per env): advance (step / done / success / auto-reset) on the shared row,
-//                             write-back of what changed.
-template <int W, int H, int WIN, int E>
-__global__ void __launch_bounds__(128)
+// Warp-specialised: CTA = NE env threads + NFW feature warps = one super-tile of NE envs at a time.
+//   all warps      : coalesced 128-bit copy of the super-tile's grid rows and agent records into
+//                    shared memory (the only read of the state).
+//   env warps      (one env per thread): teacher action (hint walk + bitboard floods), then
+//                    advance (step / done / success / auto-reset) with write-back to HBM.
+//   feature warps  : each an autonomous pipeline over its share of the super-tile's envs
+//                    (warp_feature_chunk: zero-fill + scatter into its smem buffers, TMA store).
+// The integer-ALU-bound teacher and the store-bound feature stream therefore overlap inside
+// every CTA instead of alternating.
+template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA>
+__global__ void __launch_bounds__(NE + NFW * 32)
 craft_tick_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__restrict__ grid,
                   uint8_t *__restrict__ agent, const uint8_t *__restrict__ action_in,
                   const uint8_t *__restrict__ scen_grid, const int32_t *__restrict__ scen_idx,
@@ -618,107 +763,97 @@ craft_tick_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__restric
                   uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
                   uint8_t *__restrict__ success_out, unsigned long long *stats,
                   int32_t *err_flags, int64_t n, int cell_stride, int K, int nf) {
-    constexpr int NT = 128, TPE = NT / E;
+    constexpr int NT = NE + NFW * 32;
+    constexpr int TPE = 8, EPW = 32 / TPE;
+    constexpr int SPW = NE / NFW;              // env slots per feature warp
+    static_assert(SPW % EPW == 0, "feature warps take whole chunks");
     constexpr int CP = ((W * H + 63) / 64) * 64;
     constexpr int NW4 = (W * H + 15) / 16;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ SharedTables st;
-    __shared__ __align__(16) uint8_t s_rows[NT * CP];
-    __shared__ __align__(16) uint32_t s_agent[NT * 8];
-    float *tile[2] = {reinterpret_cast<float *>(smem_raw),
-                      reinterpret_cast<float *>(smem_raw) + (size_t)E * nf};
+    __shared__ __align__(16) uint8_t s_rows[NE * CP];
+    __shared__ __align__(16) uint32_t s_agent[NE * 8];
     stage_tables(st, T);
     const int tid = threadIdx.x;
+    const bool env_warp = tid < NE;
     uint32_t flags = 0;
-    int it = 0;  // running count of feature sub-tiles handed to the TMA (buffer parity)
-    const int64_t n_super = (n + NT - 1) / NT;
+    int it = 0;  // this feature warp's chunk counter
+    const int64_t n_super = (n + NE - 1) / NE;
     for (int64_t sp = blockIdx.x; sp < n_super; sp += gridDim.x) {
-        const int64_t e = sp * NT + tid;
-        const bool live = e < n;
-        // ---- phase A
-        Agent a;
-        int act = PSK_ACT_STOP;
-        if (live) {
-            a = load_agent(agent, e);
-            uint32_t words[NW4 * 4];
-            const uint8_t *row = grid + e * cell_stride;
-            load_row<NW4>(row, words);
-#pragma unroll
-            for (int i = 0; i < NW4; i++)
-                reinterpret_cast<uint4 *>(s_rows + tid * CP)[i] =
-                    make_uint4(words[4 * i], words[4 * i + 1], words[4 * i + 2], words[4 * i + 3]);
-#pragma unroll
-            for (int i = 0; i < 8; i++) s_agent[tid * 8 + i] = a.w[i];
-            const int facing = facing_kind<W, H>(a, s_rows + tid * CP);
-            int dist;
-            act = expert_env<W, H>(st, a, a.task(), words, facing, dist, flags);
-            expert_out[e] = (uint8_t)act;
-            if (action_in) act = action_in[e];
+        const int64_t e_base = sp * NE;
+        const int ne_sp = (int)((n - e_base) < NE ? (n - e_base) : NE);
+        {   // ---- state super-tile -> shared memory
+            const uint4 *grow = reinterpret_cast<const uint4 *>(grid + e_base * CP);
+            uint4 *srow = reinterpret_cast<uint4 *>(s_rows);
+            for (int i = tid; i < ne_sp * (CP / 16); i += NT) srow[i] = grow[i];
+            const uint4 *gag = reinterpret_cast<const uint4 *>(agent + e_base * PSK_AGENT_BYTES);
+            uint4 *sag = reinterpret_cast<uint4 *>(s_agent);
+            for (int i = tid; i < ne_sp * 2; i += NT) sag[i] = gag[i];
         }
         __syncthreads();
-        // ---- phase B
-        if (features_out) {
-            const int tile_f4 = E * nf / 4;
-            for (int sub = 0; sub < NT / E; sub++, it++) {
-                const int64_t e0 = sp * NT + sub * E;
-                if (e0 >= n) break;
-                float *buf = tile[it & 1];
-                if (tid == 0) bulk_wait_read<1>();
-                __syncthreads();
-                float4 *b4 = reinterpret_cast<float4 *>(buf);
-                for (int i = tid; i < tile_f4; i += NT) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                __syncthreads();
-                const int le = tid / TPE, j = tid % TPE;
-                const int se = sub * E + le;  // env slot inside the super-tile
-                if (e0 + le < n) {
-                    Agent b;
+        if (env_warp) {
+            const bool live = tid < ne_sp;
+            const int slot = live ? tid : 0;             // dead lanes replay slot 0, unsaved
+            const int64_t e = e_base + slot;
+            bool done = false, success = false;
+            Agent a;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) b.w[i] = s_agent[se * 8 + i];
-                    scatter_features<W, H, WIN, TPE>(buf + (size_t)le * nf, s_rows + se * CP, CP,
-                                                     b, K, j);
+            for (int i = 0; i < 2; i++) {
+                const uint4 v = reinterpret_cast<const uint4 *>(s_agent)[slot * 2 + i];
+                a.w[4 * i] = v.x; a.w[4 * i + 1] = v.y; a.w[4 * i + 2] = v.z; a.w[4 * i + 3] = v.w;
+            }
+            const uint8_t *srow = s_rows + slot * CP;
+            uint32_t words[NW4 * 4];
+#pragma unroll
+            for (int i = 0; i < NW4; i++) {
+                const uint4 v = reinterpret_cast<const uint4 *>(srow)[i];
+                words[4 * i] = v.x; words[4 * i + 1] = v.y; words[4 * i + 2] = v.z; words[4 * i + 3] = v.w;
+            }
+            const int facing = facing_kind<W, H>(a, srow);
+            int dist;
+            uint32_t fl = 0;
+            int act = expert_env<W, H>(st, a, a.task(), words, facing, dist, fl);
+            if (live) {
+                flags |= fl;
+                const Agent before = a;
+                expert_out[e] = (uint8_t)act;
+                if (action_in) act = action_in[e];
+                done = advance_env<W, H>(st, a, grid + e * CP, srow, act,
+                                         scen_grid + (int64_t)scen_idx[e] * CP,
+                                         init_agent + e * PSK_AGENT_BYTES, CP, success, flags);
+                bool changed = false;
+#pragma unroll
+                for (int i = 0; i < 8; i++) changed |= a.w[i] != before.w[i];
+                if (changed) store_agent(agent, e, a);
+                if (done_out) done_out[e] = done;
+                if (success_out) success_out[e] = success;
+            }
+            add_stats(stats, done, success, live);
+        } else if (features_out) {
+            const int fw = (tid - NE) >> 5, lane = tid & 31;
+            const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)fw * (USE_TMA ? 2 : 1) * EPW * nf * 4;
+            for (int c = 0; c < SPW / EPW; c++) {
+                const int s0 = fw * SPW + c * EPW;      // first env slot of the chunk
+                if (s0 >= ne_sp) break;
+                const int ne = (ne_sp - s0) < EPW ? (ne_sp - s0) : EPW;
+                int se = s0 + lane / TPE;
+                if (se >= ne_sp) se = s0;
+                Agent b;
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(s_agent)[se * 2 + i];
+                    b.w[4 * i] = v.x; b.w[4 * i + 1] = v.y; b.w[4 * i + 2] = v.z; b.w[4 * i + 3] = v.w;
                 }
-                const int ne = (int)((n - e0) < E ? (n - e0) : E);
-                const uint32_t bytes = (uint32_t)ne * (uint32_t)nf * 4u;
-                float *gdst = features_out + e0 * nf;
-                if ((bytes & 15u) == 0) {
-                    fence_async_smem();
-                    __syncthreads();
-                    if (tid == 0) bulk_store(gdst, buf, bytes);
-                } else {
-                    __syncthreads();
-                    for (int i = tid; i < ne * nf; i += NT) gdst[i] = buf[i];
-                    __syncthreads();
-                }
+                RowChunks<W, H, TPE> cells;
+                cells.load(s_rows + se * CP, lane % TPE);
+                warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA>(
+                    wbuf_s, it, features_out + (e_base + s0) * nf, ne, cells, b, K, nf);
+                it++;
             }
         }
-        // ---- phase C
-        bool done = false, success = false;
-        if (live) {
-            const Agent before = a;
-            uint8_t *srow = s_rows + tid * CP;
-            done = advance_env<W, H>(st, a, srow, act,
-                                     scen_grid + (int64_t)scen_idx[e] * cell_stride,
-                                     init_agent + e * PSK_AGENT_BYTES, CP, success, flags);
-            bool changed = false;
-#pragma unroll
-            for (int i = 0; i < 8; i++) changed |= a.w[i] != before.w[i];
-            if (changed) store_agent(agent, e, a);
-            // the grid row changes on reset, pick-up, bridge and axe; write 16-byte chunks that differ
-            uint8_t *row = grid + e * cell_stride;
-            if (done || act == PSK_ACT_USE) {
-#pragma unroll
-                for (int i = 0; i < NW4; i++) {
-                    const uint4 nv = reinterpret_cast<const uint4 *>(srow)[i];
-                    reinterpret_cast<uint4 *>(row)[i] = nv;
-                }
-            }
-            if (done_out) done_out[e] = done;
-            if (success_out) success_out[e] = success;
-        }
-        add_stats(stats, done, success, live);
         __syncthreads();  // s_rows / s_agent are recycled by the next super-tile
     }
-    if (tid == 0) bulk_wait_read<0>();
+    if (USE_TMA && !env_warp && (tid & 31) == 0) bulk_wait_read<0>();
     if (flags && err_flags) atomicOr(err_flags, (int)flags);
 }
 
@@ -746,9 +881,7 @@ static inline int check(cudaError_t e) { return e == cudaSuccess ? PSK_OK : PSK_
 
 template <int W, int H, int WIN> struct Config {
     static constexpr int CP = ((W * H + 63) / 64) * 64;
-    // envs per feature tile: two f32 tiles of E rows must fit next to 3 more CTAs on the SM
-    static constexpr int E = (WIN == 3) ? 16 : 8;
-    static constexpr int TPE = 8;
+    static constexpr int TPE = 8;   // threads per env in the feature scatter
 
     static bool matches(const psk_craft_tables *t) {
         return t->width == W && t->height == H && t->window_w == WIN && t->window_h == WIN &&
@@ -784,27 +917,34 @@ template <int W, int H, int WIN> struct Config {
     template <bool TMA>
     static int features_impl(const psk_craft_tables *t, psk_craft_state s, float *out,
                              cudaStream_t st) {
+        constexpr int WPB = 4, EPW = 32 / TPE;
         const int f = nf(t);
-        const size_t smem = (size_t)2 * E * f * sizeof(float);
-        auto kern = craft_features_kernel<W, H, WIN, E, TPE, TMA>;
-        static size_t configured = 0;  // opt in to > 48 KB dynamic smem once per size
+        const size_t smem = (size_t)WPB * (TMA ? 2 : 1) * EPW * f * sizeof(float);
+        // the default cookbook has 21 kinds: that case is compiled with K fixed
+        auto kern = t->n_kinds == 21 ? craft_features_kernel<W, H, WIN, WPB, TPE, 21, TMA>
+                                     : craft_features_kernel<W, H, WIN, WPB, TPE, 0, TMA>;
+        // opt in to > 48 KB dynamic smem (both instantiations, once per size)
+        static size_t configured = 0;
         if (configured != smem) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem) != cudaSuccess)
+            if (cudaFuncSetAttribute(craft_features_kernel<W, H, WIN, WPB, TPE, 21, TMA>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(craft_features_kernel<W, H, WIN, WPB, TPE, 0, TMA>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return PSK_ERR_CUDA;
             configured = smem;
         }
-        const int per_sm = (int)((220 * 1024) / (smem + 1024));
-        const int64_t tiles = (s.n + E - 1) / E;
+        int per_sm = (int)((224 * 1024) / (smem + 1024));
+        if (per_sm > 16) per_sm = 16;
+        const int64_t ctas = (s.n + (int64_t)WPB * EPW - 1) / ((int64_t)WPB * EPW);
         int64_t g = (int64_t)num_sms() * (per_sm > 0 ? per_sm : 1);
-        if (g > tiles) g = tiles > 0 ? tiles : 1;
-        kern<<<(int)g, E * TPE, smem, st>>>(s.grid, s.agent, out, s.n, s.cell_stride, t->n_kinds, f);
+        if (g > ctas) g = ctas > 0 ? ctas : 1;
+        kern<<<(int)g, WPB * 32, smem, st>>>(s.grid, s.agent, out, s.n, s.cell_stride, t->n_kinds, f);
         return check(cudaGetLastError());
     }
     static int features(const psk_craft_tables *t, psk_craft_state s, float *out, int impl,
                         cudaStream_t st) {
         if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) impl = 1;
-        return impl == 1 ? features_impl<false>(t, s, out, st) : features_impl<true>(t, s, out, st);
+        return impl == 2 ? features_impl<true>(t, s, out, st) : features_impl<false>(t, s, out, st);
     }
     static int advance(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
                        const uint8_t *action, uint8_t *done, uint8_t *success,
@@ -814,29 +954,68 @@ template <int W, int H, int WIN> struct Config {
             stats, err, s.n, s.cell_stride);
         return check(cudaGetLastError());
     }
+    template <int NE, int NFW, bool TMA>
+    static int tick_variant(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
+                            const uint8_t *action_in, float *features_out, uint8_t *expert_out,
+                            uint8_t *done, uint8_t *success, unsigned long long *stats,
+                            int32_t *err, cudaStream_t st) {
+        constexpr int EPW = 32 / TPE;
+        const int f = nf(t);
+        const size_t smem = (size_t)NFW * (TMA ? 2 : 1) * EPW * f * sizeof(float);
+        auto kern = t->n_kinds == 21 ? craft_tick_kernel<W, H, WIN, NE, NFW, 21, TMA>
+                                     : craft_tick_kernel<W, H, WIN, NE, NFW, 0, TMA>;
+        static size_t configured = 0;
+        if (configured != smem) {
+            if (cudaFuncSetAttribute(craft_tick_kernel<W, H, WIN, NE, NFW, 21, TMA>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(craft_tick_kernel<W, H, WIN, NE, NFW, 0, TMA>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return PSK_ERR_CUDA;
+            configured = smem;
+        }
+        const size_t static_smem = sizeof(SharedTables) + (size_t)NE * (CP + 32);
+        int per_sm = (int)((224 * 1024) / (smem + static_smem + 1024));
+        const int by_threads = 2048 / (NE + NFW * 32);
+        if (per_sm > by_threads) per_sm = by_threads;
+        const int64_t tiles = (s.n + NE - 1) / NE;
+        int64_t g = (int64_t)num_sms() * (per_sm > 0 ? per_sm : 1);
+        if (g > tiles) g = tiles > 0 ? tiles : 1;
+        kern<<<(int)g, NE + NFW * 32, smem, st>>>(
+            *t, s.grid, s.agent, action_in, ep.scen_grid, ep.scen_idx, ep.init_agent, features_out,
+            expert_out, done, success, stats, err, s.n, s.cell_stride, t->n_kinds, f);
+        return check(cudaGetLastError());
+    }
     static int tick_fused(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
                           const uint8_t *action_in, float *features_out, uint8_t *expert_out,
                           uint8_t *done, uint8_t *success, unsigned long long *stats,
                           int32_t *err, cudaStream_t st) {
-        const int f = nf(t);
-        const size_t smem = (size_t)2 * E * f * sizeof(float);
-        auto kern = craft_tick_kernel<W, H, WIN, E>;
-        static size_t configured = 0;
-        if (configured != smem) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem) != cudaSuccess)
-                return PSK_ERR_CUDA;
-            configured = smem;
+        // Defaults from the sweep in profiles/README.md: small batches are latency-bound and
+        // prefer big CTAs with plain vector stores; large batches prefer many small CTAs whose
+        // feature warps stream through the TMA.  PSK_TICK_VARIANT / PSK_TICK_TMA override.
+        static int env_variant = -2, env_tma = -2;
+        if (env_variant == -2) {
+            const char *v = getenv("PSK_TICK_VARIANT");
+            env_variant = v ? atoi(v) : -1;
+            const char *m = getenv("PSK_TICK_TMA");
+            env_tma = m ? atoi(m) : -1;
         }
-        const size_t static_smem = sizeof(SharedTables) + (size_t)128 * CP + 128 * 32;
-        const int per_sm = (int)((220 * 1024) / (smem + static_smem + 1024));
-        const int64_t tiles = (s.n + 127) / 128;
-        int64_t g = (int64_t)num_sms() * (per_sm > 0 ? per_sm : 1);
-        if (g > tiles) g = tiles > 0 ? tiles : 1;
-        kern<<<(int)g, 128, smem, st>>>(*t, s.grid, s.agent, action_in, ep.scen_grid, ep.scen_idx,
-                                        ep.init_agent, features_out, expert_out, done, success,
-                                        stats, err, s.n, s.cell_stride, t->n_kinds, f);
-        return check(cudaGetLastError());
+        const bool big = s.n > 262144;
+        const int variant = env_variant >= 0 ? env_variant : (big ? 4 : 1);
+        const int tma = env_tma >= 0 ? env_tma : (big ? 1 : 0);
+#define PSK_TV(NE, NFW)                                                                          \
+    return tma ? tick_variant<NE, NFW, true>(t, s, ep, action_in, features_out, expert_out, done, \
+                                             success, stats, err, st)                            \
+               : tick_variant<NE, NFW, false>(t, s, ep, action_in, features_out, expert_out, done, \
+                                              success, stats, err, st)
+        if (WIN != 3) PSK_TV(64, 2);
+        switch (variant) {
+            case 1: PSK_TV(128, 4);
+            case 2: PSK_TV(32, 1);
+            case 3: PSK_TV(64, 4);
+            case 4: PSK_TV(32, 2);
+            default: PSK_TV(64, 2);
+        }
+#undef PSK_TV
     }
 };
 

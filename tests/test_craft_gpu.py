@@ -26,7 +26,7 @@ def _check_states(tables, oracle, S):
     env = _env_from_states(tables, S)
     # ---- features, both store paths
     ref_f = S["features"].astype(np.float32)
-    for impl in (0, 1):
+    for impl in (0, 1, 2):
         f = env.features(impl=impl)
         assert f.dtype == torch.float32 and tuple(f.shape) == (n, tables.n_features)
         assert np.array_equal(_np(f), ref_f), "features impl %d" % impl
