@@ -62,7 +62,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -166,35 +166,43 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def time_kernel(fn, iters, torch):
+def time_kernel(fn, torch, inner=10, reps=20):
+    """Average device time of one launch: `inner` launches captured in a CUDA graph (so that the
+    Python/ctypes launch cost is not what is measured), replayed `reps` times between events."""
     fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(inner):
+                fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(reps):
+        g.replay()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / iters * 1e-3
+    return s.elapsed_time(e) * 1e-3 / (reps * inner)
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from psketch_b200 import dist as pdist
     from psketch_b200.tables import CraftTables
     from psketch_b200.vec import VecCraft
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    rank, world, local = pdist.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     distributed = world > 1
-    if distributed:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
 
     n = args.envs_per_gpu
     K, W = args.steps, args.warmup
@@ -241,12 +249,12 @@ def run_ours(args):
             tick(done)
             done += 1
 
+    sampler = ClockSampler(local) if rank == 0 else None
     run_steps(max(W, 3))
     env.stats.zero_()
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.time()
@@ -262,9 +270,22 @@ def run_ours(args):
     stats = env.stats.clone()
     if distributed:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)       # the path's only collective
+    pdist.allreduce_stats(stats)                            # the path's only collective (NCCL)
     elapsed = float(el.item())
-    clocks = sampler.stop(t0, t1) if sampler else None
+    clocks = None
+    if sampler:
+        t1c, window = t1, "timed region"
+        if t1 - t0 < 0.6:
+            # nvidia-smi cannot sample faster than ~20 ms: keep the same step running (untimed)
+            # so that the clocks are read under the same load
+            tc = time.time()
+            while time.time() - tc < 0.8:
+                run_steps(ring * 8)
+                torch.cuda.synchronize()
+            t1c, window = time.time(), "timed region + 0.8 s untimed continuation of the same step"
+        clocks = sampler.stop(t0, t1c)
+        clocks["window"] = window
+    stats_after = None
     env.check_errors()
     total_steps = n * K * world
     value = total_steps / elapsed
@@ -294,7 +315,8 @@ def run_ours(args):
         "config": {
             "workload": "craft_medium train tasks (17,600 instances tiled), %d parallel envs per GPU, "
                         "teacher BFS + f32[404] features + step/auto-reset per tick" % n,
-            "envs_per_gpu": n, "max_timesteps": 40, "kernel": "fused tick" if fused else "expert+features+advance",
+            "envs_per_gpu": n, "max_timesteps": 40,
+            "kernel": "craft_tick_kernel (fused, warp-specialised)" if fused else "expert+features+advance",
             "cuda_graph": graph is not None,
             "l2": "feature outputs rotate through a ring of %d buffers (%.0f MB > 126 MB L2)"
                   % (ring, ring * feat_bytes / 1e6),
@@ -314,7 +336,6 @@ def run_ours(args):
                             "algorithmic_bytes_per_env_step": BYTES_FUSED}
     # per-kernel numbers (north star: step and features as a fraction of the HBM roofline)
     kern = {}
-    it = 50
     act = env.expert()
     big = [torch.empty((n, nf), dtype=torch.float32, device=dev) for _ in range(min(ring, 8))]
     cnt = [0]
@@ -329,7 +350,7 @@ def run_ours(args):
     for name, fn, b in (("features_tma", f_feat(2), BYTES_FEATURES), ("features_plain", f_feat(1), BYTES_FEATURES),
                         ("expert", lambda: env.expert(out=act), BYTES_EXPERT),
                         ("step", lambda: env.step(act), BYTES_STEP)):
-        dt = time_kernel(fn, it, torch)
+        dt = time_kernel(fn, torch, inner=len(big) if name.startswith("features") else 10)
         kern[name] = {"us": dt * 1e6, "GBps": b * n / dt / 1e9, "frac": b * n / dt / 1e9 / peak,
                       "env_per_s": n / dt}
     env.restore(snap)
@@ -352,46 +373,31 @@ def run_ours(args):
 
 
 def measure_e2e(torch, tables, wl, n, dev, args):
-    """Same tick through the public API with HOST buffers: every step copies the states in from
-    pinned host memory, runs the fused tick and reads features, teacher actions, done/success and
-    the new states back to pinned host memory."""
-    from psketch_b200.vec import VecCraft
-    env = VecCraft.from_instances(tables, wl["grids"], wl["env"], wl["pos"], wl["task"],
-                                  max_timesteps=40, device=dev)
-    nf = env.n_features
-    h_grid = env.grid.cpu().pin_memory()
-    h_agent = env.agent.cpu().pin_memory()
-    h_feat = torch.empty((n, nf), dtype=torch.float32).pin_memory()
-    h_small = torch.empty((3, n), dtype=torch.uint8).pin_memory()
-    d_feat = torch.empty((n, nf), dtype=torch.float32, device=dev)
-    out = {}
-    steps = max(3, min(args.steps, 20))
-
-    def one():
-        env.grid.copy_(h_grid, non_blocking=True)
-        env.agent.copy_(h_agent, non_blocking=True)
-        env.tick(features_out=d_feat, fused=not args.unfused, out=out)
-        h_feat.copy_(d_feat, non_blocking=True)
-        h_small[0].copy_(out["expert"], non_blocking=True)
-        h_small[1].copy_(out["done"], non_blocking=True)
-        h_small[2].copy_(out["success"], non_blocking=True)
-        h_grid.copy_(env.grid, non_blocking=True)
-        h_agent.copy_(env.agent, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
+    """Same tick through the reference-facing C ABI with HOST buffers (psk_craft_host_tick):
+    every step copies the states in from pinned host memory, runs the fused tick, and reads
+    features, teacher actions, done/success and the new states back to pinned host memory."""
+    from psketch_b200.host import HostCraft
+    env = HostCraft(tables, wl["grids"], wl["env"], wl["pos"], wl["task"], max_timesteps=40,
+                    chunk_envs=args.e2e_chunk)
+    steps = max(3, min(args.steps, 30))
     for _ in range(3):
-        one()
+        env.tick()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     s.record()
     for _ in range(steps):
-        one()
+        env.tick()                      # returns after the D2H copies have landed
     e.record()
     torch.cuda.synchronize()
-    state_bytes = n * (env.cell_stride + 32)
-    return {"elapsed": s.elapsed_time(e) * 1e-3, "steps": steps, "h2d": state_bytes,
-            "d2h": n * nf * 4 + 3 * n + state_bytes,
-            "how": "VecCraft.tick with pinned host buffers: H2D states, fused tick, D2H features+actions+flags+states, sync per step"}
+    wall = time.perf_counter() - t0
+    assert int(env.stats[2]) == (steps + 3) * n
+    res = {"elapsed": max(s.elapsed_time(e) * 1e-3, wall), "steps": steps, "h2d": env.h2d_bytes,
+           "d2h": env.d2h_bytes,
+           "how": "psk_craft_host_tick (C ABI, pinned host numpy buffers): per step H2D states, fused "
+                  "tick, D2H features+actions+flags+states in %d-env chunks over 3 streams" % args.e2e_chunk}
+    env.close()
+    return res
 
 
 def main():
@@ -404,6 +410,7 @@ def main():
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=16384)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -24,6 +24,7 @@
 #ifndef PSK_CRAFT_H
 #define PSK_CRAFT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -142,6 +143,35 @@ int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episo
                    const uint8_t *action_in, float *features_out, uint8_t *expert_out,
                    uint8_t *done_out, uint8_t *success_out, unsigned long long *stats,
                    int32_t *err_flags, int fused, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer entry points: the caller keeps its environments in HOST memory, as the reference
+ * does (every CraftState is a CPU object).  All pointers below are HOST pointers; pass pinned
+ * memory (psk_host_alloc) so that the copies overlap with the kernels.  Chunks of the batch are
+ * pipelined over several streams:  H2D(state) -> fused tick -> D2H(features, actions, state). */
+typedef struct psk_craft_host_ctx psk_craft_host_ctx;
+
+void *psk_host_alloc(size_t bytes); /* pinned host memory, NULL on failure */
+void psk_host_free(void *p);
+
+int psk_craft_host_create(const psk_craft_tables *t, int64_t max_envs, int64_t chunk_envs,
+                          psk_craft_host_ctx **out);
+void psk_craft_host_destroy(psk_craft_host_ctx *ctx);
+
+/* Episode starts (same meaning as psk_craft_episodes), uploaded once and kept on the device. */
+int psk_craft_host_set_episodes(psk_craft_host_ctx *ctx, const uint8_t *host_scen_grid,
+                                int64_t n_scen, const int32_t *host_scen_idx,
+                                const uint8_t *host_init_agent, int64_t n);
+
+/* psk_craft_tick over host arrays: host_grid u8[n][cell_stride] and host_agent u8[n][32] are
+ * read and overwritten with the new state; host_features f32[n][n_features] (may be NULL),
+ * host_expert u8[n], host_done / host_success u8[n] (may be NULL), host_action_in u8[n] (may be
+ * NULL = follow the teacher), host_stats u64[4] and host_err_flags (may be NULL) receive the
+ * running episode statistics and the PSK_FLAG_* bits.  Returns after everything has landed. */
+int psk_craft_host_tick(psk_craft_host_ctx *ctx, uint8_t *host_grid, uint8_t *host_agent,
+                        const uint8_t *host_action_in, float *host_features,
+                        uint8_t *host_expert, uint8_t *host_done, uint8_t *host_success,
+                        int64_t n, unsigned long long *host_stats, int32_t *host_err_flags);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,9 @@ MAX_INV = 24
 CRAFT_EXPORTS = (
     "psk_version", "psk_craft_n_features", "psk_craft_supported", "psk_craft_step",
     "psk_craft_features", "psk_craft_satisfies", "psk_craft_expert", "psk_craft_find_closest",
-    "psk_craft_reset", "psk_craft_tick",
+    "psk_craft_reset", "psk_craft_tick", "psk_host_alloc", "psk_host_free",
+    "psk_craft_host_create", "psk_craft_host_destroy", "psk_craft_host_set_episodes",
+    "psk_craft_host_tick",
 )
 
 
@@ -78,8 +80,19 @@ def load():
     lib.psk_craft_reset.argtypes = [CraftStateC, CraftEpisodesC, vp, vp]
     lib.psk_craft_tick.argtypes = [tp, CraftStateC, CraftEpisodesC, vp, vp, vp, vp, vp, vp, vp,
                                    i32, vp]
+    i64 = ctypes.c_int64
+    lib.psk_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.psk_host_alloc.restype = ctypes.c_void_p
+    lib.psk_host_free.argtypes = [vp]
+    lib.psk_host_free.restype = None
+    lib.psk_craft_host_create.argtypes = [tp, i64, i64, ctypes.POINTER(vp)]
+    lib.psk_craft_host_destroy.argtypes = [vp]
+    lib.psk_craft_host_destroy.restype = None
+    lib.psk_craft_host_set_episodes.argtypes = [vp, vp, i64, vp, vp, i64]
+    lib.psk_craft_host_tick.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp]
     for name in CRAFT_EXPORTS[1:]:
-        getattr(lib, name).restype = ctypes.c_int
+        if name not in ("psk_host_alloc", "psk_host_free", "psk_craft_host_destroy"):
+            getattr(lib, name).restype = ctypes.c_int
     _lib = lib
     return lib
 

@@ -1,0 +1,117 @@
+"""HostCraft — the batched tick for callers whose environments live in HOST memory.
+
+This is the end-to-end entry point for a CPU-resident caller (the reference keeps every
+CraftState on the CPU): numpy arrays in pinned memory go through ``psk_craft_host_tick``
+(include/psk_craft.h), which pipelines H2D copies, the fused tick kernel and D2H copies over
+several CUDA streams.  No torch tensors cross this boundary.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .tables import CraftTables
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class PinnedArray(object):
+    """numpy view over cudaHostAlloc'ed memory (freed when the object dies)."""
+
+    def __init__(self, lib, shape, dtype):
+        self.lib = lib
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib.psk_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise _lib.PskError("psk_host_alloc(%d) failed" % self.nbytes)
+        buf = (ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.psk_host_free(ctypes.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class HostCraft(object):
+    def __init__(self, tables, scen_grids, scen_idx, init_pos, task, init_dir=None,
+                 max_timesteps=40, chunk_envs=16384):
+        self.lib = _lib.load()
+        self.tables = tables if tables is not None else CraftTables()
+        self.ct = _lib.make_tables(self.tables)
+        t = self.tables
+        scen_grids = np.asarray(scen_grids, np.uint8)
+        scen_idx = np.ascontiguousarray(scen_idx, np.int32)
+        self.n = n = len(scen_idx)
+        self.C = t.W * t.H
+        self.cell_stride = cs = ((self.C + 63) // 64) * 64
+        self.n_features = t.n_features
+        sg = np.zeros((len(scen_grids), cs), np.uint8)
+        sg[:, :self.C] = scen_grids
+        ia = np.zeros((n, _lib.AGENT_BYTES), np.uint8)
+        init_pos = np.asarray(init_pos)
+        ia[:, _lib.AG_X], ia[:, _lib.AG_Y] = init_pos[:, 0], init_pos[:, 1]
+        ia[:, _lib.AG_DIR] = 0 if init_dir is None else np.asarray(init_dir)
+        ia[:, _lib.AG_TASK] = np.asarray(task)
+        ia[:, _lib.AG_TIMER] = max_timesteps
+        ctx = ctypes.c_void_p()
+        _lib.check(self.lib.psk_craft_host_create(ctypes.byref(self.ct), n, chunk_envs,
+                                                  ctypes.byref(ctx)), "psk_craft_host_create")
+        self.ctx = ctx
+        _lib.check(self.lib.psk_craft_host_set_episodes(self.ctx, _np_ptr(sg), len(sg),
+                                                        _np_ptr(scen_idx), _np_ptr(ia), n),
+                   "psk_craft_host_set_episodes")
+        # pinned host-side state and outputs
+        self._pins = {k: PinnedArray(self.lib, shape, dt) for k, (shape, dt) in dict(
+            grid=((n, cs), np.uint8), agent=((n, _lib.AGENT_BYTES), np.uint8),
+            features=((n, self.n_features), np.float32), expert=((n,), np.uint8),
+            done=((n,), np.uint8), success=((n,), np.uint8), action=((n,), np.uint8)).items()}
+        self.grid = self._pins["grid"].array
+        self.agent = self._pins["agent"].array
+        self.features = self._pins["features"].array
+        self.expert = self._pins["expert"].array
+        self.done = self._pins["done"].array
+        self.success = self._pins["success"].array
+        self.action = self._pins["action"].array
+        self.grid[:] = sg[scen_idx]
+        self.agent[:] = ia
+        self.stats = np.zeros(4, np.uint64)
+        self.err = np.zeros(1, np.int32)
+
+    def tick(self, actions=None, want_features=True):
+        if actions is not None:
+            self.action[:] = actions
+        rc = self.lib.psk_craft_host_tick(
+            self.ctx, _np_ptr(self.grid), _np_ptr(self.agent),
+            _np_ptr(self.action) if actions is not None else None,
+            _np_ptr(self.features) if want_features else None, _np_ptr(self.expert),
+            _np_ptr(self.done), _np_ptr(self.success), self.n, _np_ptr(self.stats),
+            _np_ptr(self.err))
+        _lib.check(rc, "psk_craft_host_tick")
+        if self.err[0] & _lib.FLAG_BAD_ACTION:
+            raise Exception("Unexpected action")
+        return self.expert
+
+    @property
+    def h2d_bytes(self):
+        return self.n * (self.cell_stride + _lib.AGENT_BYTES)
+
+    @property
+    def d2h_bytes(self):
+        return self.n * (self.n_features * 4 + 3 + self.cell_stride + _lib.AGENT_BYTES)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.psk_craft_host_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,418 @@
+"""Drop-in mirror of the reference's ``worlds/craft.py`` object API, backed by the CUDA kernels.
+
+Same names, argument meaning and error behaviour as the reference so that its trainers, students
+and teachers run unchanged:
+
+    world = CraftWorld(config)                    worlds/craft.py:58-109
+    state = world.init_state(grid, pos, dir=0)    worlds/craft.py:258-259
+    reward, state2 = state.step(action)           worlds/craft.py:332-424   (state is not mutated)
+    state.features()  -> float64[n_features]      worlds/craft.py:296-330
+    state.satisfies(task)                         worlds/craft.py:285-294
+    state.pos / .dir / .inventory / .grid / .world / .scenario
+
+States are persistent host-side records (64 + 32 bytes); all arithmetic happens on the GPU.
+The trainers call ``states[i].step(a)`` one env at a time, so ``step`` only *records* the
+transition; the first read of any derived value flushes every pending transition of the world
+in ONE batched launch sequence (step -> features -> teacher -> satisfies) and caches the results
+on the state objects, exactly like the reference caches ``_cached_features``.
+"""
+import os
+
+import numpy as np
+
+from .. import _lib
+from ..tables import (COORD_CHANGE, Cookbook, CraftTables, TaskManager, WORLD_CONFIGS, DOWN, UP,
+                      LEFT, RIGHT, USE, STOP, N_ACTIONS)
+
+
+class _Struct(object):
+    """Attribute bag compatible with misc.util.Struct for the fields the trainers read."""
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, _Struct(**v) if isinstance(v, dict) else v)
+
+
+def _cfg_get(config, path, default=None):
+    cur = config
+    for name in path.split("."):
+        if cur is None or not hasattr(cur, name):
+            return default
+        cur = getattr(cur, name)
+    return cur
+
+
+class CraftWorld(object):
+    def __init__(self, config=None, tables=None, device=None):
+        recipes = _cfg_get(config, "recipes")
+        cookbook = Cookbook(recipes if recipes and os.path.exists(recipes) else None)
+        world_name = _cfg_get(config, "world.config", "craft_medium")
+        world_file = os.path.join("configs/worlds", "%s.yaml" % world_name)
+        if os.path.exists(world_file):
+            import yaml
+            with open(world_file) as f:
+                world_cfg = yaml.safe_load(f)
+        else:
+            world_cfg = dict(WORLD_CONFIGS[world_name])
+        for k, v in world_cfg.items():          # worlds/craft.py:64-67
+            setattr(self, k, v)
+        hints = _cfg_get(config, "trainer.hints")
+        tm = TaskManager(hints if hints and os.path.exists(hints) else None)
+        self.tables = tables if tables is not None else CraftTables(cookbook, tm, world_cfg)
+        self.cookbook = self.tables.cookbook
+        self.task_manager = self.tables.task_manager
+        self.n_features = self.tables.n_features
+        self.n_actions = N_ACTIONS
+        if config is not None and _cfg_get(config, "student.model") is not None:
+            config.student.model.input_size = self.n_features      # worlds/craft.py:69
+            config.student.model.n_actions = self.n_actions        # worlds/craft.py:76
+        names = ("DOWN", "UP", "LEFT", "RIGHT", "USE", "STOP")
+        self.actions = _Struct(**{n: {"index": i, "coord_change": COORD_CHANGE[i]}
+                                  for i, n in enumerate(names)})
+        self.action_space = [getattr(self.actions, n) for n in names]
+        env = self.cookbook.environment
+        self.non_grabbable_indices = env
+        self.grabbable_indices = [i for i in range(self.cookbook.n_kinds) if i not in env]
+        self.workshop_indices = list(self.tables.workshop_kinds)
+        self.water_index = self.cookbook.index["water"]
+        self.stone_index = self.cookbook.index["stone"]
+        self.random = _cfg_get(config, "random")
+        self._device = device
+        self._backend = None
+        self._pending = []          # states whose transition has not been computed yet
+        self._fresh = []            # initial states whose derived values are not cached yet
+        self._grid_cache = {}
+
+    # -- reference API -----------------------------------------------------------------------
+    def make_scenario(self, grid, pos, dir=0):
+        return CraftScenario(grid, pos, self, init_dir=dir)
+
+    def init_state(self, grid, pos, dir=0):
+        return self.make_scenario(grid, pos, dir=dir).init()
+
+    def render(self, state):
+        inv = {self.cookbook.index.get(i): int(v) for i, v in enumerate(state.inventory) if v > 0}
+        print("\nInventory:", inv)
+        rows = []
+        arrows = {LEFT: "<", RIGHT: ">", UP: "^", DOWN: "v"}
+        cells = state.cells.reshape(self.WIDTH, self.HEIGHT)
+        for y in range(self.HEIGHT):
+            row = ""
+            for x in range(self.WIDTH):
+                if (x, y) == state.pos:
+                    row += arrows[state.dir] + " "
+                elif cells[x, y] == 0:
+                    row += ". "
+                else:
+                    row += "%-2s" % self.cookbook.index.get(int(cells[x, y]))[:2]
+            rows.append(row)
+        rows = rows[::-1]
+        print("\n".join(rows))
+        return rows
+
+    # -- batching machinery ------------------------------------------------------------------
+    def cells_of(self, grid):
+        """one-hot float grid [W,H,K] (dataset item) or kind-id grid -> u8[W*H] kind ids."""
+        g = np.asarray(grid)
+        if g.ndim == 3:
+            key = (g.__array_interface__["data"][0], g.shape)
+            hit = self._grid_cache.get(key)
+            if hit is not None and hit[0] is grid:
+                return hit[1]
+            assert (g.sum(axis=2) <= 1).all(), "impossible world configuration"   # craft.py:371
+            ids = (g.argmax(axis=2) * (g.sum(axis=2) > 0)).astype(np.uint8).reshape(-1)
+            if len(self._grid_cache) > 4096:
+                self._grid_cache.clear()
+            self._grid_cache[key] = (grid, ids)
+            return ids
+        return g.astype(np.uint8).reshape(-1)
+
+    def backend(self):
+        if self._backend is None:
+            self._backend = _Backend(self)
+        return self._backend
+
+    def flush(self):
+        """Computes every pending transition (and the derived values of the new states)."""
+        if self._pending:
+            pend, self._pending = self._pending, []
+            self.backend().evaluate(pend)
+
+
+class CraftScenario(object):
+    def __init__(self, grid, init_pos, world, init_dir=0):
+        self.init_grid = grid
+        self.init_pos = init_pos
+        self.init_dir = init_dir
+        self.world = world
+
+    def init(self):
+        w = self.world
+        agent = np.zeros(_lib.AGENT_BYTES, np.uint8)
+        agent[_lib.AG_X], agent[_lib.AG_Y] = int(self.init_pos[0]), int(self.init_pos[1])
+        agent[_lib.AG_DIR] = int(self.init_dir)
+        onehot = self.init_grid if np.ndim(self.init_grid) == 3 else None
+        state = CraftState(self, w.cells_of(self.init_grid), agent, grid_onehot=onehot)
+        w._fresh.append(state)
+        if len(w._fresh) > 65536:
+            del w._fresh[:32768]
+        return state
+
+
+class CraftState(object):
+    """Persistent state record.  ``_cells``/``_agent`` are None while the transition that produces
+    this state is still pending (``_parent``, ``_action``)."""
+
+    def __init__(self, scenario, cells, agent, grid_onehot=None, parent=None, action=None):
+        self.scenario = scenario
+        self.world = scenario.world
+        self._cells = cells
+        self._agent = agent
+        self._grid = grid_onehot
+        self._parent = parent
+        self._action = action
+        self._cached_features = None
+        self._task_hint = parent._task_hint if parent is not None else 0
+        self._expert = {}           # task id -> action
+        self._sat = {}              # task id -> 0 / 1 / 2
+        self._evaluated = False     # features / teacher / satisfies cached for the hinted task
+
+    # -- materialisation ---------------------------------------------------------------------
+    def _need(self):
+        if self._cells is None:
+            self.world.flush()
+        if self._cells is None:      # created outside the queue (should not happen)
+            self.world.backend().evaluate([self])
+
+    @property
+    def cells(self):
+        self._need()
+        return self._cells
+
+    @property
+    def pos(self):
+        self._need()
+        return (int(self._agent[_lib.AG_X]), int(self._agent[_lib.AG_Y]))
+
+    @property
+    def dir(self):
+        self._need()
+        return int(self._agent[_lib.AG_DIR])
+
+    @property
+    def inventory(self):
+        self._need()
+        return self._agent[:self.world.cookbook.n_kinds].astype(np.float64)
+
+    @inventory.setter
+    def inventory(self, value):
+        self._need()
+        self._agent = self._agent.copy()
+        self._agent[:self.world.cookbook.n_kinds] = np.asarray(value).astype(np.uint8)
+        self._invalidate()
+
+    @property
+    def grid(self):
+        """one-hot float64 [W,H,K] view of the grid, as the reference stores it."""
+        if self._grid is None:
+            w = self.world
+            cells = self.cells.reshape(w.WIDTH, w.HEIGHT)
+            g = np.zeros((w.WIDTH, w.HEIGHT, w.cookbook.n_kinds))
+            xs, ys = np.nonzero(cells)
+            g[xs, ys, cells[xs, ys]] = 1
+            self._grid = g
+        return self._grid
+
+    def _invalidate(self):
+        self._cached_features = None
+        self._expert, self._sat, self._evaluated = {}, {}, False
+
+    def _task_id(self, task):
+        tm = self.world.task_manager
+        t = tm.tasks_by_goal.get("%s[%s]" % (task.goal_name, task.goal_arg))
+        if t is None:
+            raise KeyError("unknown task %r" % (task,))
+        return t.task_id
+
+    def _evaluate(self, task_id=None):
+        self._need()
+        if task_id is not None and task_id != self._task_hint:
+            self._task_hint = task_id
+            self._evaluated = False
+        if not self._evaluated:
+            w = self.world
+            w.flush()
+            if not self._evaluated:
+                # evaluate together with every other initial state that is still waiting
+                batch = [self] + [s for s in w._fresh if s is not self and not s._evaluated]
+                w._fresh = []
+                w.backend().evaluate(batch, step=False)
+
+    # -- reference API -----------------------------------------------------------------------
+    def step(self, action):
+        action = int(action)
+        if action < 0 or action >= N_ACTIONS:
+            raise Exception("Unexpected action: %s" % action)      # worlds/craft.py:415-416
+        child = CraftState(self.scenario, None, None, parent=self, action=action)
+        self.world._pending.append(child)
+        return 0, child
+
+    def features(self):
+        if self._cached_features is None:
+            self._evaluate()
+        return self._cached_features
+
+    def satisfies(self, task):
+        tid = self._task_id(task)
+        if tid not in self._sat:
+            self._evaluate(tid)
+        v = self._sat[tid]
+        return None if v == 2 else bool(v)
+
+    def expert_action(self, task):
+        tid = self._task_id(task)
+        if tid not in self._expert:
+            self._evaluate(tid)
+        a = self._expert[tid]
+        if a == 255:
+            raise AssertionError("subtask is neither 'use' nor 'go'")   # demonstration.py:18
+        return a
+
+    def neighbors(self, pos, dir=None):
+        x, y = pos
+        w = self.world
+        out = []
+        if x > 0 and (dir is None or dir == LEFT):
+            out.append((x - 1, y))
+        if y > 0 and (dir is None or dir == DOWN):
+            out.append((x, y - 1))
+        if x < w.WIDTH - 1 and (dir is None or dir == RIGHT):
+            out.append((x + 1, y))
+        if y < w.HEIGHT - 1 and (dir is None or dir == UP):
+            out.append((x, y + 1))
+        return out
+
+    def next_to(self, i_kind):
+        x, y = self.pos
+        c = self.cells.reshape(self.world.WIDTH, self.world.HEIGHT)
+        return bool((c[max(x - 1, 0):x + 2, max(y - 1, 0):y + 2] == i_kind).any())
+
+    def hit_wall(self):
+        return not self.neighbors(self.pos, self.dir)
+
+    def render(self):
+        return self.world.render(self)
+
+    def make_navigation_grid(self):
+        return (self.cells.reshape(self.world.WIDTH, self.world.HEIGHT) != 0).astype(np.float64)
+
+    def find_resource_positions(self, goal_arg):
+        thing = self.world.cookbook.index[goal_arg]
+        c = self.cells.reshape(self.world.WIDTH, self.world.HEIGHT)
+        return list(zip(*np.nonzero(c == thing)))
+
+
+class _Backend(object):
+    """Device scratch + launch sequence for a list of states (any size; typically the batch)."""
+
+    def __init__(self, world):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.PskError("the Craft façade needs a CUDA device (there is no CPU fallback)")
+        self.torch = torch
+        self.world = world
+        self.lib = _lib.load()
+        self.ct = _lib.make_tables(world.tables)
+        self.device = torch.device(world._device or "cuda:%d" % torch.cuda.current_device())
+        self.cap = 0
+        self.C = world.tables.W * world.tables.H
+        self.cs = ((self.C + 63) // 64) * 64
+        self.nf = world.tables.n_features
+        self.K = world.tables.K
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _reserve(self, n):
+        if n <= self.cap:
+            return
+        torch = self.torch
+        cap = max(64, 1 << (n - 1).bit_length())
+        dev = self.device
+        self.h_grid = torch.zeros((cap, self.cs), dtype=torch.uint8).pin_memory()
+        self.h_agent = torch.zeros((cap, _lib.AGENT_BYTES), dtype=torch.uint8).pin_memory()
+        self.h_small = torch.zeros((4, cap), dtype=torch.uint8).pin_memory()   # action, task, expert, sat
+        self.h_feat = torch.zeros((cap, self.nf), dtype=torch.float32).pin_memory()
+        self.d_grid = torch.zeros((cap, self.cs), dtype=torch.uint8, device=dev)
+        self.d_agent = torch.zeros((cap, _lib.AGENT_BYTES), dtype=torch.uint8, device=dev)
+        self.d_small = torch.zeros((4, cap), dtype=torch.uint8, device=dev)
+        self.d_feat = torch.zeros((cap, self.nf), dtype=torch.float32, device=dev)
+        self.cap = cap
+
+    def evaluate(self, states, step=True):
+        """step=True: ``states`` are pending children (parent + action); computes their state.
+        Always computes features, teacher action and satisfies for each state's hinted task."""
+        import ctypes
+        torch = self.torch
+        if step:
+            # parents may themselves be pending only if they are in the same queue *earlier*:
+            # resolve generations in order
+            order, rest = [], states
+            while rest:
+                ready = [s for s in rest if s._parent._cells is not None]
+                if not ready:
+                    raise _lib.PskError("dangling pending state")
+                self._run(ready, True)
+                rest = [s for s in rest if s._cells is None]
+                order += ready
+            return
+        self._run(states, False)
+
+    def _run(self, states, step):
+        import ctypes
+        torch = self.torch
+        n = len(states)
+        self._reserve(n)
+        hg, ha, hs = self.h_grid.numpy(), self.h_agent.numpy(), self.h_small.numpy()
+        for i, s in enumerate(states):
+            src = s._parent if step else s
+            hg[i, :self.C] = src._cells
+            ha[i] = src._agent
+            hs[0, i] = s._action if step else STOP
+            hs[1, i] = s._task_hint
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            self.d_grid[:n].copy_(self.h_grid[:n], non_blocking=True)
+            self.d_agent[:n].copy_(self.h_agent[:n], non_blocking=True)
+            self.d_small[:2, :n].copy_(self.h_small[:2, :n], non_blocking=True)
+            st = _lib.CraftStateC(self.d_grid.data_ptr(), self.d_agent.data_ptr(), n, self.cs, 0)
+            tb = ctypes.byref(self.ct)
+            p = lambda t: ctypes.c_void_p(t.data_ptr())
+            if step:
+                _lib.check(self.lib.psk_craft_step(tb, st, p(self.d_small[0]), None, None,
+                                                   p(self.err), stream), "psk_craft_step")
+            _lib.check(self.lib.psk_craft_features(tb, st, p(self.d_feat), 0, stream),
+                       "psk_craft_features")
+            _lib.check(self.lib.psk_craft_expert(tb, st, p(self.d_small[1]), p(self.d_small[2]),
+                                                 None, None, stream), "psk_craft_expert")
+            _lib.check(self.lib.psk_craft_satisfies(tb, st, p(self.d_small[1]), p(self.d_small[3]),
+                                                    stream), "psk_craft_satisfies")
+            if step:
+                self.h_grid[:n].copy_(self.d_grid[:n], non_blocking=True)
+                self.h_agent[:n].copy_(self.d_agent[:n], non_blocking=True)
+            self.h_small[2:, :n].copy_(self.d_small[2:, :n], non_blocking=True)
+            self.h_feat[:n].copy_(self.d_feat[:n], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        hf = self.h_feat.numpy()
+        for i, s in enumerate(states):
+            if step:
+                parent = s._parent
+                cells = hg[i, :self.C]
+                s._cells = parent._cells if np.array_equal(cells, parent._cells) else cells.copy()
+                if s._cells is parent._cells:
+                    s._grid = parent._grid
+                s._agent = ha[i].copy()
+                s._parent = None
+            s._cached_features = hf[i].astype(np.float64)
+            if s._task_hint:
+                s._expert[s._task_hint] = int(hs[2, i])
+                s._sat[s._task_hint] = int(hs[3, i])
+            s._evaluated = True

@@ -250,3 +250,30 @@ def test_full_size_properties(splits, medium_tables, medium_oracle):
     ref_len = splits["train_ref_len"][idx].astype(np.int64)
     assert st[0] == int((100 // ref_len).sum())
     env.check_errors()
+
+
+def test_host_buffer_tick_matches_oracle(splits, medium_tables, medium_oracle):
+    """psk_craft_host_tick: host (pinned numpy) buffers in and out, chunked over streams."""
+    from psketch_b200.host import HostCraft
+    n = 5003
+    idx = np.arange(n) % 2200
+    grids = splits["dev_grids"]
+    ienv, ipos, itask = (splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
+                         splits["dev_inst_task"][idx])
+    env = HostCraft(medium_tables, grids, ienv, ipos, itask, max_timesteps=40, chunk_envs=1024)
+    init_grid = grids[ienv.astype(np.int64)]
+    state = None
+    tot = np.zeros(4, np.int64)
+    for t in range(30):
+        env.tick()
+        state, stats, feats, act = medium_oracle.rollout(
+            1, 40, init_grid, ipos.astype(np.int32), itask.astype(np.int32), state=state,
+            want_features=True)
+        tot += stats
+        assert np.array_equal(env.expert.astype(np.int32), act), t
+        assert np.array_equal(env.features, feats), t
+        assert np.array_equal(env.grid[:, :64], state["grid"]), t
+        assert np.array_equal(env.agent[:, :21].astype(np.int32), state["inv"]), t
+        assert np.array_equal(env.agent[:, 24:26].astype(np.int32), state["pos"]), t
+    assert int(env.stats[0]) == tot[0] and int(env.stats[1]) == tot[1]
+    env.close()
