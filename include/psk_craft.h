@@ -144,6 +144,24 @@ int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episo
                    uint8_t *done_out, uint8_t *success_out, unsigned long long *stats,
                    int32_t *err_flags, int fused, void *stream);
 
+/* Scenario sampling (make_data.py:74-144, `random_free` / `sample_scenario`) with a counter-based
+ * Philox4x32-10 generator: boundary ring, then place_kinds[0..n_place) in order, then the agent,
+ * each at a uniformly random free cell that keeps all free cells connected and every occupied
+ * interior cell next to a free cell.  scen_grid u8[n][cell_stride], init_pos u8[n][2];
+ * *fail_count (device, may be NULL) counts scenarios that ran out of draws.  Scenario i uses the
+ * Philox stream (seed, i + offset): results do not depend on the launch geometry or the GPU. */
+int psk_craft_sample_scenarios(const psk_craft_tables *t, uint8_t *scen_grid, uint8_t *init_pos,
+                               const uint8_t *place_kinds, int32_t n_place, int32_t boundary_kind,
+                               uint64_t seed, uint64_t offset, int64_t n, int32_t cell_stride,
+                               int32_t *fail_count, void *stream);
+
+/* Dataset instance positions (make_data.py:203-208): per group, `per_group` distinct uniformly
+ * random free cells of scenario group_scen[g]; out_pos u8[n_groups][per_group][2]. */
+int psk_craft_sample_positions(const psk_craft_tables *t, const uint8_t *scen_grid,
+                               const int32_t *group_scen, int32_t per_group, uint8_t *out_pos,
+                               uint64_t seed, uint64_t offset, int64_t n_groups,
+                               int32_t cell_stride, int32_t *fail_count, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points: the caller keeps its environments in HOST memory, as the reference
  * does (every CraftState is a CPU object).  All pointers below are HOST pointers; pass pinned

@@ -16,6 +16,8 @@ Outputs (all numpy .npz, compressed):
   ``step_*`` for all six actions, ``satisfies`` for every task id (0 False, 1 True, 2 None),
   ``expert`` for every task id (0..5, 255 AssertionError, 254 TypeError), ``closest_*`` from
   find_closest_resources for every kind that has a go[...] task.
+* sampler_stats.npz — cell-occupancy statistics of 3,000 scenarios drawn by the reference's own
+  sampler (make_data.py:105-144), the yardstick for the Philox sampler kernel.
 * light_states.npz — Light world scenarios for the 10 goals of resources/light/hints.yaml with
   random-action rollouts: walls, doors, keys, pos -> features f32[12], step results, satisfies.
 """
@@ -317,8 +319,48 @@ def export_light(R, path, seed=7):
           "max doors", o["n_doors"].max(), "max keys", o["n_keys"].max())
 
 
+def export_sampler_stats(R, path, n_scen=3000, seed=4242):
+    """Runs the reference's own sampler (make_data.py:27-144: all_free_cells_reachable,
+    random_free, sample_scenario — the function definitions are exec'ed from the source text, the
+    module-level dataset script after them is not) and stores the cell-occupancy statistics."""
+    src = open(os.path.join(ref_shim.REF_ROOT, "make_data.py")).read()
+    head = src[:src.index("config = flags.make_config()")]
+    head = head.replace("import flags", "").replace("import models", "")
+    ns = {"__name__": "__make_data_defs__"}
+    with ref_shim.reference_cwd():
+        exec(compile(head, "make_data_defs", "exec"), ns)
+    world = R.world
+    ns["world"] = world                       # all_free_cells_reachable reads the global
+    cfg = R.config
+    cfg.random = np.random.RandomState(seed)
+    W, H, K = world.WIDTH, world.HEIGHT, world.cookbook.n_kinds
+    kind_cell = np.zeros((K, W, H), np.int64)
+    pos_cell = np.zeros((W, H), np.int64)
+    n_free_nbr = np.zeros(5, np.int64)        # free 4-neighbours of placed items
+    grids = []
+    for i in range(n_scen):
+        grid, init_pos = ns["sample_scenario"](world, None, cfg)
+        ids = to_ids(grid)
+        for k in range(2, K):
+            kind_cell[k] += ids == k
+        pos_cell[init_pos] += 1
+        for x, y in np.argwhere((ids > 1)):
+            nb = sum(ids[x + dx, y + dy] == 0 for dx, dy in ((0, 1), (0, -1), (1, 0), (-1, 0)))
+            n_free_nbr[nb] += 1
+        if i < 64:
+            grids.append(ids.reshape(-1))
+        if i % 500 == 0:
+            print("  sampled", i, flush=True)
+    np.savez_compressed(path, n_scen=np.int64(n_scen), kind_cell=kind_cell, pos_cell=pos_cell,
+                        n_free_nbr=n_free_nbr, example_grids=np.stack(grids))
+    print("wrote", path)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--sampler-only" in sys.argv:
+        export_sampler_stats(ref_shim.Reference(), os.path.join(OUT, "sampler_stats.npz"))
+        return
     regen_dir = os.environ.get("PSK_REGEN_DIR", "/tmp/psk_data")
     if not os.path.exists(os.path.join(regen_dir, "craft_medium_train.json")):
         print("regenerating the dataset with the reference's make_data.py (~30 s)")
@@ -331,6 +373,7 @@ def main():
     states = collect_states(RL, None, 0, 0, 2500, seed=99)
     export_states(RL, states, os.path.join(OUT, "craft_large_states.npz"))
     export_light(R, os.path.join(OUT, "light_states.npz"))
+    export_sampler_stats(ref_shim.Reference(), os.path.join(OUT, "sampler_stats.npz"))
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libpsk_b200.so")
-SOURCES = ["psk_craft.cu", "psk_light.cu", "psk_host.cu"]
+SOURCES = ["psk_craft.cu", "psk_scenario.cu", "psk_light.cu", "psk_host.cu"]
 HEADERS = ["psk_common.cuh", os.path.join("..", "..", "include", "psk_craft.h"),
            os.path.join("..", "..", "include", "psk_light.h")]
 

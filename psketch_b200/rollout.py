@@ -1,0 +1,95 @@
+"""Batched rollout drivers: the per-env Python loops of the trainers
+(trainers/imitation.py:18-101, make_data.py:146-152) as a handful of device launches per
+timestep, with the bookkeeping (timer / done / success / action sequences / distances) kept in
+tensors."""
+import numpy as np
+import torch
+
+from .tables import STOP
+
+
+def teacher_rollouts(env, max_len=64):
+    """make_data.py:146-152 for every env at once: follow the teacher until it says STOP.
+    Returns (ref_actions u8[N, L] padded with 255, ref_len i32[N], satisfied bool[N])."""
+    n = env.n
+    env.reset()
+    alive = torch.ones(n, dtype=torch.uint8, device=env.device)
+    acts = torch.full((n, max_len), 255, dtype=torch.uint8, device=env.device)
+    length = torch.zeros(n, dtype=torch.int32, device=env.device)
+    ok = torch.zeros(n, dtype=torch.bool, device=env.device)
+    for t in range(max_len):
+        a = env.expert()
+        live = alive.bool()
+        acts[:, t] = torch.where(live, a, acts[:, t])
+        length += live.to(torch.int32)
+        stop = live & (a == STOP)
+        if bool(stop.any()):
+            ok |= stop & (env.satisfies() == 1)
+        alive = (live & ~stop).to(torch.uint8)
+        if not bool(alive.any()):
+            break
+        env.step(a, active=alive)
+    env.check_errors()
+    L = int(length.max().item())
+    return acts[:, :L].cpu().numpy(), length.cpu().numpy(), ok.cpu().numpy()
+
+
+def policy_rollouts(env, policy, max_timesteps=40, is_eval=True, mix=None):
+    """trainers/imitation.py:18-101 for every env at once.
+
+    ``policy(features f32[N, n_features], t) -> actions (uint8 tensor [N])`` plays the student;
+    when ``is_eval`` is False the teacher is queried every step (``ref_actions``) and ``mix``
+    (bool tensor [N] or None) marks the envs that follow the teacher (behaviour cloning).
+    Returns dict(action_seqs, ref_seqs, success, distances, num_steps, num_interactions) with the
+    reference's meanings; distances: for failed get-tasks the teacher's path length from the final
+    pose on the ORIGINAL grid (imitation.py:83-91), 0 for successful ones, -1 for other tasks."""
+    from . import _lib
+    n = env.n
+    dev = env.device
+    env.reset()
+    env.timer.fill_(255)                      # the loop below keeps its own timer, like the trainer
+    timer = torch.full((n,), max_timesteps, dtype=torch.int32, device=dev)
+    done = torch.zeros(n, dtype=torch.bool, device=dev)
+    success = torch.zeros(n, dtype=torch.bool, device=dev)
+    acts = torch.full((n, max_timesteps), 255, dtype=torch.uint8, device=dev)
+    refs = torch.full((n, max_timesteps), 255, dtype=torch.uint8, device=dev)
+    feats = torch.empty((n, env.n_features), dtype=torch.float32, device=dev)
+    num_steps = num_inter = 0
+    t = 0
+    while not bool(done.all()):
+        env.features(out=feats)
+        a = policy(feats, t).to(device=dev, dtype=torch.uint8)
+        if not is_eval:
+            ref = env.expert()
+            refs[:, t] = torch.where(done, refs[:, t], ref)
+            num_inter += int((~done).sum())
+            if mix is not None:
+                a = torch.where(mix & ~done, ref, a)
+        acts[:, t] = torch.where(done, acts[:, t], a)
+        timer -= 1
+        newly = ~done & ((a == STOP) | (timer <= 0))
+        if bool(newly.any()):
+            success |= newly & (env.satisfies() == 1)
+        done |= newly
+        active = (~done).to(torch.uint8)
+        env.step(a, active=active)
+        num_steps += int(active.sum()) * (not is_eval)
+        t += 1
+    env.check_errors()
+    # distances for get-tasks that failed: closest resource from the final pose, original grid
+    tm = env.tables.task_manager
+    is_get = torch.from_numpy(env.tables.task_is_get.astype(np.bool_)).to(dev)[env.task.long()]
+    goal_kind = torch.from_numpy(np.asarray(
+        [0] + [env.tables.cookbook.index[tm.by_id(i).goal_arg] or 0 for i in range(1, len(tm.tasks))],
+        np.uint8)).to(dev)[env.task.long()]
+    final_agent = env.agent.clone()
+    final_grid = env.grid.clone()
+    env.grid.copy_(env.scen_grid[env.scen_idx.long()])
+    _, length, _ = env.find_closest(goal_kind)
+    env.grid.copy_(final_grid)
+    env.agent.copy_(final_agent)
+    dist = torch.where(is_get, torch.where(success, torch.zeros_like(length), length),
+                       torch.full_like(length, -1))
+    return dict(action_seqs=acts.cpu().numpy(), ref_seqs=refs.cpu().numpy(),
+                success=success.cpu().numpy(), distances=dist.cpu().numpy(),
+                num_steps=num_steps, num_interactions=num_inter, timesteps=t)
