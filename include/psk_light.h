@@ -1,0 +1,59 @@
+/*
+ * psk_light.h — C ABI of the batched Light world (rooms / doors / keys), worlds/light.py.
+ *
+ * Replaces, for N environments per launch: LightState.step (worlds/light.py:212-235),
+ * LightState.features (:191-204), LightState.satisfies (:208-210) and LightScenario.init
+ * (:175-180).  The reference has no teacher for this world; psk_light_expert is specified here
+ * (shortest action sequence over (position, remaining keys) to the goal room, ties broken by
+ * the smallest action index) and validated against a brute-force search, not against psketch.
+ *
+ * Same conventions as psk_craft.h: DEVICE pointers, void* cudaStream_t, int status codes.
+ * Scenario tables are shared between environments (scen_idx selects one per env).
+ */
+#ifndef PSK_LIGHT_H
+#define PSK_LIGHT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSK_LIGHT_MAX_BOARD 32
+#define PSK_LIGHT_MAX_DOORS 8
+#define PSK_LIGHT_MAX_KEYS 8
+#define PSK_LIGHT_N_FEATURES 12
+#define PSK_LIGHT_N_ACTIONS 5 /* DOWN, UP, LEFT, RIGHT, USE */
+#define PSK_LIGHT_ROOM 6      /* ROOM_W = ROOM_H = 6, worlds/light.py:11-12 */
+
+/* One scenario (LightScenario, worlds/light.py:163-173), 192 bytes. */
+typedef struct psk_light_scenario {
+    uint32_t walls[PSK_LIGHT_MAX_BOARD];   /* row x: bit y set = wall (cells beyond the board are walls) */
+    uint8_t doors[PSK_LIGHT_MAX_DOORS][2]; /* x, y */
+    uint8_t keys[PSK_LIGHT_MAX_KEYS][4];   /* key x, key y, door x, door y (the scenario's initial key set) */
+    uint8_t n_doors, n_keys, board_w, board_h;
+    uint8_t goal_rx, goal_ry, init_x, init_y;
+    uint8_t reserved[8];
+} psk_light_scenario;
+
+/* Per-env state u8[n][4]: x, y, bitmask of keys still on the map, reserved. */
+#define PSK_LIGHT_STATE_BYTES 4
+
+int psk_light_reset(const psk_light_scenario *scen, const int32_t *scen_idx, uint8_t *state,
+                    const uint8_t *mask, int64_t n, void *stream);
+int psk_light_step(const psk_light_scenario *scen, const int32_t *scen_idx, uint8_t *state,
+                   const uint8_t *action, const uint8_t *active, float *reward,
+                   int32_t *err_flags, int64_t n, void *stream);
+int psk_light_features(const psk_light_scenario *scen, const int32_t *scen_idx,
+                       const uint8_t *state, float *out, int64_t n, void *stream);
+int psk_light_satisfies(const psk_light_scenario *scen, const int32_t *scen_idx,
+                        const uint8_t *state, uint8_t *out, int64_t n, void *stream);
+/* action u8[n] (255 = goal room unreachable, 254 = already in the goal room), dist i16[n]. */
+int psk_light_expert(const psk_light_scenario *scen, const int32_t *scen_idx,
+                     const uint8_t *state, uint8_t *action, int16_t *dist, int64_t n,
+                     void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSK_LIGHT_H */

@@ -100,6 +100,28 @@ def load():
     return lib
 
 
+LIGHT_EXPORTS = ("psk_light_reset", "psk_light_step", "psk_light_features", "psk_light_satisfies",
+                 "psk_light_expert")
+_light_bound = False
+
+
+def load_light():
+    """Binds the psk_light.h entry points (same shared library)."""
+    global _light_bound
+    lib = load()
+    if not _light_bound:
+        vp, i64 = ctypes.c_void_p, ctypes.c_int64
+        lib.psk_light_reset.argtypes = [vp, vp, vp, vp, i64, vp]
+        lib.psk_light_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp]
+        lib.psk_light_features.argtypes = [vp, vp, vp, vp, i64, vp]
+        lib.psk_light_satisfies.argtypes = [vp, vp, vp, vp, i64, vp]
+        lib.psk_light_expert.argtypes = [vp, vp, vp, vp, vp, i64, vp]
+        for name in LIGHT_EXPORTS:
+            getattr(lib, name).restype = ctypes.c_int
+        _light_bound = True
+    return lib
+
+
 def check(rc, what):
     if rc == PSK_OK:
         return

@@ -1,0 +1,315 @@
+// psk_light.cu — batched Light world (worlds/light.py): step, features, satisfies, reset, and a
+// warp-cooperative shortest-path teacher over (position, remaining keys).
+#include "psk_common.cuh"
+#include "../../include/psk_light.h"
+
+namespace psk {
+
+__device__ __forceinline__ bool light_wall(const psk_light_scenario &s, int x, int y) {
+    if (x < 0 || y < 0 || x >= PSK_LIGHT_MAX_BOARD || y >= PSK_LIGHT_MAX_BOARD) return true;
+    return (s.walls[x] >> y) & 1;
+}
+
+// is (x, y) a door whose key is still on the map?  (worlds/light.py:233)
+__device__ __forceinline__ bool light_locked_door(const psk_light_scenario &s, int x, int y,
+                                                  uint32_t alive) {
+    bool is_door = false;
+    for (int d = 0; d < s.n_doors; d++) is_door |= (s.doors[d][0] == x && s.doors[d][1] == y);
+    if (!is_door) return false;
+    for (int k = 0; k < s.n_keys; k++)
+        if (((alive >> k) & 1) && s.keys[k][2] == x && s.keys[k][3] == y) return true;
+    return false;
+}
+
+__global__ void __launch_bounds__(256)
+light_reset_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
+                   uint8_t *__restrict__ state, const uint8_t *__restrict__ mask, int64_t n) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[e]) continue;
+        const psk_light_scenario &s = scen[scen_idx[e]];
+        // LightScenario.init: centre of the initial room, every key on the map (light.py:175-180)
+        const uint32_t alive = s.n_keys >= 8 ? 0xFFu : ((1u << s.n_keys) - 1u);
+        reinterpret_cast<uint32_t *>(state)[e] = uint32_t(s.init_x) | (uint32_t(s.init_y) << 8) | (alive << 16);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+light_step_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
+                  uint8_t *__restrict__ state, const uint8_t *__restrict__ action,
+                  const uint8_t *__restrict__ active, float *__restrict__ reward,
+                  int32_t *err_flags, int64_t n) {
+    uint32_t flags = 0;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        if (reward) reward[e] = 0.0f;                       // light.py:235
+        if (active && !active[e]) continue;
+        const psk_light_scenario &s = scen[scen_idx[e]];
+        const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
+        const int x = st & 0xFF, y = (st >> 8) & 0xFF;
+        const uint32_t alive = (st >> 16) & 0xFF;
+        uint32_t n_alive = alive;
+        const int a = action[e];
+        int dx = 0, dy = 0;
+        if (a < 4) {                                        // light.py:216-223
+            dx = dx_of(a);
+            dy = dy_of(a);
+        } else if (a == 4) {                                // USE: pick up the key underfoot (:224-228)
+            for (int k = 0; k < s.n_keys; k++)
+                if (((alive >> k) & 1) && s.keys[k][0] == x && s.keys[k][1] == y) n_alive &= ~(1u << k);
+        } else {
+            flags |= PSK_FLAG_BAD_ACTION;                   // the reference fails with UnboundLocalError
+            continue;
+        }
+        int nx = x + dx, ny = y + dy;
+        if (light_wall(s, nx, ny)) { nx = x; ny = y; }      // light.py:231-232
+        // doors are tested against the keys BEFORE this step's pick-up (light.py:233 uses self.keys)
+        if (light_locked_door(s, nx, ny, alive)) { nx = x; ny = y; }
+        reinterpret_cast<uint32_t *>(state)[e] = uint32_t(nx) | (uint32_t(ny) << 8) | (n_alive << 16);
+    }
+    if (flags && err_flags) atomicOr(err_flags, (int)flags);
+}
+
+// worlds/light.py:191-204 with the precomputed maps of :105-146.  `strength //= 10` leaves 1.0
+// only at distance 0, so a door/key contributes (1,1,1,1) exactly when the agent stands on it:
+// locked doors -> out[0:4], open doors -> out[4:8], keys still on the map -> out[8:12].
+__global__ void __launch_bounds__(256)
+light_features_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
+                      const uint8_t *__restrict__ state, float *__restrict__ out, int64_t n) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const psk_light_scenario &s = scen[scen_idx[e]];
+        const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
+        const int x = st & 0xFF, y = (st >> 8) & 0xFF;
+        const uint32_t alive = (st >> 16) & 0xFF;
+        float locked = 0.f, open = 0.f, key = 0.f;
+        for (int d = 0; d < s.n_doors; d++) {
+            if (s.doors[d][0] != x || s.doors[d][1] != y) continue;
+            bool lk = false;
+            for (int k = 0; k < s.n_keys; k++)
+                lk |= ((alive >> k) & 1) && s.keys[k][2] == x && s.keys[k][3] == y;
+            if (lk) locked += 1.f; else open += 1.f;
+        }
+        for (int k = 0; k < s.n_keys; k++)
+            if (((alive >> k) & 1) && s.keys[k][0] == x && s.keys[k][1] == y &&
+                x % PSK_LIGHT_ROOM != 0 && y % PSK_LIGHT_ROOM != 0)
+                key += 1.f;
+        float4 *o = reinterpret_cast<float4 *>(out + e * PSK_LIGHT_N_FEATURES);
+        o[0] = make_float4(locked, locked, locked, locked);
+        o[1] = make_float4(open, open, open, open);
+        o[2] = make_float4(key, key, key, key);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+light_satisfies_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
+                       const uint8_t *__restrict__ state, uint8_t *__restrict__ out, int64_t n) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const psk_light_scenario &s = scen[scen_idx[e]];
+        const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
+        const int x = st & 0xFF, y = (st >> 8) & 0xFF;
+        out[e] = (x / PSK_LIGHT_ROOM == s.goal_rx) && (y / PSK_LIGHT_ROOM == s.goal_ry);   // light.py:208-210
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Teacher (specified here; the reference has none for this world): fewest actions from
+// (pos, keys) to any cell of the goal room, where a move costs 1 and picking up a key (USE on the
+// key's cell) costs 1 and unlocks its door; the first action of the best plan, ties -> smallest
+// action index (DOWN, UP, LEFT, RIGHT, USE).
+//
+// One WARP per env.  Lane x holds row x of every board as a 32-bit word (boards are <= 31 x 31):
+// vertical moves are bit shifts inside the lane, horizontal moves are __shfl_up/down_sync between
+// lanes, emptiness tests are __ballot_sync.  The search runs BACKWARD from the goal room over the
+// layers "key subset still on the map" (<= 2^n_keys layers, kept in shared memory): R[m] = cells
+// from which the goal is reachable within the current number of steps when the keys in m are still
+// lying around.  A level adds to R[m]: the passable neighbours of R[m] (a move), and every key
+// cell k in m whose lower layer R[m \ {k}] already contains it (USE).  The first level at which
+// the agent's cell enters R[alive] is the distance; the action is the smallest a whose successor
+// state was in R one level earlier.
+constexpr int LIGHT_MAX_LAYERS = 1 << PSK_LIGHT_MAX_KEYS;
+
+__global__ void __launch_bounds__(128)
+light_expert_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
+                    const uint8_t *__restrict__ state, uint8_t *__restrict__ action,
+                    int16_t *__restrict__ dist_out, int64_t n) {
+    extern __shared__ uint32_t s_layers[];          // [warps][2][n_layers_cap][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    constexpr unsigned FULL = 0xffffffffu;
+    for (int64_t e = blockIdx.x * (int64_t)wpb + warp; e < n; e += (int64_t)gridDim.x * wpb) {
+        const psk_light_scenario &s = scen[scen_idx[e]];
+        const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
+        const int px = st & 0xFF, py = (st >> 8) & 0xFF;
+        const uint32_t alive = (st >> 16) & 0xFF;
+        const int nk = s.n_keys;
+        const int n_layers = 1 << nk;
+        uint32_t *R = s_layers + (size_t)warp * 2 * LIGHT_MAX_LAYERS * 32;   // reached so far
+        uint32_t *P = R + LIGHT_MAX_LAYERS * 32;                             // reached one level earlier
+        const uint32_t wall_row = s.walls[lane];
+        // goal room rows / cells
+        uint32_t goal_row = 0;
+        if (lane / PSK_LIGHT_ROOM == s.goal_rx)
+            goal_row = (0x3Fu << (s.goal_ry * PSK_LIGHT_ROOM)) & ~wall_row;
+        // locked-door cells per layer are recomputed on the fly: door d is locked in layer m if a
+        // key of m points at it
+        if (((py < 32) && ((__shfl_sync(FULL, goal_row, px & 31) >> py) & 1))) {
+            if (lane == 0) {
+                action[e] = 254;
+                if (dist_out) dist_out[e] = 0;
+            }
+            continue;
+        }
+        for (int m = 0; m < n_layers; m++) {
+            // a cell of the goal room that is a locked door in layer m cannot be stood on
+            uint32_t lockrow = 0;
+            for (int k = 0; k < nk; k++)
+                if (((m >> k) & 1) && s.keys[k][2] == lane) lockrow |= 1u << s.keys[k][3];
+            R[m * 32 + lane] = goal_row & ~lockrow;
+            P[m * 32 + lane] = 0;
+        }
+        __syncwarp();
+        int found = -1;
+        const int max_levels = 32 * 32 + 64;
+        for (int level = 1; level <= max_levels; level++) {
+            bool grew = false;
+            // only layers that are subsets of `alive` can be reached from the current state
+            for (int m = 0; m < n_layers; m++) {
+                if ((m & ~alive) != 0) continue;
+                uint32_t lockrow = 0;
+                for (int k = 0; k < nk; k++)
+                    if (((m >> k) & 1) && s.keys[k][2] == lane) lockrow |= 1u << s.keys[k][3];
+                const uint32_t pass = ~wall_row & ~lockrow;      // cells one may stand on in layer m
+                const uint32_t cur = R[m * 32 + lane];
+                P[m * 32 + lane] = cur;
+                // predecessors by a move: p -> p+delta in R, p itself passable (agent stands there)
+                const uint32_t up = __shfl_up_sync(FULL, cur, 1), dn = __shfl_down_sync(FULL, cur, 1);
+                uint32_t add = (cur << 1) | (cur >> 1) | (lane > 0 ? up : 0u) | (lane < 31 ? dn : 0u);
+                // predecessors by USE: standing on key k (in m) with R[m \ {k}] containing the cell
+                for (int k = 0; k < nk; k++) {
+                    if (!((m >> k) & 1)) continue;
+                    if (s.keys[k][0] == lane) {
+                        const uint32_t bit = 1u << s.keys[k][1];
+                        // lower layer as of the PREVIOUS level: layers are swept in increasing m and
+                        // m \ {k} < m was already advanced this level, so read its snapshot P
+                        if (P[(m & ~(1 << k)) * 32 + lane] & bit) add |= bit;
+                    }
+                }
+                const uint32_t nxt = cur | (add & pass);
+                R[m * 32 + lane] = nxt;
+                grew |= nxt != cur;
+            }
+            __syncwarp();
+            const uint32_t mine = __shfl_sync(FULL, R[alive * 32 + lane], px & 31);
+            if ((mine >> py) & 1) { found = level; break; }
+            if (!__any_sync(FULL, grew)) break;
+        }
+        if (found < 0) {
+            if (lane == 0) {
+                action[e] = 255;
+                if (dist_out) dist_out[e] = -1;
+            }
+            continue;
+        }
+        // first action: smallest a whose successor was reached one level earlier (snapshot P)
+        int best = 255;
+        if (lane == 0) {
+            for (int a = 0; a < 5 && best == 255; a++) {
+                int nx = px, ny = py;
+                uint32_t m2 = alive;
+                if (a < 4) {
+                    nx = px + dx_of(a);
+                    ny = py + dy_of(a);
+                    if (light_wall(s, nx, ny) || light_locked_door(s, nx, ny, alive)) continue;  // no progress
+                } else {
+                    for (int k = 0; k < nk; k++)
+                        if (((alive >> k) & 1) && s.keys[k][0] == px && s.keys[k][1] == py) m2 &= ~(1u << k);
+                    if (m2 == alive) continue;
+                }
+                const uint32_t *L = (found == 1) ? nullptr : P;
+                bool ok;
+                if (found == 1) {
+                    // successor must be in the goal room itself
+                    ok = (nx / PSK_LIGHT_ROOM == s.goal_rx) && (ny / PSK_LIGHT_ROOM == s.goal_ry);
+                } else {
+                    ok = (L[m2 * 32 + nx] >> ny) & 1;
+                }
+                if (ok) best = a;
+            }
+            action[e] = (uint8_t)best;
+            if (dist_out) dist_out[e] = (int16_t)found;
+        }
+        __syncwarp();
+    }
+}
+
+static inline int lblocks(int64_t n, int per) {
+    int64_t b = (n + per - 1) / per;
+    return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+}  // namespace psk
+
+using namespace psk;
+
+extern "C" {
+
+static int light_args_ok(const void *scen, const void *idx, const void *state, int64_t n) {
+    return n >= 0 && (n == 0 || (scen && idx && state));
+}
+
+int psk_light_reset(const psk_light_scenario *scen, const int32_t *scen_idx, uint8_t *state,
+                    const uint8_t *mask, int64_t n, void *stream) {
+    if (!light_args_ok(scen, scen_idx, state, n)) return PSK_ERR_BADARG;
+    if (n == 0) return PSK_OK;
+    light_reset_kernel<<<lblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(scen, scen_idx, state, mask, n);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+int psk_light_step(const psk_light_scenario *scen, const int32_t *scen_idx, uint8_t *state,
+                   const uint8_t *action, const uint8_t *active, float *reward,
+                   int32_t *err_flags, int64_t n, void *stream) {
+    if (!light_args_ok(scen, scen_idx, state, n) || (n && !action)) return PSK_ERR_BADARG;
+    if (n == 0) return PSK_OK;
+    light_step_kernel<<<lblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(scen, scen_idx, state, action,
+                                                                        active, reward, err_flags, n);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+int psk_light_features(const psk_light_scenario *scen, const int32_t *scen_idx,
+                       const uint8_t *state, float *out, int64_t n, void *stream) {
+    if (!light_args_ok(scen, scen_idx, state, n) || (n && !out)) return PSK_ERR_BADARG;
+    if (n == 0) return PSK_OK;
+    light_features_kernel<<<lblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(scen, scen_idx, state, out, n);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+int psk_light_satisfies(const psk_light_scenario *scen, const int32_t *scen_idx,
+                        const uint8_t *state, uint8_t *out, int64_t n, void *stream) {
+    if (!light_args_ok(scen, scen_idx, state, n) || (n && !out)) return PSK_ERR_BADARG;
+    if (n == 0) return PSK_OK;
+    light_satisfies_kernel<<<lblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(scen, scen_idx, state, out, n);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+int psk_light_expert(const psk_light_scenario *scen, const int32_t *scen_idx,
+                     const uint8_t *state, uint8_t *action, int16_t *dist, int64_t n,
+                     void *stream) {
+    if (!light_args_ok(scen, scen_idx, state, n) || (n && !action)) return PSK_ERR_BADARG;
+    if (n == 0) return PSK_OK;
+    const int wpb = 1;   // 2 x 256 layers x 32 rows x 4 B = 64 KB of shared memory per warp
+    const size_t smem = (size_t)wpb * 2 * LIGHT_MAX_LAYERS * 32 * sizeof(uint32_t);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(light_expert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return PSK_ERR_CUDA;
+        configured = true;
+    }
+    light_expert_kernel<<<lblocks(n, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(
+        scen, scen_idx, state, action, dist, n);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+}  // extern "C"
