@@ -438,6 +438,222 @@ craft_find_closest_kernel(const __grid_constant__ psk_craft_tables T,
 }
 
 // =============================================================================================
+// enlarged grids (W, H <= 32): one WARP per env, lane x = row x of every board as a 32-bit word
+// =============================================================================================
+// Same two floods as bfs_first_action, with the boards laid out row-per-lane: vertical moves
+// (y +- 1) are bit shifts inside a lane, horizontal moves (x +- 1) are __shfl_up/down_sync
+// between lanes, emptiness tests are __ballot_sync / __any_sync.  Every value is warp-uniform in
+// control flow, so there is no divergence at all; the reference's 1000-slot queue
+// (teachers/base.py:42) would overflow on these sizes, the floods have no such limit.
+template <int W, int H> struct Rows {
+    static_assert(W <= 32 && H <= 32, "row-per-lane boards cover up to 32 x 32");
+    static constexpr unsigned FULL = 0xffffffffu;
+    static constexpr uint32_t HMASK = H == 32 ? 0xffffffffu : ((1u << (H % 32)) - 1u);
+    // positions p + delta(A) for p in v
+    template <int A> static __device__ __forceinline__ uint32_t shift(uint32_t v, int lane) {
+        if (A == 0) return v >> 1;                               // DOWN  (0,-1)
+        if (A == 1) return (v << 1) & HMASK;                     // UP    (0,+1)
+        if (A == 2) {                                            // LEFT  (-1,0): row x <- row x+1
+            const uint32_t t = __shfl_down_sync(FULL, v, 1);
+            return lane < W - 1 ? t : 0u;
+        }
+        const uint32_t t = __shfl_up_sync(FULL, v, 1);           // RIGHT (+1,0): row x <- row x-1
+        return (lane > 0 && lane < W) ? t : 0u;
+    }
+    template <int A> static __device__ __forceinline__ uint32_t unshift(uint32_t v, int lane) {
+        return shift<(A ^ 1)>(v, lane);
+    }
+    static __device__ __forceinline__ uint32_t spread(uint32_t v, int lane) {
+        return shift<0>(v, lane) | shift<1>(v, lane) | shift<2>(v, lane) | shift<3>(v, lane);
+    }
+};
+
+// occupancy / goal row of this lane's row from the env's grid row (global memory)
+template <int W, int H>
+__device__ __forceinline__ void build_rows(const uint8_t *row, int lane, int goal_kind,
+                                           uint32_t &occ, uint32_t &goal) {
+    occ = 0;
+    goal = 0;
+    if (lane < W) {
+        const uint8_t *p = row + lane * H;
+        if (H % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < H / 4; i++) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(p + 4 * i);
+                const uint32_t nz = nonzero_flags(w);
+                const uint32_t eq = nonzero_flags(w ^ (uint32_t(goal_kind) * 0x01010101u)) ^ 0x80808080u;
+                occ |= ((nz * 0x00204081u) >> 28) << (4 * i);
+                goal |= ((eq * 0x00204081u) >> 28) << (4 * i);
+            }
+        } else {
+            for (int y = 0; y < H; y++) {
+                const int k = p[y];
+                occ |= uint32_t(k != 0) << y;
+                goal |= uint32_t(k == goal_kind) << y;
+            }
+        }
+    } else {
+        occ = Rows<W, H>::HMASK;   // rows beyond the grid are solid
+    }
+    if (goal_kind == 0) goal = 0;
+}
+
+// Warp-cooperative twin of bfs_first_action.  All lanes return the same values.
+template <int W, int H>
+__device__ __forceinline__ int bfs_rows(bool need, uint32_t occ, uint32_t goal, int px, int py,
+                                        int d0, int lane, int &first, int &gx, int &gy) {
+    using R = Rows<W, H>;
+    constexpr unsigned FULL = R::FULL;
+    const uint32_t freeb = ~occ & R::HMASK & (lane < W ? 0xffffffffu : 0u);
+    const uint32_t root = lane == px ? (1u << py) : 0u;
+    first = -1;
+    gx = gy = -1;
+    {   // depth 0: already facing a goal cell
+        const int fx = px + dx_of(d0), fy = py + dy_of(d0);
+        const bool in = fx >= 0 && fy >= 0 && fx < W && fy < H;
+        const uint32_t grow = __shfl_sync(FULL, goal, in ? fx : 0);
+        if (need && in && ((grow >> fy) & 1)) {
+            gx = fx;
+            gy = fy;
+            return 0;
+        }
+    }
+    const uint32_t T0 = R::template unshift<0>(goal, lane), T1 = R::template unshift<1>(goal, lane),
+                   T2 = R::template unshift<2>(goal, lane), T3 = R::template unshift<3>(goal, lane);
+    const uint32_t src_all = T0 | T1 | T2 | T3 | R::template unshift<0>(freeb & T0, lane) |
+                             R::template unshift<1>(freeb & T1, lane) |
+                             R::template unshift<2>(freeb & T2, lane) |
+                             R::template unshift<3>(freeb & T3, lane);
+    if (!need || !__any_sync(FULL, goal != 0)) return -1;
+    uint32_t VF = root;
+    int k = 0;
+    while (!__any_sync(FULL, (VF & src_all) != 0)) {
+        const uint32_t nv = VF | (R::spread(VF, lane) & freeb);
+        if (!__any_sync(FULL, nv != VF)) return -1;          // queue drained (base.py:87)
+        VF = nv;
+        k++;
+    }
+    const uint32_t hit =
+        (R::template shift<0>(VF & T0, lane) | R::template shift<1>(VF & T1, lane) |
+         R::template shift<2>(VF & T2, lane) | R::template shift<3>(VF & T3, lane) |
+         R::template shift<0>(R::template shift<0>(VF, lane) & freeb & T0, lane) |
+         R::template shift<1>(R::template shift<1>(VF, lane) & freeb & T1, lane) |
+         R::template shift<2>(R::template shift<2>(VF, lane) & freeb & T2, lane) |
+         R::template shift<3>(R::template shift<3>(VF, lane) & freeb & T3, lane)) & goal;
+    // lowest cell index x*H + y: lowest row with a hit, lowest bit in it (np.nonzero order)
+    gx = __ffs(__ballot_sync(FULL, hit != 0)) - 1;
+    gy = __ffs(__shfl_sync(FULL, hit, gx)) - 1;
+    const uint32_t g = lane == gx ? (1u << gy) : 0u;
+    const uint32_t g0 = R::template unshift<0>(g, lane), g1 = R::template unshift<1>(g, lane),
+                   g2 = R::template unshift<2>(g, lane), g3 = R::template unshift<3>(g, lane);
+    const uint32_t s0 = g0 | R::template unshift<0>(freeb & g0, lane),
+                   s1 = g1 | R::template unshift<1>(freeb & g1, lane),
+                   s2 = g2 | R::template unshift<2>(freeb & g2, lane),
+                   s3 = g3 | R::template unshift<3>(freeb & g3, lane);
+    if (k == 0) {
+        first = __any_sync(FULL, (root & s0) != 0) ? 0 : __any_sync(FULL, (root & s1) != 0) ? 1
+              : __any_sync(FULL, (root & s2) != 0) ? 2 : 3;
+        return 1;
+    }
+    uint32_t VB = (s0 | s1 | s2 | s3) & VF;
+    for (int j = 1; j < k; j++) VB |= R::spread(VB, lane) & freeb;
+    const uint32_t ok = VB & freeb;
+    first = __any_sync(FULL, (R::template shift<0>(root, lane) & ok) != 0)   ? 0
+            : __any_sync(FULL, (R::template shift<1>(root, lane) & ok) != 0) ? 1
+            : __any_sync(FULL, (R::template shift<2>(root, lane) & ok) != 0) ? 2
+                                                                              : 3;
+    return k + 1;
+}
+
+template <int W, int H>
+__global__ void __launch_bounds__(128)
+craft_expert_rows_kernel(const __grid_constant__ psk_craft_tables T, const uint8_t *__restrict__ grid,
+                         const uint8_t *__restrict__ agent, const uint8_t *__restrict__ task,
+                         uint8_t *__restrict__ action, int16_t *__restrict__ dist_out,
+                         int32_t *err_flags, int64_t n, int cell_stride) {
+    __shared__ SharedTables st;
+    stage_tables(st, T);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    uint32_t flags = 0;
+    for (int64_t e = blockIdx.x * (int64_t)wpb + warp; e < n; e += (int64_t)gridDim.x * wpb) {
+        const Agent a = load_agent_ro(agent, e);
+        const uint8_t *row = grid + e * cell_stride;
+        const int tk = task ? task[e] : a.task();
+        const int facing = facing_kind<W, H>(a, row);
+        const uint32_t leaf = find_incomplete(st, tk, a, facing);
+        const int kind = (leaf >> 16) & 0x7F;
+        const bool need = leaf && kind == LEAF_GO;
+        uint32_t occ, goal;
+        build_rows<W, H>(row, lane, need ? (leaf >> 8) & 0xFF : 0, occ, goal);
+        int first, gx, gy;
+        const int d = bfs_rows<W, H>(need, occ, goal, a.x(), a.y(), a.dir(), lane, first, gx, gy);
+        int act;
+        if (!leaf) act = PSK_ACT_STOP;
+        else if (kind == LEAF_USE) act = PSK_ACT_USE;
+        else if (kind != LEAF_GO) { act = PSK_ACT_INVALID; flags |= PSK_FLAG_BAD_LEAF; }
+        else if (d < 0) act = PSK_ACT_STOP;
+        else act = first >= 0 ? first : PSK_ACT_INVALID;
+        if (lane == 0) {
+            action[e] = (uint8_t)act;
+            if (dist_out) dist_out[e] = (int16_t)(need ? d : -1);
+        }
+    }
+    if (flags && err_flags && lane == 0) atomicOr(err_flags, (int)flags);
+}
+
+template <int W, int H>
+__global__ void __launch_bounds__(128)
+craft_find_closest_rows_kernel(const uint8_t *__restrict__ grid, const uint8_t *__restrict__ agent,
+                               const uint8_t *__restrict__ kind, uint8_t *__restrict__ goal_out,
+                               int16_t *__restrict__ len_out, uint8_t *__restrict__ seq,
+                               int seq_cap, int64_t n, int cell_stride) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int64_t e = blockIdx.x * (int64_t)wpb + warp; e < n; e += (int64_t)gridDim.x * wpb) {
+        const Agent a = load_agent_ro(agent, e);
+        const uint8_t *row = grid + e * cell_stride;
+        uint32_t occ, goal;
+        build_rows<W, H>(row, lane, kind[e], occ, goal);
+        int x = a.x(), y = a.y(), d = a.dir(), first, gx, gy;
+        const int len = bfs_rows<W, H>(true, occ, goal, x, y, d, lane, first, gx, gy);
+        if (len < 0) {
+            // last goal cell in scan order (teachers/base.py:31 keeps replacing while None)
+            const unsigned m = __ballot_sync(FULL, goal != 0);
+            int lx = 255, ly = 255;
+            if (m) {
+                lx = 31 - __clz(m);
+                ly = 31 - __clz(__shfl_sync(FULL, goal, lx));
+            }
+            gx = lx;
+            gy = ly;
+        }
+        if (lane == 0) {
+            len_out[e] = (int16_t)len;
+            goal_out[2 * e] = (uint8_t)gx;
+            goal_out[2 * e + 1] = (uint8_t)gy;
+        }
+        if (seq) {
+            uint8_t *sq = seq + e * (int64_t)seq_cap;
+            const uint32_t g1 = (len > 0 && lane == gx) ? (1u << gy) : 0u;
+            int f = first;
+            for (int k = 0; k < len; k++) {
+                if (lane == 0 && k < seq_cap) sq[k] = (uint8_t)f;
+                const int tx = x + dx_of(f), ty = y + dy_of(f);
+                const bool in = tx >= 0 && ty >= 0 && tx < W && ty < H;
+                const uint32_t orow = __shfl_sync(FULL, occ, in ? tx : 0);
+                if (in && !((orow >> ty) & 1)) { x = tx; y = ty; }
+                d = f;
+                if (k + 1 < len) {
+                    int g2x, g2y;
+                    bfs_rows<W, H>(true, occ, g1, x, y, d, lane, f, g2x, g2y);
+                }
+            }
+            for (int k = (len > 0 ? len : 0) + lane; k < seq_cap; k += 32) sq[k] = 255;
+        }
+    }
+}
+
+// =============================================================================================
 // features  (worlds/craft.py:296-330)
 // =============================================================================================
 // Shared-space stores by 32-bit address (no generic-address conversion in the hot loop).
@@ -882,6 +1098,8 @@ static inline int check(cudaError_t e) { return e == cudaSuccess ? PSK_OK : PSK_
 template <int W, int H, int WIN> struct Config {
     static constexpr int CP = ((W * H + 63) / 64) * 64;
     static constexpr int TPE = 8;   // threads per env in the feature scatter
+    // <= 128 cells: one env per thread on 64/128-bit bitboards; larger: one env per warp, row per lane
+    static constexpr bool BITBOARD = W * H <= 128;
 
     static bool matches(const psk_craft_tables *t) {
         return t->width == W && t->height == H && t->window_w == WIN && t->window_h == WIN &&
@@ -903,15 +1121,23 @@ template <int W, int H, int WIN> struct Config {
     }
     static int expert(const psk_craft_tables *t, psk_craft_state s, const uint8_t *task,
                       uint8_t *action, int16_t *dist, int32_t *err, cudaStream_t st) {
-        craft_expert_kernel<W, H><<<grid_for(s.n, 128, 8), 128, 0, st>>>(
-            *t, s.grid, s.agent, task, action, dist, err, s.n, s.cell_stride);
+        if constexpr (BITBOARD)
+            craft_expert_kernel<W, H><<<grid_for(s.n, 128, 8), 128, 0, st>>>(
+                *t, s.grid, s.agent, task, action, dist, err, s.n, s.cell_stride);
+        else
+            craft_expert_rows_kernel<W, H><<<grid_for(s.n, 4, 16), 128, 0, st>>>(
+                *t, s.grid, s.agent, task, action, dist, err, s.n, s.cell_stride);
         return check(cudaGetLastError());
     }
     static int find_closest(const psk_craft_tables *t, psk_craft_state s, const uint8_t *kind,
                             uint8_t *goal, int16_t *len, uint8_t *seq, int seq_cap,
                             cudaStream_t st) {
-        craft_find_closest_kernel<W, H><<<grid_for(s.n, 128, 8), 128, 0, st>>>(
-            *t, s.grid, s.agent, kind, goal, len, seq, seq_cap, s.n, s.cell_stride);
+        if constexpr (BITBOARD)
+            craft_find_closest_kernel<W, H><<<grid_for(s.n, 128, 8), 128, 0, st>>>(
+                *t, s.grid, s.agent, kind, goal, len, seq, seq_cap, s.n, s.cell_stride);
+        else
+            craft_find_closest_rows_kernel<W, H><<<grid_for(s.n, 4, 16), 128, 0, st>>>(
+                s.grid, s.agent, kind, goal, len, seq, seq_cap, s.n, s.cell_stride);
         return check(cudaGetLastError());
     }
     template <bool TMA>
@@ -989,6 +1215,9 @@ template <int W, int H, int WIN> struct Config {
                           const uint8_t *action_in, float *features_out, uint8_t *expert_out,
                           uint8_t *done, uint8_t *success, unsigned long long *stats,
                           int32_t *err, cudaStream_t st) {
+        if constexpr (!BITBOARD) {
+            return PSK_ERR_UNSUPPORTED;   // psk_craft_tick falls back to the three-kernel pipeline
+        } else {
         // Defaults from the sweep in profiles/README.md: small batches are latency-bound and
         // prefer big CTAs with plain vector stores; large batches prefer many small CTAs whose
         // feature warps stream through the TMA.  PSK_TICK_VARIANT / PSK_TICK_TMA override.
@@ -1016,17 +1245,22 @@ template <int W, int H, int WIN> struct Config {
             default: PSK_TV(64, 2);
         }
 #undef PSK_TV
+        }
     }
 };
 
 using Medium = Config<8, 8, 3>;    // configs/worlds/craft_medium.yaml
 using Large = Config<10, 10, 5>;   // configs/worlds/craft_large.yaml
+using Stress16 = Config<16, 16, 3>;  // enlarged-grid stress tests (BASELINE configs[4])
+using Stress32 = Config<32, 32, 3>;
 
-#define PSK_DISPATCH(t, CALL)                         \
-    do {                                              \
-        if (Medium::matches(t)) return Medium::CALL;  \
-        if (Large::matches(t)) return Large::CALL;    \
-        return PSK_ERR_UNSUPPORTED;                   \
+#define PSK_DISPATCH(t, CALL)                             \
+    do {                                                  \
+        if (Medium::matches(t)) return Medium::CALL;      \
+        if (Large::matches(t)) return Large::CALL;        \
+        if (Stress16::matches(t)) return Stress16::CALL;  \
+        if (Stress32::matches(t)) return Stress32::CALL;  \
+        return PSK_ERR_UNSUPPORTED;                       \
     } while (0)
 
 static bool state_ok(const psk_craft_tables *t, const psk_craft_state &s) {
@@ -1050,7 +1284,7 @@ const char *psk_version(void) { return "psketch_b200 0.1 sm_100a"; }
 
 int psk_craft_supported(const psk_craft_tables *t) {
     if (!t) return 0;
-    return Medium::matches(t) || Large::matches(t);
+    return Medium::matches(t) || Large::matches(t) || Stress16::matches(t) || Stress32::matches(t);
 }
 
 int psk_craft_n_features(const psk_craft_tables *t) {
@@ -1115,7 +1349,7 @@ int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episo
     if (!expert_out || !ep.scen_grid || !ep.scen_idx || !ep.init_agent) return PSK_ERR_BADARG;
     if (features_out && (reinterpret_cast<uintptr_t>(features_out) & 15)) return PSK_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (fused) {
+    if (fused && t->width * t->height <= 128) {
         PSK_DISPATCH(t, tick_fused(t, s, ep, action_in, features_out, expert_out, done_out,
                                    success_out, stats, err_flags, st));
     }
