@@ -328,11 +328,18 @@ def run_ours(args):
         "episodes": int(st[0]), "successes": int(st[1]),
     }
     # ---- roofline of the dominant kernel
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["craft_tick_kernel"]
+        if tr["n_envs"] == n:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     if fused:
         achieved = BYTES_FUSED * n / per_launch_s / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": "craft_tick_kernel", "achieved": achieved,
                             "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "peak_source": peak_src,
+                            "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_env_step": BYTES_FUSED}
     # per-kernel numbers (north star: step and features as a fraction of the HBM roofline)
     kern = {}
