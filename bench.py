@@ -131,6 +131,7 @@ def cpu_native_oracle(n_envs=65536, ticks=20):
     from oracle.craft_oracle import CraftOracle
     tables = CraftTables()
     o = CraftOracle(tables)
+    o.set_threads(os.cpu_count() or 1)
     w = load_workload(n_envs)
     init_grid = w["grids"][w["env"].astype(np.int64)]
     state, _, _, _ = o.rollout(1, 40, init_grid, w["pos"].astype(np.int32), w["task"].astype(np.int32))

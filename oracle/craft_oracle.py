@@ -74,7 +74,11 @@ class CraftOracle(object):
             getattr(self.lib, name).restype = None
 
     def set_threads(self, n):
-        os.environ["OMP_NUM_THREADS"] = str(n)
+        """OpenMP thread count of the batched calls (torchrun exports OMP_NUM_THREADS=1)."""
+        try:
+            ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+        except OSError:
+            os.environ["OMP_NUM_THREADS"] = str(n)
 
     def features(self, grid, inv, pos, dirs):
         grid, inv, pos, dirs = _u8(grid), _i32(inv), _i32(pos), _i32(dirs)

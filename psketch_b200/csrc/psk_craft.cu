@@ -79,7 +79,7 @@ __device__ __forceinline__ void step_env(const SharedTables &st, Agent &a, uint8
 
 template <int W, int H>
 __global__ void __launch_bounds__(256)
-craft_step_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__restrict__ grid,
+craft_step_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                   uint8_t *__restrict__ agent, const uint8_t *__restrict__ action,
                   const uint8_t *__restrict__ active, float *__restrict__ reward,
                   int32_t *err_flags, int64_t n, int cell_stride) {
@@ -139,7 +139,7 @@ __device__ __forceinline__ uint32_t find_incomplete(const SharedTables &st, int 
 
 template <int W, int H>
 __global__ void __launch_bounds__(256)
-craft_satisfies_kernel(const __grid_constant__ psk_craft_tables T,
+craft_satisfies_kernel(const psk_craft_tables *__restrict__ T,
                        const uint8_t *__restrict__ grid, const uint8_t *__restrict__ agent,
                        const uint8_t *__restrict__ task, uint8_t *__restrict__ out, int64_t n,
                        int cell_stride) {
@@ -339,7 +339,7 @@ __device__ __forceinline__ int expert_env(const SharedTables &st, const Agent &a
 
 template <int W, int H>
 __global__ void __launch_bounds__(128)
-craft_expert_kernel(const __grid_constant__ psk_craft_tables T, const uint8_t *__restrict__ grid,
+craft_expert_kernel(const psk_craft_tables *__restrict__ T, const uint8_t *__restrict__ grid,
                     const uint8_t *__restrict__ agent, const uint8_t *__restrict__ task,
                     uint8_t *__restrict__ action, int16_t *__restrict__ dist_out,
                     int32_t *err_flags, int64_t n, int cell_stride) {
@@ -376,7 +376,7 @@ craft_expert_kernel(const __grid_constant__ psk_craft_tables T, const uint8_t *_
 // chosen goal cell after every move (only the length is used on the training path).
 template <int W, int H>
 __global__ void __launch_bounds__(128)
-craft_find_closest_kernel(const __grid_constant__ psk_craft_tables T,
+craft_find_closest_kernel(const psk_craft_tables *__restrict__ T,
                           const uint8_t *__restrict__ grid, const uint8_t *__restrict__ agent,
                           const uint8_t *__restrict__ kind, uint8_t *__restrict__ goal_out,
                           int16_t *__restrict__ len_out, uint8_t *__restrict__ seq, int seq_cap,
@@ -567,7 +567,7 @@ __device__ __forceinline__ int bfs_rows(bool need, uint32_t occ, uint32_t goal, 
 
 template <int W, int H>
 __global__ void __launch_bounds__(128)
-craft_expert_rows_kernel(const __grid_constant__ psk_craft_tables T, const uint8_t *__restrict__ grid,
+craft_expert_rows_kernel(const psk_craft_tables *__restrict__ T, const uint8_t *__restrict__ grid,
                          const uint8_t *__restrict__ agent, const uint8_t *__restrict__ task,
                          uint8_t *__restrict__ action, int16_t *__restrict__ dist_out,
                          int32_t *err_flags, int64_t n, int cell_stride) {
@@ -656,6 +656,15 @@ craft_find_closest_rows_kernel(const uint8_t *__restrict__ grid, const uint8_t *
 // =============================================================================================
 // features  (worlds/craft.py:296-330)
 // =============================================================================================
+// Experiment knob for the vector-store path (PSK_STORE_MODE): 0 st.global.cs, 1 st.global,
+// 2 st.global.wt.  Set once from the environment by the host wrappers.
+__constant__ int g_store_mode = 0;
+__device__ __forceinline__ void store_out16(float4 *p, const float4 &t) {
+    if (g_store_mode == 0) __stcs(p, t);
+    else if (g_store_mode == 1) *p = t;
+    else __stwt(p, t);
+}
+
 // Shared-space stores by 32-bit address (no generic-address conversion in the hot loop).
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
@@ -675,6 +684,15 @@ template <int W, int H, int TPE> struct RowChunks {
         for (int c = 0; c < NCH; c++)
             v[c] = *reinterpret_cast<const uint2 *>(row + (j * NCH + c) * 8);
     }
+    // same from global memory, as volatile asm: the load is issued where it is written (the
+    // prefetch of the next chunk), not sunk by the compiler to its first use an iteration later
+    __device__ __forceinline__ void prefetch(const uint8_t *row, int j) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+            asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];"
+                         : "=r"(v[c].x), "=r"(v[c].y)
+                         : "l"(row + (j * NCH + c) * 8));
+    }
 };
 
 // Scatter of one env's non-zero features into its f32 row at shared address `frow_s`, done by
@@ -682,7 +700,8 @@ template <int W, int H, int TPE> struct RowChunks {
 // The centre block of the pooled WIN^2 x WIN^2 window is exactly the local WIN x WIN window
 // (bhw = hw*WIN + hw), so one pass over the cells writes both feature groups.
 template <int W, int H, int WIN, int TPE>
-__device__ __forceinline__ void scatter_features(uint32_t frow_s, const RowChunks<W, H, TPE> &cells,
+__device__ __forceinline__ void scatter_features(uint32_t frow_s, uint32_t trash_s,
+                                                 const RowChunks<W, H, TPE> &cells,
                                                  const Agent &a, int K, int j) {
     constexpr int HW = WIN / 2, BHW = (WIN * WIN) / 2;  // craft.py:299-302
     constexpr int WW = WIN * WIN;
@@ -696,13 +715,14 @@ __device__ __forceinline__ void scatter_features(uint32_t frow_s, const RowChunk
         const uint2 v = cells.v[ch];
         if (cc >= W * H || (v.x | v.y) == 0) continue;
         if (H % 8 == 0) {
-            // the 8 cells share one column x; y = y0 + b
+            // the 8 cells share one column x; y = y0 + b.  Stores are unconditional: a cell that
+            // contributes nothing writes into the warp's trash slot instead (no branches).
             const int x = cc / H, y0 = cc % H;
             const int bx = x - px + BHW;
             const bool bx_ok = (unsigned)bx < (unsigned)WW;
             const int bi = bx / WIN;
             const uint32_t big_col = big_s + bi * (WIN * K4);
-            const bool centre_col = bi == HW;
+            const bool centre_col = bx_ok && bi == HW;
             const uint32_t loc_col = frow_s + (bx - HW * WIN) * (WIN * K4) - HW * WIN * K4;
             const int by0 = y0 - py + BHW;
 #pragma unroll
@@ -711,10 +731,11 @@ __device__ __forceinline__ void scatter_features(uint32_t frow_s, const RowChunk
                 const int by = by0 + b;
                 const bool ok = bx_ok && (unsigned)by < (unsigned)WW && k != 0;
                 const int bj = by / WIN;
+                const uint32_t off = by * K4 + k * 4;
                 // pooled window, block (bi, bj)  (craft.py:306-310)
-                if (ok) sts_f32(big_col + bj * K4 + k * 4, 1.0f);
+                sts_f32(ok ? big_col + bj * K4 + k * 4 : trash_s, 1.0f);
                 // local window, ravel order (dx, dy, kind)  (craft.py:304-305)
-                if (ok && centre_col && bj == HW) sts_f32(loc_col + by * K4 + k * 4, 1.0f);
+                sts_f32((ok && centre_col && bj == HW) ? loc_col + off : trash_s, 1.0f);
             }
         } else {
 #pragma unroll
@@ -759,13 +780,29 @@ __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// One warp builds the feature rows of up to EPW = 32/TPE consecutive envs in its own pair of
-// shared-memory buffers and hands each finished chunk to the TMA with one bulk store; lane 0
-// owns the warp's bulk groups.  No CTA-level barrier is involved: warps are autonomous pipelines.
-//   wbuf_s  shared address of this warp's two buffers; it = this warp's chunk counter (parity)
+// One warp builds the feature rows of up to EPW = 32/TPE consecutive envs in its own shared-
+// memory buffer(s) and sends each finished chunk to HBM; no CTA-level barrier is involved: warps
+// are autonomous pipelines.  Two ways out of shared memory:
+//   USE_TMA  one cp.async.bulk (UBLKCP) per chunk, issued by lane 0, two buffers per warp so the
+//            store of chunk i overlaps the build of chunk i+1; the buffer is zero-filled per chunk;
+//   else     coalesced 128-bit st.global.cs by all lanes; every word read out is zeroed in the
+//            same pass, so one buffer per warp stays clean (feature_buffer_init zeroes it once).
+//   wbuf_s  shared address of this warp's buffer(s); it = this warp's chunk counter (parity)
 //   gdst    where the chunk's rows go; ne = live envs in the chunk (<= EPW)
 //   cells/a the lane's share of its env's grid row and the env's agent record
-// KC > 0 fixes the number of kinds at compile time (KC == K) so that the zero-fill unrolls.
+// KC > 0 fixes the number of kinds at compile time (KC == K) so that the loops unroll.
+// Each buffer is EPW*nf floats + one 16-byte trash slot for the scatter's no-op stores.
+__host__ __device__ constexpr int feature_buffer_bytes(int epw, int nf) { return epw * nf * 4 + 16; }
+
+template <int TPE, int KC, bool USE_TMA>
+__device__ __forceinline__ void feature_buffer_init(uint32_t wbuf_s, int nf, int WINSQ2K_unused = 0) {
+    constexpr int EPW = 32 / TPE;
+    const int lane = threadIdx.x & 31;
+    const int words = (USE_TMA ? 2 : 1) * feature_buffer_bytes(EPW, nf) / 4;
+    for (int i = lane; i < words; i += 32) sts_f32(wbuf_s + i * 4, 0.f);
+    __syncwarp();
+}
+
 template <int W, int H, int WIN, int TPE, int KC, bool USE_TMA>
 __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, float *gdst, int ne,
                                                    const RowChunks<W, H, TPE> &cells,
@@ -777,24 +814,27 @@ __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, floa
     }
     const int lane = threadIdx.x & 31;
     const int le = lane / TPE, j = lane % TPE;
-    const uint32_t buf_s = wbuf_s + (USE_TMA ? (uint32_t)(it & 1) * EPW * nf * 4 : 0u);
-    // the buffer was handed to the TMA two chunks ago: wait until it has been read
-    if (USE_TMA && lane == 0) bulk_wait_read<1>();
-    __syncwarp();
-    if ((nf & 3) == 0) {
-        const int n16 = EPW * nf / 4;
-        if (KC > 0) {
+    const uint32_t buf_s = wbuf_s + (USE_TMA ? (uint32_t)(it & 1) * feature_buffer_bytes(EPW, nf) : 0u);
+    const uint32_t trash_s = buf_s + EPW * nf * 4;
+    const int n16 = EPW * nf / 4;
+    if (USE_TMA) {
+        // the buffer was handed to the TMA two chunks ago: wait until it has been read, re-zero
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        if ((nf & 3) == 0) {
+            if (KC > 0) {
 #pragma unroll
-            for (int i = 0; i < (n16 + 31) / 32; i++)
-                if (i * 32 + lane < n16) sts_zero16(buf_s + (i * 32 + lane) * 16);
+                for (int i = 0; i < (n16 + 31) / 32; i++)
+                    if (i * 32 + lane < n16) sts_zero16(buf_s + (i * 32 + lane) * 16);
+            } else {
+                for (int i = lane; i < n16; i += 32) sts_zero16(buf_s + i * 16);
+            }
         } else {
-            for (int i = lane; i < n16; i += 32) sts_zero16(buf_s + i * 16);
+            for (int i = lane; i < EPW * nf; i += 32) sts_f32(buf_s + i * 4, 0.f);
         }
-    } else {
-        for (int i = lane; i < EPW * nf; i += 32) sts_f32(buf_s + i * 4, 0.f);
+        __syncwarp();
     }
-    __syncwarp();
-    if (le < ne) scatter_features<W, H, WIN, TPE>(buf_s + le * nf * 4, cells, a, K, j);
+    if (le < ne) scatter_features<W, H, WIN, TPE>(buf_s + le * nf * 4, trash_s, cells, a, K, j);
     const uint32_t bytes = (uint32_t)ne * (uint32_t)nf * 4u;
     if (USE_TMA && (bytes & 15u) == 0) {
         fence_async_smem();  // generic-proxy writes -> visible to the async proxy
@@ -804,12 +844,23 @@ __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, floa
         __syncwarp();
         if ((bytes & 15u) == 0) {
             float4 *g4 = reinterpret_cast<float4 *>(gdst);
-            for (int i = lane; i < (int)(bytes / 16); i += 32) {
+            const int m16 = (int)(bytes / 16);
+            auto move16 = [&](int i) {
                 float4 t;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                              : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
                              : "r"(buf_s + i * 16));
-                __stcs(g4 + i, t);
+                if (!USE_TMA) sts_zero16(buf_s + i * 16);
+                store_out16(g4 + i, t);
+            };
+            if (KC > 0 && m16 == n16) {
+#pragma unroll
+                for (int i = 0; i < (n16 + 31) / 32; i++)
+                    if (i * 32 + lane < n16) move16(i * 32 + lane);
+            } else {
+                for (int i = lane; i < m16; i += 32) move16(i);
+                if (!USE_TMA)   // rows of dead lanes may have been touched by nobody, but stay safe
+                    for (int i = m16 + lane; i < n16; i += 32) sts_zero16(buf_s + i * 16);
             }
         } else {
             for (int i = lane; i < ne * nf; i += 32) {
@@ -817,6 +868,9 @@ __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, floa
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(buf_s + i * 4));
                 gdst[i] = t;
             }
+            __syncwarp();
+            if (!USE_TMA)
+                for (int i = lane; i < EPW * nf; i += 32) sts_f32(buf_s + i * 4, 0.f);
         }
         __syncwarp();
     }
@@ -832,7 +886,8 @@ craft_features_kernel(const uint8_t *__restrict__ grid, const uint8_t *__restric
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int le = lane / TPE, j = lane % TPE;
-    const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)warp * (USE_TMA ? 2 : 1) * EPW * nf * 4;
+    const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)warp * (USE_TMA ? 2 : 1) * feature_buffer_bytes(EPW, nf);
+    if (!USE_TMA) feature_buffer_init<TPE, KC, USE_TMA>(wbuf_s, nf);
     const int64_t n_chunks = (n + EPW - 1) / EPW;
     const int64_t stride = (int64_t)gridDim.x * WPB;
     int64_t ch = (int64_t)blockIdx.x * WPB + warp;
@@ -842,7 +897,7 @@ craft_features_kernel(const uint8_t *__restrict__ grid, const uint8_t *__restric
         int64_t e = c * EPW + le;
         if (e >= n) e = n - 1;
         ag = load_agent_ro(agent, e);
-        rc.load(grid + e * cell_stride, j);
+        rc.prefetch(grid + e * cell_stride, j);
     };
     if (ch < n_chunks) fetch(ch, a, cells);
     for (int it = 0; ch < n_chunks; ch += stride, it++) {
@@ -932,7 +987,7 @@ __device__ __forceinline__ void add_stats(unsigned long long *stats, bool done, 
 
 template <int W, int H>
 __global__ void __launch_bounds__(256)
-craft_advance_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__restrict__ grid,
+craft_advance_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                      uint8_t *__restrict__ agent, const uint8_t *__restrict__ action,
                      const uint8_t *__restrict__ scen_grid, const int32_t *__restrict__ scen_idx,
                      const uint8_t *__restrict__ init_agent, uint8_t *__restrict__ done_out,
@@ -972,7 +1027,7 @@ craft_advance_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__rest
 // every CTA instead of alternating.
 template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA>
 __global__ void __launch_bounds__(NE + NFW * 32)
-craft_tick_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__restrict__ grid,
+craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                   uint8_t *__restrict__ agent, const uint8_t *__restrict__ action_in,
                   const uint8_t *__restrict__ scen_grid, const int32_t *__restrict__ scen_idx,
                   const uint8_t *__restrict__ init_agent, float *__restrict__ features_out,
@@ -992,6 +1047,9 @@ craft_tick_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__restric
     stage_tables(st, T);
     const int tid = threadIdx.x;
     const bool env_warp = tid < NE;
+    if (!USE_TMA && !env_warp && features_out)
+        feature_buffer_init<8, KC, USE_TMA>(
+            smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(4, nf), nf);
     uint32_t flags = 0;
     int it = 0;  // this feature warp's chunk counter
     const int64_t n_super = (n + NE - 1) / NE;
@@ -1047,7 +1105,7 @@ craft_tick_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__restric
             add_stats(stats, done, success, live);
         } else if (features_out) {
             const int fw = (tid - NE) >> 5, lane = tid & 31;
-            const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)fw * (USE_TMA ? 2 : 1) * EPW * nf * 4;
+            const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)fw * (USE_TMA ? 2 : 1) * feature_buffer_bytes(EPW, nf);
             for (int c = 0; c < SPW / EPW; c++) {
                 const int s0 = fw * SPW + c * EPW;      // first env slot of the chunk
                 if (s0 >= ne_sp) break;
@@ -1079,6 +1137,10 @@ craft_tick_kernel(const __grid_constant__ psk_craft_tables T, uint8_t *__restric
 static int g_num_sms = 0;
 static int num_sms() {
     if (!g_num_sms) {
+        if (const char *m = getenv("PSK_STORE_MODE")) {
+            const int mode = atoi(m);
+            cudaMemcpyToSymbol(g_store_mode, &mode, sizeof(int));
+        }
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1095,6 +1157,31 @@ static inline int grid_for(int64_t n, int block, int ctas_per_sm) {
 
 static inline int check(cudaError_t e) { return e == cudaSuccess ? PSK_OK : PSK_ERR_CUDA; }
 
+// Device copy of the caller's tables, one slot per device, refreshed when the content changes.
+// The refresh is a pageable H2D copy: it must not happen inside a CUDA-graph capture, so call any
+// entry point once with new tables before capturing (every caller's warm-up does).
+static const psk_craft_tables *device_tables(const psk_craft_tables *t, cudaStream_t st) {
+    constexpr int MAX_DEV = 32;
+    static psk_craft_tables host_copy[MAX_DEV];
+    static psk_craft_tables *dev_copy[MAX_DEV] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    if (!dev_copy[dev]) {
+        if (cudaMalloc(&dev_copy[dev], sizeof(psk_craft_tables)) != cudaSuccess) return nullptr;
+        memset(&host_copy[dev], 0xFF, sizeof(psk_craft_tables));
+    }
+    if (memcmp(&host_copy[dev], t, sizeof(psk_craft_tables)) != 0) {
+        if (cudaMemcpyAsync(dev_copy[dev], t, sizeof(psk_craft_tables), cudaMemcpyHostToDevice, st) !=
+            cudaSuccess)
+            return nullptr;
+        host_copy[dev] = *t;
+    }
+    return dev_copy[dev];
+}
+#define PSK_DT(var)                                   \
+    const psk_craft_tables *var = device_tables(t, st); \
+    if (!var) return PSK_ERR_CUDA
+
 template <int W, int H, int WIN> struct Config {
     static constexpr int CP = ((W * H + 63) / 64) * 64;
     static constexpr int TPE = 8;   // threads per env in the feature scatter
@@ -1109,32 +1196,36 @@ template <int W, int H, int WIN> struct Config {
 
     static int step(const psk_craft_tables *t, psk_craft_state s, const uint8_t *action,
                     const uint8_t *active, float *reward, int32_t *err, cudaStream_t st) {
+        PSK_DT(dt);
         craft_step_kernel<W, H><<<grid_for(s.n, 256, 8), 256, 0, st>>>(
-            *t, s.grid, s.agent, action, active, reward, err, s.n, s.cell_stride);
+            dt, s.grid, s.agent, action, active, reward, err, s.n, s.cell_stride);
         return check(cudaGetLastError());
     }
     static int satisfies(const psk_craft_tables *t, psk_craft_state s, const uint8_t *task,
                          uint8_t *out, cudaStream_t st) {
+        PSK_DT(dt);
         craft_satisfies_kernel<W, H><<<grid_for(s.n, 256, 8), 256, 0, st>>>(
-            *t, s.grid, s.agent, task, out, s.n, s.cell_stride);
+            dt, s.grid, s.agent, task, out, s.n, s.cell_stride);
         return check(cudaGetLastError());
     }
     static int expert(const psk_craft_tables *t, psk_craft_state s, const uint8_t *task,
                       uint8_t *action, int16_t *dist, int32_t *err, cudaStream_t st) {
+        PSK_DT(dt);
         if constexpr (BITBOARD)
             craft_expert_kernel<W, H><<<grid_for(s.n, 128, 8), 128, 0, st>>>(
-                *t, s.grid, s.agent, task, action, dist, err, s.n, s.cell_stride);
+                dt, s.grid, s.agent, task, action, dist, err, s.n, s.cell_stride);
         else
             craft_expert_rows_kernel<W, H><<<grid_for(s.n, 4, 16), 128, 0, st>>>(
-                *t, s.grid, s.agent, task, action, dist, err, s.n, s.cell_stride);
+                dt, s.grid, s.agent, task, action, dist, err, s.n, s.cell_stride);
         return check(cudaGetLastError());
     }
     static int find_closest(const psk_craft_tables *t, psk_craft_state s, const uint8_t *kind,
                             uint8_t *goal, int16_t *len, uint8_t *seq, int seq_cap,
                             cudaStream_t st) {
+        PSK_DT(dt);
         if constexpr (BITBOARD)
             craft_find_closest_kernel<W, H><<<grid_for(s.n, 128, 8), 128, 0, st>>>(
-                *t, s.grid, s.agent, kind, goal, len, seq, seq_cap, s.n, s.cell_stride);
+                dt, s.grid, s.agent, kind, goal, len, seq, seq_cap, s.n, s.cell_stride);
         else
             craft_find_closest_rows_kernel<W, H><<<grid_for(s.n, 4, 16), 128, 0, st>>>(
                 s.grid, s.agent, kind, goal, len, seq, seq_cap, s.n, s.cell_stride);
@@ -1145,7 +1236,7 @@ template <int W, int H, int WIN> struct Config {
                              cudaStream_t st) {
         constexpr int WPB = 4, EPW = 32 / TPE;
         const int f = nf(t);
-        const size_t smem = (size_t)WPB * (TMA ? 2 : 1) * EPW * f * sizeof(float);
+        const size_t smem = (size_t)WPB * (TMA ? 2 : 1) * feature_buffer_bytes(EPW, f);
         // the default cookbook has 21 kinds: that case is compiled with K fixed
         auto kern = t->n_kinds == 21 ? craft_features_kernel<W, H, WIN, WPB, TPE, 21, TMA>
                                      : craft_features_kernel<W, H, WIN, WPB, TPE, 0, TMA>;
@@ -1163,7 +1254,14 @@ template <int W, int H, int WIN> struct Config {
         if (per_sm > 16) per_sm = 16;
         const int64_t ctas = (s.n + (int64_t)WPB * EPW - 1) / ((int64_t)WPB * EPW);
         int64_t g = (int64_t)num_sms() * (per_sm > 0 ? per_sm : 1);
-        if (g > ctas) g = ctas > 0 ? ctas : 1;
+        static int persist = -1;
+        if (persist < 0) {
+            // One CTA per tile, dispatched in index order, keeps the DRAM write front compact:
+            // 270 us vs 330 us at 1 M envs for a persistent grid-stride grid (profiles/README.md).
+            const char *v = getenv("PSK_FEAT_PERSIST");
+            persist = v ? atoi(v) : 0;
+        }
+        if (g > ctas || !persist) g = ctas > 0 ? ctas : 1;
         kern<<<(int)g, WPB * 32, smem, st>>>(s.grid, s.agent, out, s.n, s.cell_stride, t->n_kinds, f);
         return check(cudaGetLastError());
     }
@@ -1175,8 +1273,9 @@ template <int W, int H, int WIN> struct Config {
     static int advance(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
                        const uint8_t *action, uint8_t *done, uint8_t *success,
                        unsigned long long *stats, int32_t *err, cudaStream_t st) {
+        PSK_DT(dt);
         craft_advance_kernel<W, H><<<grid_for(s.n, 256, 8), 256, 0, st>>>(
-            *t, s.grid, s.agent, action, ep.scen_grid, ep.scen_idx, ep.init_agent, done, success,
+            dt, s.grid, s.agent, action, ep.scen_grid, ep.scen_idx, ep.init_agent, done, success,
             stats, err, s.n, s.cell_stride);
         return check(cudaGetLastError());
     }
@@ -1187,7 +1286,7 @@ template <int W, int H, int WIN> struct Config {
                             int32_t *err, cudaStream_t st) {
         constexpr int EPW = 32 / TPE;
         const int f = nf(t);
-        const size_t smem = (size_t)NFW * (TMA ? 2 : 1) * EPW * f * sizeof(float);
+        const size_t smem = (size_t)NFW * (TMA ? 2 : 1) * feature_buffer_bytes(EPW, f);
         auto kern = t->n_kinds == 21 ? craft_tick_kernel<W, H, WIN, NE, NFW, 21, TMA>
                                      : craft_tick_kernel<W, H, WIN, NE, NFW, 0, TMA>;
         static size_t configured = 0;
@@ -1205,9 +1304,15 @@ template <int W, int H, int WIN> struct Config {
         if (per_sm > by_threads) per_sm = by_threads;
         const int64_t tiles = (s.n + NE - 1) / NE;
         int64_t g = (int64_t)num_sms() * (per_sm > 0 ? per_sm : 1);
-        if (g > tiles) g = tiles > 0 ? tiles : 1;
+        static int persist = -1;
+        if (persist < 0) {
+            const char *v = getenv("PSK_TICK_PERSIST");   // see features_impl: in-order tiles win
+            persist = v ? atoi(v) : 0;
+        }
+        if (g > tiles || !persist) g = tiles > 0 ? tiles : 1;
+        PSK_DT(dt);
         kern<<<(int)g, NE + NFW * 32, smem, st>>>(
-            *t, s.grid, s.agent, action_in, ep.scen_grid, ep.scen_idx, ep.init_agent, features_out,
+            dt, s.grid, s.agent, action_in, ep.scen_grid, ep.scen_idx, ep.init_agent, features_out,
             expert_out, done, success, stats, err, s.n, s.cell_stride, t->n_kinds, f);
         return check(cudaGetLastError());
     }
@@ -1229,7 +1334,7 @@ template <int W, int H, int WIN> struct Config {
             env_tma = m ? atoi(m) : -1;
         }
         const bool big = s.n > 262144;
-        const int variant = env_variant >= 0 ? env_variant : (big ? 4 : 1);
+        const int variant = env_variant >= 0 ? env_variant : (big ? 4 : 0);
         const int tma = env_tma >= 0 ? env_tma : (big ? 1 : 0);
 #define PSK_TV(NE, NFW)                                                                          \
     return tma ? tick_variant<NE, NFW, true>(t, s, ep, action_in, features_out, expert_out, done, \

@@ -18,6 +18,8 @@ def init_from_env(backend=None):
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29533")
+        # NCCL's banner/debug lines go to stdout by default; callers print JSON there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         kw = {}
