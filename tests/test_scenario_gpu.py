@@ -104,21 +104,6 @@ def test_generated_dataset_is_solvable_and_round_trips(medium_tables, tmp_path):
     assert sum(len(parts[s]["inst_env"]) for s in parts) == n_inst
 
 
-def test_wire_format_reads_reference_goldens(splits, medium_tables):
-    """The shipped dev split, re-serialised to the reference's JSON layout and read back."""
-    from psketch_b200 import data
-    packed = {k[4:]: splits[k] for k in splits.files if k.startswith("dev_")}
-    packed["inst_env"] = packed["inst_env"].astype(np.int32)
-    packed["ref_len"] = packed["ref_len"].astype(np.int32)
-    wire = data.to_wire(packed, medium_tables)
-    assert len(wire) == 10 and len(wire[0]["task_instances"]) == 11
-    assert np.asarray(wire[0]["grid"]).shape == (8, 8, 21)
-    assert wire[0]["task_instances"][0]["task"] == "get[wood]"
-    back = data.from_wire(wire, medium_tables)
-    assert np.array_equal(back["grids"], packed["grids"])
-    assert np.array_equal(back["ref_actions"], packed["ref_actions"])
-
-
 def test_policy_rollouts_match_facade_semantics(splits, medium_tables, medium_oracle):
     """Batched rollout driver with a scripted student vs the same loop on the CPU oracle."""
     from psketch_b200.rollout import policy_rollouts
