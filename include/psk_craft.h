@@ -62,7 +62,9 @@ extern "C" {
 #define PSK_ACT_STOP 5
 #define PSK_ACT_INVALID 255 /* expert output where the reference asserts */
 
-/* Domain tables (host struct, passed by pointer and copied into kernel parameters).
+/* Domain tables (host struct, passed by pointer; the library keeps a device copy per GPU and
+ * refreshes it when the content changes — do the first call with new tables outside a CUDA-graph
+ * capture).
  * Replaces: Cookbook (worlds/cookbook.py:7-26), the kind sets of CraftWorld.__init__
  * (worlds/craft.py:101-107) and the hint tree of TaskManager (data/task.py:34-59).
  * Built by psketch_b200/tables.py:CraftTables. */
