@@ -48,10 +48,11 @@ int psk_light_features(const psk_light_scenario *scen, const int32_t *scen_idx,
                        const uint8_t *state, float *out, int64_t n, void *stream);
 int psk_light_satisfies(const psk_light_scenario *scen, const int32_t *scen_idx,
                         const uint8_t *state, uint8_t *out, int64_t n, void *stream);
-/* action u8[n] (255 = goal room unreachable, 254 = already in the goal room), dist i16[n]. */
+/* action u8[n] (255 = goal room unreachable, 254 = already in the goal room), dist i16[n].
+ * max_keys: the largest n_keys among the scenarios used (sizes the per-warp shared memory). */
 int psk_light_expert(const psk_light_scenario *scen, const int32_t *scen_idx,
-                     const uint8_t *state, uint8_t *action, int16_t *dist, int64_t n,
-                     void *stream);
+                     const uint8_t *state, uint8_t *action, int16_t *dist, int32_t max_keys,
+                     int64_t n, void *stream);
 
 #ifdef __cplusplus
 }

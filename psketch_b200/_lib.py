@@ -115,7 +115,7 @@ def load_light():
         lib.psk_light_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp]
         lib.psk_light_features.argtypes = [vp, vp, vp, vp, i64, vp]
         lib.psk_light_satisfies.argtypes = [vp, vp, vp, vp, i64, vp]
-        lib.psk_light_expert.argtypes = [vp, vp, vp, vp, vp, i64, vp]
+        lib.psk_light_expert.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int32, i64, vp]
         for name in LIGHT_EXPORTS:
             getattr(lib, name).restype = ctypes.c_int
         _light_bound = True

@@ -795,11 +795,15 @@ __device__ __forceinline__ void fence_async_smem() {
 __host__ __device__ constexpr int feature_buffer_bytes(int epw, int nf) { return epw * nf * 4 + 16; }
 
 template <int TPE, int KC, bool USE_TMA>
-__device__ __forceinline__ void feature_buffer_init(uint32_t wbuf_s, int nf, int WINSQ2K_unused = 0) {
+__device__ __forceinline__ void feature_buffer_init(uint32_t wbuf_s, int nf) {
     constexpr int EPW = 32 / TPE;
     const int lane = threadIdx.x & 31;
-    const int words = (USE_TMA ? 2 : 1) * feature_buffer_bytes(EPW, nf) / 4;
-    for (int i = lane; i < words; i += 32) sts_f32(wbuf_s + i * 4, 0.f);
+    const int bytes = (USE_TMA ? 2 : 1) * feature_buffer_bytes(EPW, nf);
+    if ((bytes & 15) == 0 && (wbuf_s & 15) == 0) {
+        for (int i = lane; i < bytes / 16; i += 32) sts_zero16(wbuf_s + i * 16);
+    } else {
+        for (int i = lane; i < bytes / 4; i += 32) sts_f32(wbuf_s + i * 4, 0.f);
+    }
     __syncwarp();
 }
 

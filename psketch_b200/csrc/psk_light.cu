@@ -133,7 +133,7 @@ constexpr int LIGHT_MAX_LAYERS = 1 << PSK_LIGHT_MAX_KEYS;
 __global__ void __launch_bounds__(128)
 light_expert_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
                     const uint8_t *__restrict__ state, uint8_t *__restrict__ action,
-                    int16_t *__restrict__ dist_out, int64_t n) {
+                    int16_t *__restrict__ dist_out, int64_t n, int layer_cap) {
     extern __shared__ uint32_t s_layers[];          // [warps][2][n_layers_cap][32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
@@ -145,8 +145,15 @@ light_expert_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *
         const uint32_t alive = (st >> 16) & 0xFF;
         const int nk = s.n_keys;
         const int n_layers = 1 << nk;
-        uint32_t *R = s_layers + (size_t)warp * 2 * LIGHT_MAX_LAYERS * 32;   // reached so far
-        uint32_t *P = R + LIGHT_MAX_LAYERS * 32;                             // reached one level earlier
+        if (n_layers > layer_cap) {          // scenario has more keys than the caller announced
+            if (lane == 0) {
+                action[e] = 255;
+                if (dist_out) dist_out[e] = -2;
+            }
+            continue;
+        }
+        uint32_t *R = s_layers + (size_t)warp * 2 * layer_cap * 32;   // reached so far
+        uint32_t *P = R + layer_cap * 32;                             // reached one level earlier
         const uint32_t wall_row = s.walls[lane];
         // goal room rows / cells
         uint32_t goal_row = 0;
@@ -294,21 +301,27 @@ int psk_light_satisfies(const psk_light_scenario *scen, const int32_t *scen_idx,
 }
 
 int psk_light_expert(const psk_light_scenario *scen, const int32_t *scen_idx,
-                     const uint8_t *state, uint8_t *action, int16_t *dist, int64_t n,
-                     void *stream) {
-    if (!light_args_ok(scen, scen_idx, state, n) || (n && !action)) return PSK_ERR_BADARG;
+                     const uint8_t *state, uint8_t *action, int16_t *dist, int32_t max_keys,
+                     int64_t n, void *stream) {
+    if (!light_args_ok(scen, scen_idx, state, n) || (n && !action) || max_keys < 0 ||
+        max_keys > PSK_LIGHT_MAX_KEYS)
+        return PSK_ERR_BADARG;
     if (n == 0) return PSK_OK;
-    const int wpb = 1;   // 2 x 256 layers x 32 rows x 4 B = 64 KB of shared memory per warp
-    const size_t smem = (size_t)wpb * 2 * LIGHT_MAX_LAYERS * 32 * sizeof(uint32_t);
-    static bool configured = false;
-    if (!configured) {
+    // two boards (reached / previous level) of 32 rows per key subset and warp
+    const int layer_cap = 1 << max_keys;
+    const size_t per_warp = (size_t)2 * layer_cap * 32 * sizeof(uint32_t);
+    int wpb = (int)((48 * 1024) / per_warp);
+    wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
+    const size_t smem = (size_t)wpb * per_warp;
+    static size_t configured = 0;
+    if (smem > configured) {
         if (cudaFuncSetAttribute(light_expert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)
             return PSK_ERR_CUDA;
-        configured = true;
+        configured = smem;
     }
     light_expert_kernel<<<lblocks(n, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(
-        scen, scen_idx, state, action, dist, n);
+        scen, scen_idx, state, action, dist, n, layer_cap);
     return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
 }
 

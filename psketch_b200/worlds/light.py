@@ -194,6 +194,7 @@ class VecLight(object):
         arr = (LightScenarioC * len(scenarios))(*[s.to_c() for s in scenarios])
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).reshape(len(scenarios), ctypes.sizeof(LightScenarioC))
         self.scen = torch.from_numpy(raw.copy()).to(self.device)
+        self.max_keys = max([len(s.keys) for s in scenarios] + [0])
         self.scen_idx = torch.as_tensor(np.asarray(scen_idx, np.int32)).to(self.device)
         self.n = len(self.scen_idx)
         self.state = torch.zeros((self.n, 4), dtype=torch.uint8, device=self.device)
@@ -253,7 +254,8 @@ class VecLight(object):
         dist = self.torch.empty(self.n, dtype=self.torch.int16, device=self.device)
         with self.torch.cuda.device(self.device):
             rc = self.lib.psk_light_expert(self._p(self.scen), self._p(self.scen_idx), self._p(self.state),
-                                           self._p(act), self._p(dist), self.n, self._stream())
+                                           self._p(act), self._p(dist), self.max_keys, self.n,
+                                           self._stream())
         _lib.check(rc, "psk_light_expert")
         return act, dist
 
