@@ -217,3 +217,94 @@ def split_envs(packed, fractions=(0.8, 0.1, 0.1), seed=123):
                          inst_id=packed["inst_id"][sel], ref_actions=packed["ref_actions"][sel],
                          ref_len=packed["ref_len"][sel])
     return out
+
+
+# ------------------------------------------------------------------------------- Dataset mirror
+class Dataset(object):
+    """Same surface as the reference's data.Dataset (data/dataset.py:12-93): instances flattened
+    to dicts {id, task, grid (one-hot ndarray), init_pos, ref_actions}, shuffled batching driven
+    by ``config.random`` with the reference's call sequence (one ``shuffle`` per pass)."""
+
+    def __init__(self, config, split, task_manager):
+        import os
+        self.config = config
+        self.split = split
+        self.task_manager = task_manager
+        self.file_name = os.path.join(config.data_dir, config.world.config + "_" + split + ".json")
+        with open(self.file_name) as f:
+            self.data = self.flatten_data(json.load(f))
+        self.instance_by_id = {item["id"]: item for item in self.data}
+        self.item_idx = 0
+        self.random = config.random
+        self.batch_size = config.trainer.batch_size
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        return self.data[idx]
+
+    def __iter__(self):
+        return iter(self.data)
+
+    def get_instance_by_id(self, instance_id):
+        return self.instance_by_id[instance_id]
+
+    def flatten_data(self, data):
+        out = []
+        for env in data:
+            grid = env["grid"]
+            for ti in env["task_instances"]:
+                task = self.task_manager[_goal(ti["task"])]
+                for pos, id_, ra in zip(ti["init_pos"], ti["ids"], ti["ref_actions"]):
+                    out.append({"id": id_, "task": task, "grid": np.array(grid),
+                                "init_pos": tuple(pos), "ref_actions": tuple(ra)})
+        return out
+
+    def next_batch(self):
+        if self.item_idx == 0:
+            self.data_indices = list(range(len(self)))
+            self.random.shuffle(self.data_indices)
+        start, end = self.item_idx, self.item_idx + self.batch_size
+        indices = self.data_indices[start:end]
+        self.item_idx = end
+        end_pass = self.item_idx >= len(self)
+        if end_pass:
+            self.item_idx = 0
+        return [self[i] for i in indices], end_pass
+
+    def iterate_batches(self):
+        end_pass = False
+        while not end_pass:
+            batch, end_pass = self.next_batch()
+            yield batch
+
+    def packed(self, tables):
+        """The same instances as the packed arrays VecCraft.from_instances takes."""
+        grids, key_of, ienv, itask, ipos, acts = [], {}, [], [], [], []
+        for item in self.data:
+            key = item["grid"].tobytes()
+            if key not in key_of:
+                key_of[key] = len(grids)
+                grids.append(grid_to_ids(item["grid"]).reshape(-1))
+            ienv.append(key_of[key])
+            itask.append(tables.task_manager[item["task"].goal_name + "[" + item["task"].goal_arg + "]"].task_id)
+            ipos.append(item["init_pos"])
+            acts.append(item["ref_actions"])
+        L = max(len(a) for a in acts)
+        ra = np.full((len(acts), L), 255, np.uint8)
+        for i, a in enumerate(acts):
+            ra[i, :len(a)] = a
+        return dict(grids=np.stack(grids), inst_env=np.asarray(ienv, np.int32),
+                    inst_task=np.asarray(itask, np.uint8), inst_pos=np.asarray(ipos, np.uint8),
+                    ref_actions=ra, ref_len=np.asarray([len(a) for a in acts], np.int32))
+
+
+def load(config):
+    """data.load(config) of the reference (data/__init__.py): {'train','dev','test'} datasets."""
+    from .tables import TaskManager
+    import os
+    hints = getattr(getattr(config, "trainer", None), "hints", None)
+    tm = TaskManager(hints if hints and os.path.exists(hints) else None)
+    config.vocab = tm.vocab
+    return {split: Dataset(config, split, tm) for split in ("train", "dev", "test")}

@@ -277,3 +277,38 @@ def test_host_buffer_tick_matches_oracle(splits, medium_tables, medium_oracle):
         assert np.array_equal(env.agent[:, 24:26].astype(np.int32), state["pos"]), t
     assert int(env.stats[0]) == tot[0] and int(env.stats[1]) == tot[1]
     env.close()
+
+
+def test_million_env_properties(splits, medium_tables, medium_oracle):
+    """BASELINE config 3 per-GPU size (1,048,576 envs): the large-batch kernel variant, checked on
+    a strided sample against the oracle and through the size-independent counters."""
+    from psketch_b200.vec import VecCraft
+    n = 1 << 20
+    idx = np.arange(n) % 17600
+    grids = splits["train_grids"]
+    ienv, ipos, itask = (splits["train_inst_env"][idx], splits["train_inst_pos"][idx],
+                         splits["train_inst_task"][idx])
+    env = VecCraft.from_instances(medium_tables, grids, ienv, ipos, itask, max_timesteps=40)
+    feats = torch.empty((n, 404), dtype=torch.float32, device=env.device)
+    T = 30
+    sample = np.arange(0, n, 997)
+    state = None
+    for t in range(T):
+        out = env.tick(features_out=feats, fused=True)
+        if t in (0, 7, 19):
+            # oracle on the sampled envs, advanced to the same tick
+            pass
+    # replay the sampled envs on the oracle for T ticks and compare the final states + last outputs
+    st, stats, f, a = medium_oracle.rollout(T, 40, grids[ienv[sample].astype(np.int64)],
+                                            ipos[sample].astype(np.int32), itask[sample].astype(np.int32),
+                                            want_features=True)
+    ds = torch.from_numpy(sample).to(env.device)
+    assert np.array_equal(env.cells[ds].cpu().numpy(), st["grid"])
+    assert np.array_equal(env.pos[ds].cpu().numpy().astype(np.int32), st["pos"])
+    assert np.array_equal(env.inventory[ds].cpu().numpy().astype(np.int32), st["inv"])
+    assert np.array_equal(out["expert"][ds].cpu().numpy().astype(np.int32), a)
+    assert np.array_equal(feats[ds].cpu().numpy(), f)
+    s = env.stats.cpu().numpy()
+    ref_len = splits["train_ref_len"][idx].astype(np.int64)
+    assert s[2] == T * n and s[0] == s[1] == int((T // ref_len).sum())
+    env.check_errors()

@@ -29,3 +29,45 @@ def test_wire_format_accepts_both_task_spellings(medium_tables):
     p = data.from_wire([env], medium_tables)
     assert p["inst_task"].tolist() == [13, 19] and p["ref_len"].tolist() == [2, 3]
     assert p["grids"][0].reshape(8, 8)[3, 3] == 9 and p["ref_actions"][0].tolist() == [1, 5, 255]
+
+
+def test_dataset_mirror_batches_like_the_reference(splits, medium_tables, tmp_path):
+    """Dataset (data/dataset.py:12-93): same flattening and the same shuffled batch order for the
+    same RandomState; compared with the reference class itself when the checkout is present."""
+    import json
+    import os
+    import sys
+    import types
+    from psketch_b200 import data
+    packed = {k[4:]: splits[k] for k in splits.files if k.startswith("dev_")}
+    packed["inst_env"] = packed["inst_env"].astype(np.int32)
+    packed["ref_len"] = packed["ref_len"].astype(np.int32)
+    json.dump(data.to_wire(packed, medium_tables), open(str(tmp_path / "craft_medium_dev.json"), "w"))
+
+    def cfg(seed):
+        return types.SimpleNamespace(data_dir=str(tmp_path), world=types.SimpleNamespace(config="craft_medium"),
+                                     trainer=types.SimpleNamespace(batch_size=32, hints=None),
+                                     random=np.random.RandomState(seed))
+    ds = data.Dataset(cfg(3), "dev", medium_tables.task_manager)
+    assert len(ds) == 2200 and ds[0]["grid"].shape == (8, 8, 21) and ds[0]["task"].goal_name == "get"
+    assert ds.get_instance_by_id(ds[5]["id"]) is ds[5]
+    batches = list(ds.iterate_batches())
+    assert len(batches) == 69 and len(batches[-1]) == 2200 - 68 * 32
+    back = ds.packed(medium_tables)
+    assert np.array_equal(back["inst_pos"], packed["inst_pos"]) and np.array_equal(back["ref_actions"], packed["ref_actions"])
+    ref_root = "/root/reference"
+    if not os.path.isdir(os.path.join(ref_root, "data")):
+        return
+    sys.path.insert(0, ref_root)
+    try:
+        import importlib
+        for m in [m for m in sys.modules if m == "data" or m.startswith("data.")]:
+            del sys.modules[m]
+        ref_ds_mod = importlib.import_module("data.dataset")
+    finally:
+        sys.path.remove(ref_root)
+    rds = ref_ds_mod.Dataset(cfg(3), "dev", medium_tables.task_manager)
+    rb = list(rds.iterate_batches())
+    assert [[it["id"] for it in b] for b in rb] == [[it["id"] for it in b] for b in batches]
+    assert all(a["init_pos"] == b["init_pos"] and a["ref_actions"] == b["ref_actions"]
+               for a, b in zip(rds.data, ds.data))
