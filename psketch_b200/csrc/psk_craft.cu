@@ -1048,12 +1048,17 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
     __shared__ SharedTables st;
     __shared__ __align__(16) uint8_t s_rows[NE * CP];
     __shared__ __align__(16) uint32_t s_agent[NE * 8];
+    // Programmatic dependent launch: let the next kernel in the stream (normally the next tick)
+    // be scheduled while this one drains, and do everything that does not depend on the previous
+    // kernel (tables, buffer init) before waiting for it.  Both are no-ops for a plain launch.
+    asm volatile("griddepcontrol.launch_dependents;");
     stage_tables(st, T);
     const int tid = threadIdx.x;
     const bool env_warp = tid < NE;
     if (!USE_TMA && !env_warp && features_out)
         feature_buffer_init<8, KC, USE_TMA>(
             smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(4, nf), nf);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     uint32_t flags = 0;
     int it = 0;  // this feature warp's chunk counter
     const int64_t n_super = (n + NE - 1) / NE;
@@ -1315,10 +1320,25 @@ template <int W, int H, int WIN> struct Config {
         }
         if (g > tiles || !persist) g = tiles > 0 ? tiles : 1;
         PSK_DT(dt);
-        kern<<<(int)g, NE + NFW * 32, smem, st>>>(
-            dt, s.grid, s.agent, action_in, ep.scen_grid, ep.scen_idx, ep.init_agent, features_out,
-            expert_out, done, success, stats, err, s.n, s.cell_stride, t->n_kinds, f);
-        return check(cudaGetLastError());
+        static int pdl = -1;
+        if (pdl < 0) {
+            const char *v = getenv("PSK_TICK_PDL");
+            pdl = v ? atoi(v) : 1;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)g);
+        cfg.blockDim = dim3(NE + NFW * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        const int cell_stride = s.cell_stride, K = t->n_kinds;
+        return check(cudaLaunchKernelEx(&cfg, kern, dt, s.grid, s.agent, action_in, ep.scen_grid,
+                                        ep.scen_idx, ep.init_agent, features_out, expert_out, done,
+                                        success, stats, err, s.n, cell_stride, K, f));
     }
     static int tick_fused(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
                           const uint8_t *action_in, float *features_out, uint8_t *expert_out,
