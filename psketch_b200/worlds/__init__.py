@@ -1,12 +1,13 @@
-"""World factory with the reference's lookup-by-class-name contract (worlds/__init__.py:5-11)."""
-from .craft import CraftWorld, CraftScenario, CraftState  # noqa: F401
-from .light import LightWorld, LightScenario, LightState, VecLight  # noqa: F401
+"""World registry.  ``load(config)`` resolves ``config.world.name`` like the reference's factory
+(worlds/__init__.py:5-11) and raises the same ``Exception("No such world: ...")`` for unknown names."""
+from .craft import CraftScenario, CraftState, CraftWorld  # noqa: F401
+from .light import LightScenario, LightState, LightWorld, VecLight  # noqa: F401
+
+REGISTRY = {"CraftWorld": CraftWorld, "LightWorld": LightWorld}
 
 
 def load(config):
-    cls_name = config.world.name
-    try:
-        cls = globals()[cls_name]
-    except KeyError:
-        raise Exception("No such world: {}".format(cls_name))
-    return cls(config)
+    name = config.world.name
+    if name not in REGISTRY:
+        raise Exception("No such world: {}".format(name))
+    return REGISTRY[name](config)
