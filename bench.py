@@ -222,8 +222,12 @@ def run_ours(args):
     outs = [dict() for _ in range(ring)]
     fused = not args.unfused
 
+    rand_act = torch.empty(n, dtype=torch.uint8, device=dev) if args.policy == "random" else None
+
     def tick(i):
-        env.tick(features_out=feats[i % ring], fused=fused, out=outs[i % ring])
+        if rand_act is not None:        # off-policy variant: U{0..5} actions from Philox(123, (env, t))
+            env.random_actions(0, seed=123, out=rand_act, device_clock=True)
+        env.tick(actions=rand_act, features_out=feats[i % ring], fused=fused, out=outs[i % ring])
 
     for i in range(ring):           # allocate output tensors outside the graph
         tick(i)
@@ -308,7 +312,7 @@ def run_ours(args):
 
     peak, peak_src = measured_peaks()
     per_launch_s = elapsed / K
-    launches_per_step = 1 if fused else 3
+    launches_per_step = (1 if fused else 3) + (1 if rand_act is not None else 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": per_launch_s * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -316,7 +320,7 @@ def run_ours(args):
         "config": {
             "workload": "craft_medium train tasks (17,600 instances tiled), %d parallel envs per GPU, "
                         "teacher BFS + f32[404] features + step/auto-reset per tick" % n,
-            "envs_per_gpu": n, "max_timesteps": 40,
+            "envs_per_gpu": n, "max_timesteps": 40, "policy": args.policy,
             "kernel": "craft_tick_kernel (fused, warp-specialised)" if fused else "expert+features+advance",
             "cuda_graph": graph is not None,
             "l2": "feature outputs rotate through a ring of %d buffers (%.0f MB > 126 MB L2)"
@@ -419,6 +423,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=16384)
+    ap.add_argument("--policy", default="teacher", choices=["teacher", "random"],
+                    help="who acts: the teacher (BASELINE config) or uniform random actions (off-policy variant)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -157,6 +157,13 @@ int psk_craft_sample_scenarios(const psk_craft_tables *t, uint8_t *scen_grid, ui
                                uint64_t seed, uint64_t offset, int64_t n, int32_t cell_stride,
                                int32_t *fail_count, void *stream);
 
+/* Uniform random actions for off-policy rollouts: out[e] in [0, n_actions) from
+ * Philox4x32-10(key = seed, counter = (e, t + *t_dev)); t_dev (device, may be NULL) lets a counter
+ * that lives on the device (e.g. stats[2], the env-step count) advance the clock under CUDA-graph
+ * replay. */
+int psk_random_actions(uint8_t *out, int64_t n, int32_t n_actions, uint64_t seed, uint64_t t,
+                       const unsigned long long *t_dev, void *stream);
+
 /* Dataset instance positions (make_data.py:203-208): per group, `per_group` distinct uniformly
  * random free cells of scenario group_scen[g]; out_pos u8[n_groups][per_group][2]. */
 int psk_craft_sample_positions(const psk_craft_tables *t, const uint8_t *scen_grid,

@@ -22,6 +22,7 @@ CRAFT_EXPORTS = (
     "psk_craft_reset", "psk_craft_tick", "psk_host_alloc", "psk_host_free",
     "psk_craft_host_create", "psk_craft_host_destroy", "psk_craft_host_set_episodes",
     "psk_craft_host_tick", "psk_craft_sample_scenarios", "psk_craft_sample_positions",
+    "psk_random_actions",
 )
 
 
@@ -93,6 +94,7 @@ def load():
     u64 = ctypes.c_uint64
     lib.psk_craft_sample_scenarios.argtypes = [tp, vp, vp, vp, i32, i32, u64, u64, i64, i32, vp, vp]
     lib.psk_craft_sample_positions.argtypes = [tp, vp, vp, i32, vp, u64, u64, i64, i32, vp, vp]
+    lib.psk_random_actions.argtypes = [vp, i64, i32, u64, u64, vp, vp]
     for name in CRAFT_EXPORTS[1:]:
         if name not in ("psk_host_alloc", "psk_host_free", "psk_craft_host_destroy"):
             getattr(lib, name).restype = ctypes.c_int

@@ -172,6 +172,19 @@ craft_sample_positions_kernel(const uint8_t *__restrict__ scen_grid,
     }
 }
 
+// Off-policy action source: action[e] ~ U{0..n_actions-1} from
+// Philox(key = seed, counter = (env, t)): reproducible whatever the launch geometry.
+__global__ void __launch_bounds__(256)
+random_actions_kernel(uint8_t *__restrict__ out, int64_t n, int n_actions, uint64_t seed, uint64_t t,
+                      const unsigned long long *__restrict__ t_dev) {
+    if (t_dev) t += *t_dev;   // device-side clock (e.g. the env-step counter): advances under graph replay
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        Philox rng(seed, (uint64_t)e, t);
+        out[e] = (uint8_t)rng.below(n_actions);
+    }
+}
+
 static inline int blocks_for(int64_t n) {
     int64_t b = (n + 127) / 128;
     return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
@@ -200,6 +213,16 @@ int psk_craft_sample_scenarios(const psk_craft_tables *t, uint8_t *scen_grid, ui
             scen_grid, init_pos, place_kinds, n_place, boundary_kind, seed, offset, n, cell_stride, fail_count);
     else
         return PSK_ERR_UNSUPPORTED;
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+int psk_random_actions(uint8_t *out, int64_t n, int32_t n_actions, uint64_t seed, uint64_t t,
+                       const unsigned long long *t_dev, void *stream) {
+    if (n < 0 || n_actions <= 0 || n_actions > 255 || (n && !out)) return PSK_ERR_BADARG;
+    if (n == 0) return PSK_OK;
+    int64_t b = (n + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    random_actions_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(out, n, n_actions, seed, t, t_dev);
     return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
 }
 

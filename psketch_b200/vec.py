@@ -209,6 +209,19 @@ class VecCraft(object):
         _lib.check(rc, "psk_craft_tick")
         return out
 
+    def random_actions(self, t=0, seed=123, out=None, device_clock=False):
+        """u8[N] uniform actions from Philox(seed, counter=(env, t)) — off-policy rollouts.
+        device_clock=True adds the env-step counter (stats[2]) to t on the device, so a captured
+        CUDA graph draws fresh actions on every replay."""
+        if out is None:
+            out = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        clock = ctypes.c_void_p(self.stats.data_ptr() + 16) if device_clock else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.psk_random_actions(_ptr(out), self.n, 6, ctypes.c_uint64(seed),
+                                             ctypes.c_uint64(t), clock, self._stream())
+        _lib.check(rc, "psk_random_actions")
+        return out
+
     # ------------------------------------------------------------------ views / checks
     @property
     def pos(self):

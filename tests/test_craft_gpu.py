@@ -312,3 +312,15 @@ def test_million_env_properties(splits, medium_tables, medium_oracle):
     ref_len = splits["train_ref_len"][idx].astype(np.int64)
     assert s[2] == T * n and s[0] == s[1] == int((T // ref_len).sum())
     env.check_errors()
+
+
+def test_random_actions_are_uniform_and_reproducible(medium_tables, medium_states):
+    S = {k: medium_states[k][:4096] for k in ("grid", "inv", "pos", "dir")}
+    env = _env_from_states(medium_tables, S)
+    a0 = env.random_actions(0).cpu().numpy()
+    assert np.array_equal(a0, env.random_actions(0).cpu().numpy())
+    a1 = env.random_actions(1).cpu().numpy()
+    assert not np.array_equal(a0, a1) and a0.max() == 5 and a0.min() == 0
+    big = np.concatenate([env.random_actions(t).cpu().numpy() for t in range(50)])
+    hist = np.bincount(big, minlength=6) / len(big)
+    assert np.abs(hist - 1 / 6).max() < 0.005
