@@ -17,7 +17,7 @@ from psketch_b200.vec import VecCraft  # noqa: E402
 def stress_env(size, n):
     from test_stress_gpu import _random_states, _tables
     tables = _tables(size)
-    m = min(n, 4096)
+    m = min(n, 4096 if size < 64 else 512)
     grid, inv, pos, dirs, task = _random_states(tables, m, seed=size, wall_frac=0.2)
     rep = (n + m - 1) // m
     tile = lambda a: np.concatenate([a] * rep)[:n]
@@ -28,7 +28,7 @@ def main():
     time_it = "--time" in sys.argv
     n = 65536
     rows = []
-    for size in (16, 32):
+    for size in (16, 32, 64):
         env = stress_env(size, n)
         act = env.expert()
         feats = env.features()

@@ -438,130 +438,244 @@ craft_find_closest_kernel(const psk_craft_tables *__restrict__ T,
 }
 
 // =============================================================================================
-// enlarged grids (W, H <= 32): one WARP per env, lane x = row x of every board as a 32-bit word
+// enlarged grids (W, H <= 64): one WARP per env, rows of every board spread over the lanes
 // =============================================================================================
 // Same two floods as bfs_first_action, with the boards laid out row-per-lane: vertical moves
 // (y +- 1) are bit shifts inside a lane, horizontal moves (x +- 1) are __shfl_up/down_sync
 // between lanes, emptiness tests are __ballot_sync / __any_sync.  Every value is warp-uniform in
 // control flow, so there is no divergence at all; the reference's 1000-slot queue
 // (teachers/base.py:42) would overflow on these sizes, the floods have no such limit.
-template <int W, int H> struct Rows {
-    static_assert(W <= 32 && H <= 32, "row-per-lane boards cover up to 32 x 32");
+// Up to 32 rows: lane x holds row x.  Up to 64 rows: lane l holds rows 2l and 2l+1, so a
+// horizontal move is one register move plus one shuffle.  Rows are 32- or 64-bit words.
+template <int H> struct RowWord { using type = uint64_t; };
+template <> struct RowWord<32> { using type = uint32_t; };
+
+template <int W, int H> struct RowBoard {
+    static_assert(W <= 64 && H <= 64, "row-per-lane boards cover up to 64 x 64");
+    static constexpr int RPL = W > 32 ? 2 : 1;   // rows per lane
+    using RT = typename RowWord<(H > 32 ? 64 : 32)>::type;
     static constexpr unsigned FULL = 0xffffffffu;
-    static constexpr uint32_t HMASK = H == 32 ? 0xffffffffu : ((1u << (H % 32)) - 1u);
-    // positions p + delta(A) for p in v
-    template <int A> static __device__ __forceinline__ uint32_t shift(uint32_t v, int lane) {
-        if (A == 0) return v >> 1;                               // DOWN  (0,-1)
-        if (A == 1) return (v << 1) & HMASK;                     // UP    (0,+1)
-        if (A == 2) {                                            // LEFT  (-1,0): row x <- row x+1
-            const uint32_t t = __shfl_down_sync(FULL, v, 1);
-            return lane < W - 1 ? t : 0u;
+    RT r[RPL];
+
+    static __device__ __forceinline__ RT hmask() {
+        return H == 8 * (int)sizeof(RT) ? ~RT(0) : ((RT(1) << (H % (8 * (int)sizeof(RT)))) - 1);
+    }
+    static __device__ __forceinline__ int row_of(int lane, int slot) { return RPL * lane + slot; }
+    static __device__ __forceinline__ RowBoard zero() {
+        RowBoard b;
+#pragma unroll
+        for (int s = 0; s < RPL; s++) b.r[s] = 0;
+        return b;
+    }
+    static __device__ __forceinline__ RowBoard bit(int x, int y, int lane) {
+        RowBoard b = zero();
+#pragma unroll
+        for (int s = 0; s < RPL; s++)
+            if (row_of(lane, s) == x) b.r[s] = RT(1) << y;
+        return b;
+    }
+    __device__ __forceinline__ RowBoard operator&(const RowBoard &o) const {
+        RowBoard b;
+#pragma unroll
+        for (int s = 0; s < RPL; s++) b.r[s] = r[s] & o.r[s];
+        return b;
+    }
+    __device__ __forceinline__ RowBoard operator|(const RowBoard &o) const {
+        RowBoard b;
+#pragma unroll
+        for (int s = 0; s < RPL; s++) b.r[s] = r[s] | o.r[s];
+        return b;
+    }
+    __device__ __forceinline__ bool lane_any() const {
+        RT t = 0;
+#pragma unroll
+        for (int s = 0; s < RPL; s++) t |= r[s];
+        return t != 0;
+    }
+    __device__ __forceinline__ bool any() const { return __any_sync(FULL, lane_any()); }
+    __device__ __forceinline__ bool differs(const RowBoard &o) const {
+        bool d = false;
+#pragma unroll
+        for (int s = 0; s < RPL; s++) d |= r[s] != o.r[s];
+        return __any_sync(FULL, d);
+    }
+    // free cells from an occupancy board: complement within the grid
+    __device__ __forceinline__ RowBoard free_of(int lane) const {
+        RowBoard b;
+#pragma unroll
+        for (int s = 0; s < RPL; s++) b.r[s] = row_of(lane, s) < W ? (~r[s] & hmask()) : RT(0);
+        return b;
+    }
+    // positions p + delta(A) for p in this board
+    template <int A> __device__ __forceinline__ RowBoard shift(int lane) const {
+        RowBoard b;
+        if (A == 0) {                                   // DOWN  (0,-1)
+#pragma unroll
+            for (int s = 0; s < RPL; s++) b.r[s] = r[s] >> 1;
+        } else if (A == 1) {                            // UP    (0,+1)
+#pragma unroll
+            for (int s = 0; s < RPL; s++) b.r[s] = (r[s] << 1) & hmask();
+        } else if (A == 2) {                            // LEFT  (-1,0): row x <- row x+1
+            const RT nxt = __shfl_down_sync(FULL, r[0], 1);      // first row of the next lane
+            if (RPL == 1) b.r[0] = lane < 31 ? nxt : RT(0);
+            else {
+                b.r[0] = r[RPL - 1];
+                b.r[RPL - 1] = lane < 31 ? nxt : RT(0);
+            }
+        } else {                                        // RIGHT (+1,0): row x <- row x-1
+            const RT prv = __shfl_up_sync(FULL, r[RPL - 1], 1);  // last row of the previous lane
+            if (RPL == 1) b.r[0] = lane > 0 ? prv : RT(0);
+            else {
+                b.r[RPL - 1] = r[0];
+                b.r[0] = lane > 0 ? prv : RT(0);
+            }
         }
-        const uint32_t t = __shfl_up_sync(FULL, v, 1);           // RIGHT (+1,0): row x <- row x-1
-        return (lane > 0 && lane < W) ? t : 0u;
+#pragma unroll
+        for (int s = 0; s < RPL; s++)
+            if (row_of(lane, s) >= W) b.r[s] = 0;
+        return b;
     }
-    template <int A> static __device__ __forceinline__ uint32_t unshift(uint32_t v, int lane) {
-        return shift<(A ^ 1)>(v, lane);
+    template <int A> __device__ __forceinline__ RowBoard unshift(int lane) const {
+        return shift<(A ^ 1)>(lane);
     }
-    static __device__ __forceinline__ uint32_t spread(uint32_t v, int lane) {
-        return shift<0>(v, lane) | shift<1>(v, lane) | shift<2>(v, lane) | shift<3>(v, lane);
+    __device__ __forceinline__ RowBoard spread(int lane) const {
+        return shift<0>(lane) | shift<1>(lane) | shift<2>(lane) | shift<3>(lane);
+    }
+    // row `x` of the board, broadcast to every lane
+    __device__ __forceinline__ RT row(int x) const {
+        RT v = __shfl_sync(FULL, r[0], x / RPL);
+        if (RPL == 2) {
+            const RT v1 = __shfl_sync(FULL, r[RPL - 1], x / RPL);
+            if (x % RPL) v = v1;
+        }
+        return v;
+    }
+    static __device__ __forceinline__ int low_bit(RT v) {
+        return sizeof(RT) == 8 ? __ffsll((long long)v) - 1 : __ffs((int)v) - 1;
+    }
+    static __device__ __forceinline__ int high_bit(RT v) {
+        return sizeof(RT) == 8 ? 63 - __clzll((long long)v) : 31 - __clz((int)v);
+    }
+    // lowest / highest cell in x-major order (np.nonzero order); false when empty
+    __device__ __forceinline__ bool lowest(int &x, int &y) const {
+        const unsigned m = __ballot_sync(FULL, lane_any());
+        if (!m) return false;
+        const int l = __ffs(m) - 1;
+        const RT a = __shfl_sync(FULL, r[0], l), b = __shfl_sync(FULL, r[RPL - 1], l);
+        const int slot = (RPL == 2 && a == 0) ? 1 : 0;
+        x = RPL * l + slot;
+        y = low_bit(slot ? b : a);
+        return true;
+    }
+    __device__ __forceinline__ bool highest(int &x, int &y) const {
+        const unsigned m = __ballot_sync(FULL, lane_any());
+        if (!m) return false;
+        const int l = 31 - __clz(m);
+        const RT a = __shfl_sync(FULL, r[0], l), b = __shfl_sync(FULL, r[RPL - 1], l);
+        const int slot = (RPL == 2 && b != 0) ? 1 : 0;
+        x = RPL * l + slot;
+        y = high_bit(slot ? b : a);
+        return true;
     }
 };
 
-// occupancy / goal row of this lane's row from the env's grid row (global memory)
+// occupancy / goal boards of this lane's rows from the env's grid row (global memory)
 template <int W, int H>
 __device__ __forceinline__ void build_rows(const uint8_t *row, int lane, int goal_kind,
-                                           uint32_t &occ, uint32_t &goal) {
-    occ = 0;
-    goal = 0;
-    if (lane < W) {
-        const uint8_t *p = row + lane * H;
-        if (H % 4 == 0) {
+                                           RowBoard<W, H> &occ, RowBoard<W, H> &goal) {
+    using RB = RowBoard<W, H>;
+    using RT = typename RB::RT;
 #pragma unroll
-            for (int i = 0; i < H / 4; i++) {
-                const uint32_t w = *reinterpret_cast<const uint32_t *>(p + 4 * i);
-                const uint32_t nz = nonzero_flags(w);
-                const uint32_t eq = nonzero_flags(w ^ (uint32_t(goal_kind) * 0x01010101u)) ^ 0x80808080u;
-                occ |= ((nz * 0x00204081u) >> 28) << (4 * i);
-                goal |= ((eq * 0x00204081u) >> 28) << (4 * i);
+    for (int s = 0; s < RB::RPL; s++) {
+        RT o = 0, g = 0;
+        const int x = RB::row_of(lane, s);
+        if (x < W) {
+            const uint8_t *p = row + x * H;
+            if (H % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < H / 4; i++) {
+                    const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(p + 4 * i));
+                    const uint32_t nz = nonzero_flags(w);
+                    const uint32_t eq = nonzero_flags(w ^ (uint32_t(goal_kind) * 0x01010101u)) ^ 0x80808080u;
+                    o |= RT((nz * 0x00204081u) >> 28) << (4 * i);
+                    g |= RT((eq * 0x00204081u) >> 28) << (4 * i);
+                }
+            } else {
+                for (int y = 0; y < H; y++) {
+                    const int k = p[y];
+                    o |= RT(k != 0) << y;
+                    g |= RT(k == goal_kind) << y;
+                }
             }
         } else {
-            for (int y = 0; y < H; y++) {
-                const int k = p[y];
-                occ |= uint32_t(k != 0) << y;
-                goal |= uint32_t(k == goal_kind) << y;
-            }
+            o = RB::hmask();   // rows beyond the grid are solid
         }
-    } else {
-        occ = Rows<W, H>::HMASK;   // rows beyond the grid are solid
+        occ.r[s] = o;
+        goal.r[s] = goal_kind ? g : RT(0);
     }
-    if (goal_kind == 0) goal = 0;
 }
 
 // Warp-cooperative twin of bfs_first_action.  All lanes return the same values.
 template <int W, int H>
-__device__ __forceinline__ int bfs_rows(bool need, uint32_t occ, uint32_t goal, int px, int py,
-                                        int d0, int lane, int &first, int &gx, int &gy) {
-    using R = Rows<W, H>;
-    constexpr unsigned FULL = R::FULL;
-    const uint32_t freeb = ~occ & R::HMASK & (lane < W ? 0xffffffffu : 0u);
-    const uint32_t root = lane == px ? (1u << py) : 0u;
+__device__ __forceinline__ int bfs_rows(bool need, const RowBoard<W, H> &occ,
+                                        const RowBoard<W, H> &goal, int px, int py, int d0,
+                                        int lane, int &first, int &gx, int &gy) {
+    using RB = RowBoard<W, H>;
+    const RB freeb = occ.free_of(lane);
+    const RB root = RB::bit(px, py, lane);
     first = -1;
     gx = gy = -1;
     {   // depth 0: already facing a goal cell
         const int fx = px + dx_of(d0), fy = py + dy_of(d0);
         const bool in = fx >= 0 && fy >= 0 && fx < W && fy < H;
-        const uint32_t grow = __shfl_sync(FULL, goal, in ? fx : 0);
+        const typename RB::RT grow = goal.row(in ? fx : 0);
         if (need && in && ((grow >> fy) & 1)) {
             gx = fx;
             gy = fy;
             return 0;
         }
     }
-    const uint32_t T0 = R::template unshift<0>(goal, lane), T1 = R::template unshift<1>(goal, lane),
-                   T2 = R::template unshift<2>(goal, lane), T3 = R::template unshift<3>(goal, lane);
-    const uint32_t src_all = T0 | T1 | T2 | T3 | R::template unshift<0>(freeb & T0, lane) |
-                             R::template unshift<1>(freeb & T1, lane) |
-                             R::template unshift<2>(freeb & T2, lane) |
-                             R::template unshift<3>(freeb & T3, lane);
-    if (!need || !__any_sync(FULL, goal != 0)) return -1;
-    uint32_t VF = root;
+    const RB T0 = goal.template unshift<0>(lane), T1 = goal.template unshift<1>(lane),
+             T2 = goal.template unshift<2>(lane), T3 = goal.template unshift<3>(lane);
+    const RB src_all = T0 | T1 | T2 | T3 | (freeb & T0).template unshift<0>(lane) |
+                       (freeb & T1).template unshift<1>(lane) |
+                       (freeb & T2).template unshift<2>(lane) |
+                       (freeb & T3).template unshift<3>(lane);
+    if (!need || !goal.any()) return -1;
+    RB VF = root;
     int k = 0;
-    while (!__any_sync(FULL, (VF & src_all) != 0)) {
-        const uint32_t nv = VF | (R::spread(VF, lane) & freeb);
-        if (!__any_sync(FULL, nv != VF)) return -1;          // queue drained (base.py:87)
+    while (!(VF & src_all).any()) {
+        const RB nv = VF | (VF.spread(lane) & freeb);
+        if (!nv.differs(VF)) return -1;                 // queue drained (base.py:87)
         VF = nv;
         k++;
     }
-    const uint32_t hit =
-        (R::template shift<0>(VF & T0, lane) | R::template shift<1>(VF & T1, lane) |
-         R::template shift<2>(VF & T2, lane) | R::template shift<3>(VF & T3, lane) |
-         R::template shift<0>(R::template shift<0>(VF, lane) & freeb & T0, lane) |
-         R::template shift<1>(R::template shift<1>(VF, lane) & freeb & T1, lane) |
-         R::template shift<2>(R::template shift<2>(VF, lane) & freeb & T2, lane) |
-         R::template shift<3>(R::template shift<3>(VF, lane) & freeb & T3, lane)) & goal;
-    // lowest cell index x*H + y: lowest row with a hit, lowest bit in it (np.nonzero order)
-    gx = __ffs(__ballot_sync(FULL, hit != 0)) - 1;
-    gy = __ffs(__shfl_sync(FULL, hit, gx)) - 1;
-    const uint32_t g = lane == gx ? (1u << gy) : 0u;
-    const uint32_t g0 = R::template unshift<0>(g, lane), g1 = R::template unshift<1>(g, lane),
-                   g2 = R::template unshift<2>(g, lane), g3 = R::template unshift<3>(g, lane);
-    const uint32_t s0 = g0 | R::template unshift<0>(freeb & g0, lane),
-                   s1 = g1 | R::template unshift<1>(freeb & g1, lane),
-                   s2 = g2 | R::template unshift<2>(freeb & g2, lane),
-                   s3 = g3 | R::template unshift<3>(freeb & g3, lane);
+    const RB hit =
+        ((VF & T0).template shift<0>(lane) | (VF & T1).template shift<1>(lane) |
+         (VF & T2).template shift<2>(lane) | (VF & T3).template shift<3>(lane) |
+         (VF.template shift<0>(lane) & freeb & T0).template shift<0>(lane) |
+         (VF.template shift<1>(lane) & freeb & T1).template shift<1>(lane) |
+         (VF.template shift<2>(lane) & freeb & T2).template shift<2>(lane) |
+         (VF.template shift<3>(lane) & freeb & T3).template shift<3>(lane)) & goal;
+    hit.lowest(gx, gy);                                 // lowest cell index (np.nonzero order)
+    const RB g = RB::bit(gx, gy, lane);
+    const RB g0 = g.template unshift<0>(lane), g1 = g.template unshift<1>(lane),
+             g2 = g.template unshift<2>(lane), g3 = g.template unshift<3>(lane);
+    const RB s0 = g0 | (freeb & g0).template unshift<0>(lane),
+             s1 = g1 | (freeb & g1).template unshift<1>(lane),
+             s2 = g2 | (freeb & g2).template unshift<2>(lane),
+             s3 = g3 | (freeb & g3).template unshift<3>(lane);
     if (k == 0) {
-        first = __any_sync(FULL, (root & s0) != 0) ? 0 : __any_sync(FULL, (root & s1) != 0) ? 1
-              : __any_sync(FULL, (root & s2) != 0) ? 2 : 3;
+        first = (root & s0).any() ? 0 : (root & s1).any() ? 1 : (root & s2).any() ? 2 : 3;
         return 1;
     }
-    uint32_t VB = (s0 | s1 | s2 | s3) & VF;
-    for (int j = 1; j < k; j++) VB |= R::spread(VB, lane) & freeb;
-    const uint32_t ok = VB & freeb;
-    first = __any_sync(FULL, (R::template shift<0>(root, lane) & ok) != 0)   ? 0
-            : __any_sync(FULL, (R::template shift<1>(root, lane) & ok) != 0) ? 1
-            : __any_sync(FULL, (R::template shift<2>(root, lane) & ok) != 0) ? 2
-                                                                              : 3;
+    RB VB = (s0 | s1 | s2 | s3) & VF;
+    for (int j = 1; j < k; j++) VB = VB | (VB.spread(lane) & freeb);
+    const RB ok = VB & freeb;
+    first = (root.template shift<0>(lane) & ok).any()   ? 0
+            : (root.template shift<1>(lane) & ok).any() ? 1
+            : (root.template shift<2>(lane) & ok).any() ? 2
+                                                        : 3;
     return k + 1;
 }
 
@@ -583,7 +697,7 @@ craft_expert_rows_kernel(const psk_craft_tables *__restrict__ T, const uint8_t *
         const uint32_t leaf = find_incomplete(st, tk, a, facing);
         const int kind = (leaf >> 16) & 0x7F;
         const bool need = leaf && kind == LEAF_GO;
-        uint32_t occ, goal;
+        RowBoard<W, H> occ, goal;
         build_rows<W, H>(row, lane, need ? (leaf >> 8) & 0xFF : 0, occ, goal);
         int first, gx, gy;
         const int d = bfs_rows<W, H>(need, occ, goal, a.x(), a.y(), a.dir(), lane, first, gx, gy);
@@ -607,25 +721,18 @@ craft_find_closest_rows_kernel(const uint8_t *__restrict__ grid, const uint8_t *
                                const uint8_t *__restrict__ kind, uint8_t *__restrict__ goal_out,
                                int16_t *__restrict__ len_out, uint8_t *__restrict__ seq,
                                int seq_cap, int64_t n, int cell_stride) {
-    constexpr unsigned FULL = 0xffffffffu;
+    using RB = RowBoard<W, H>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     for (int64_t e = blockIdx.x * (int64_t)wpb + warp; e < n; e += (int64_t)gridDim.x * wpb) {
         const Agent a = load_agent_ro(agent, e);
         const uint8_t *row = grid + e * cell_stride;
-        uint32_t occ, goal;
+        RB occ, goal;
         build_rows<W, H>(row, lane, kind[e], occ, goal);
         int x = a.x(), y = a.y(), d = a.dir(), first, gx, gy;
         const int len = bfs_rows<W, H>(true, occ, goal, x, y, d, lane, first, gx, gy);
         if (len < 0) {
             // last goal cell in scan order (teachers/base.py:31 keeps replacing while None)
-            const unsigned m = __ballot_sync(FULL, goal != 0);
-            int lx = 255, ly = 255;
-            if (m) {
-                lx = 31 - __clz(m);
-                ly = 31 - __clz(__shfl_sync(FULL, goal, lx));
-            }
-            gx = lx;
-            gy = ly;
+            if (!goal.highest(gx, gy)) gx = gy = 255;
         }
         if (lane == 0) {
             len_out[e] = (int16_t)len;
@@ -634,13 +741,13 @@ craft_find_closest_rows_kernel(const uint8_t *__restrict__ grid, const uint8_t *
         }
         if (seq) {
             uint8_t *sq = seq + e * (int64_t)seq_cap;
-            const uint32_t g1 = (len > 0 && lane == gx) ? (1u << gy) : 0u;
+            const RB g1 = len > 0 ? RB::bit(gx, gy, lane) : RB::zero();
             int f = first;
             for (int k = 0; k < len; k++) {
                 if (lane == 0 && k < seq_cap) sq[k] = (uint8_t)f;
                 const int tx = x + dx_of(f), ty = y + dy_of(f);
                 const bool in = tx >= 0 && ty >= 0 && tx < W && ty < H;
-                const uint32_t orow = __shfl_sync(FULL, occ, in ? tx : 0);
+                const typename RB::RT orow = occ.row(in ? tx : 0);
                 if (in && !((orow >> ty) & 1)) { x = tx; y = ty; }
                 d = f;
                 if (k + 1 < len) {
@@ -673,25 +780,33 @@ __device__ __forceinline__ void sts_zero16(uint32_t addr) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0) : "memory");
 }
 
-// The grid-row bytes one feature thread owns: NCH chunks of 8 consecutive cells.
+// The grid-row bytes one feature thread owns: NCH chunks of 8 consecutive cells.  Grids above
+// 128 cells are not copied at all (WINDOWED): the features only depend on the WIN^2 x WIN^2
+// window around the agent, so the scatter gathers those cells straight from the row.
 template <int W, int H, int TPE> struct RowChunks {
+    static constexpr bool WINDOWED = W * H > 128;
     static constexpr int CP = ((W * H + 63) / 64) * 64;
-    static constexpr int NCH = CP / (8 * TPE);
+    static constexpr int NCH = WINDOWED ? 1 : CP / (8 * TPE);
     uint2 v[NCH];
+    const uint8_t *row;
     // thread j of the env reads cells [j*NCH*8, (j+1)*NCH*8) (global or shared, 8-byte aligned)
-    __device__ __forceinline__ void load(const uint8_t *row, int j) {
+    __device__ __forceinline__ void load(const uint8_t *r, int j) {
+        row = r;
+        if (WINDOWED) return;
 #pragma unroll
         for (int c = 0; c < NCH; c++)
-            v[c] = *reinterpret_cast<const uint2 *>(row + (j * NCH + c) * 8);
+            v[c] = *reinterpret_cast<const uint2 *>(r + (j * NCH + c) * 8);
     }
     // same from global memory, as volatile asm: the load is issued where it is written (the
     // prefetch of the next chunk), not sunk by the compiler to its first use an iteration later
-    __device__ __forceinline__ void prefetch(const uint8_t *row, int j) {
+    __device__ __forceinline__ void prefetch(const uint8_t *r, int j) {
+        row = r;
+        if (WINDOWED) return;
 #pragma unroll
         for (int c = 0; c < NCH; c++)
             asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];"
                          : "=r"(v[c].x), "=r"(v[c].y)
-                         : "l"(row + (j * NCH + c) * 8));
+                         : "l"(r + (j * NCH + c) * 8));
     }
 };
 
@@ -709,6 +824,19 @@ __device__ __forceinline__ void scatter_features(uint32_t frow_s, uint32_t trash
     const int px = a.x(), py = a.y();
     const int K4 = K * 4;
     const uint32_t big_s = frow_s + WW * K4;
+    if (RowChunks<W, H, TPE>::WINDOWED) {
+        // gather the WW x WW window cells (thread j takes every TPE-th)
+        for (int idx = j; idx < WW * WW; idx += TPE) {
+            const int bx = idx / WW, by = idx % WW;
+            const int x = px - BHW + bx, y = py - BHW + by;
+            if (x < 0 || y < 0 || x >= W || y >= H) continue;
+            const int k = __ldg(cells.row + x * H + y);
+            if (k == 0) continue;
+            sts_f32(big_s + (((bx / WIN) * WIN + (by / WIN)) * K + k) * 4, 1.0f);
+            if (bx / WIN == HW && by / WIN == HW)
+                sts_f32(frow_s + (((bx - HW * WIN) * WIN + (by - HW * WIN)) * K + k) * 4, 1.0f);
+        }
+    } else
 #pragma unroll
     for (int ch = 0; ch < NCH; ch++) {
         const int cc = (j * NCH + ch) * 8;
@@ -1382,6 +1510,7 @@ using Medium = Config<8, 8, 3>;    // configs/worlds/craft_medium.yaml
 using Large = Config<10, 10, 5>;   // configs/worlds/craft_large.yaml
 using Stress16 = Config<16, 16, 3>;  // enlarged-grid stress tests (BASELINE configs[4])
 using Stress32 = Config<32, 32, 3>;
+using Stress64 = Config<64, 64, 3>;
 
 #define PSK_DISPATCH(t, CALL)                             \
     do {                                                  \
@@ -1389,6 +1518,7 @@ using Stress32 = Config<32, 32, 3>;
         if (Large::matches(t)) return Large::CALL;        \
         if (Stress16::matches(t)) return Stress16::CALL;  \
         if (Stress32::matches(t)) return Stress32::CALL;  \
+        if (Stress64::matches(t)) return Stress64::CALL;  \
         return PSK_ERR_UNSUPPORTED;                       \
     } while (0)
 
@@ -1413,7 +1543,8 @@ const char *psk_version(void) { return "psketch_b200 0.1 sm_100a"; }
 
 int psk_craft_supported(const psk_craft_tables *t) {
     if (!t) return 0;
-    return Medium::matches(t) || Large::matches(t) || Stress16::matches(t) || Stress32::matches(t);
+    return Medium::matches(t) || Large::matches(t) || Stress16::matches(t) || Stress32::matches(t) ||
+           Stress64::matches(t);
 }
 
 int psk_craft_n_features(const psk_craft_tables *t) {

@@ -1,4 +1,4 @@
-"""Enlarged-grid Craft (16x16 and 32x32, BASELINE configs[4]): the warp-cooperative row-per-lane
+"""Enlarged-grid Craft (16x16, 32x32 and 64x64, BASELINE configs[4]): the warp-cooperative row-per-lane
 teacher, features, step and the (unfused) tick against the CPU oracle, whose BFS has the
 reference's 1000-slot queue cap lifted (it would overflow beyond ~250 free cells)."""
 import numpy as np
@@ -49,7 +49,8 @@ def _random_states(tables, n, seed, wall_frac):
     return grid.reshape(n, W * H), inv, pos, dirs, task
 
 
-@pytest.mark.parametrize("size,n,wall", [(16, 3000, 0.15), (16, 1500, 0.35), (32, 1500, 0.2), (32, 800, 0.4)])
+@pytest.mark.parametrize("size,n,wall", [(16, 3000, 0.15), (16, 1500, 0.35), (32, 1500, 0.2), (32, 800, 0.4),
+                                         (64, 500, 0.2), (64, 300, 0.4)])
 def test_enlarged_grid_parity(size, n, wall):
     from oracle.craft_oracle import CraftOracle
     from psketch_b200.vec import VecCraft
