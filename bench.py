@@ -223,16 +223,30 @@ def run_ours(args):
     fused = not args.unfused
 
     rand_act = torch.empty(n, dtype=torch.uint8, device=dev) if args.policy == "random" else None
+    # Teacher-driven rollouts need nothing from outside the kernel, so T ticks run per launch
+    # (psk_craft_rollout: state stays in shared memory between ticks).  T = 1, the random policy
+    # and --unfused use one psk_craft_tick launch per step.
+    T = max(1, args.ticks_per_launch) if (fused and rand_act is None) else 1
+    feat_ring = torch.stack(feats) if T > 1 else None
+    if T > 1:
+        feats = [feat_ring[i] for i in range(ring)]
+    rout = {}
 
     def tick(i):
         if rand_act is not None:        # off-policy variant: U{0..5} actions from Philox(123, (env, t))
             env.random_actions(0, seed=123, out=rand_act, device_clock=True)
         env.tick(actions=rand_act, features_out=feats[i % ring], fused=fused, out=outs[i % ring])
 
+    def launch_rollout():
+        env.rollout(T, features_out=feat_ring, out=rout, want_flags=True)
+
     for i in range(ring):           # allocate output tensors outside the graph
         tick(i)
+    if T > 1:
+        launch_rollout()
     torch.cuda.synchronize()
-    # CUDA graph of `ring` consecutive ticks (launch-bound otherwise: ~25 us of work per tick)
+    # CUDA graph of consecutive launches (launch-bound otherwise: ~20 us of work per tick)
+    per_graph = ring if T == 1 else 4          # launches per graph replay
     graph = None
     if not args.no_graph:
         side = torch.cuda.Stream(device=dev)
@@ -240,19 +254,31 @@ def run_ours(args):
         with torch.cuda.stream(side):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
-                for i in range(ring):
-                    tick(i)
+                for i in range(per_graph):
+                    if T > 1:
+                        launch_rollout()
+                    else:
+                        tick(i)
         torch.cuda.current_stream().wait_stream(side)
+    launches = [0]
+    per_tick_launches = (1 if fused else 3) + (1 if rand_act is not None else 0)
 
     def run_steps(k):
+        """Exactly k ticks: graph replays of per_graph launches of T ticks, then single launches."""
         done = 0
         if graph is not None:
-            while k - done >= ring:
+            while k - done >= per_graph * T:
                 graph.replay()
-                done += ring
+                done += per_graph * T
+                launches[0] += per_graph * (1 if T > 1 else per_tick_launches)
+        while T > 1 and k - done >= T:
+            launch_rollout()
+            done += T
+            launches[0] += 1
         while done < k:
             tick(done)
             done += 1
+            launches[0] += per_tick_launches
 
     sampler = ClockSampler(local) if rank == 0 else None
     run_steps(max(W, 3))
@@ -263,9 +289,11 @@ def run_ours(args):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.time()
+    launches[0] = 0
     start.record()
     run_steps(K)
     end.record()
+    timed_launches = launches[0]
     torch.cuda.synchronize()
     t1 = time.time()
     if distributed:
@@ -311,8 +339,7 @@ def run_ours(args):
         return
 
     peak, peak_src = measured_peaks()
-    per_launch_s = elapsed / K
-    launches_per_step = (1 if fused else 3) + (1 if rand_act is not None else 0)
+    per_launch_s = elapsed / K          # seconds per tick (= per step)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": per_launch_s * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -320,14 +347,15 @@ def run_ours(args):
         "config": {
             "workload": "craft_medium train tasks (17,600 instances tiled), %d parallel envs per GPU, "
                         "teacher BFS + f32[404] features + step/auto-reset per tick" % n,
-            "envs_per_gpu": n, "max_timesteps": 40, "policy": args.policy,
-            "kernel": "craft_tick_kernel (fused, warp-specialised)" if fused else "expert+features+advance",
+            "envs_per_gpu": n, "max_timesteps": 40, "policy": args.policy, "ticks_per_launch": T,
+            "kernel": ("craft_rollout_kernel (fused tick, %d ticks per launch)" % T if T > 1 else
+                       "craft_tick_kernel (fused, warp-specialised)") if fused else "expert+features+advance",
             "cuda_graph": graph is not None,
             "l2": "feature outputs rotate through a ring of %d buffers (%.0f MB > 126 MB L2)"
                   % (ring, ring * feat_bytes / 1e6),
         },
         "clocks": clocks,
-        "gpu_launches": K * launches_per_step,
+        "gpu_launches": timed_launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                 "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"], "how": e2e["how"]},
         "episodes": int(st[0]), "successes": int(st[1]),
@@ -341,11 +369,16 @@ def run_ours(args):
     except Exception:
         pass
     if fused:
-        achieved = BYTES_FUSED * n / per_launch_s / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "craft_tick_kernel", "achieved": achieved,
-                            "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": traffic, "peak_source": peak_src,
-                            "algorithmic_bytes_per_env_step": BYTES_FUSED}
+        # per env: T x (404 f32 features + action + done + success) + one state read and write
+        bytes_per_tick = BYTES_FUSED if T == 1 else (1616 + 3) + (2 * 96 + 4) / T
+        launch_s = elapsed / max(1, timed_launches)
+        ticks_per_launch_eff = K / max(1, timed_launches)
+        achieved = bytes_per_tick * ticks_per_launch_eff * n / launch_s / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "craft_rollout_kernel" if T > 1 else "craft_tick_kernel",
+                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": traffic if T == 1 else None, "peak_source": peak_src,
+                            "algorithmic_bytes_per_env_step": bytes_per_tick,
+                            "launch_us": launch_s * 1e6, "ticks_per_launch": ticks_per_launch_eff}
     # per-kernel numbers (north star: step and features as a fraction of the HBM roofline)
     kern = {}
     act = env.expert()
@@ -423,6 +456,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=16384)
+    ap.add_argument("--ticks-per-launch", type=int, default=8,
+                    help="teacher-driven rollouts run this many ticks per kernel launch (1 = one tick per launch)")
     ap.add_argument("--policy", default="teacher", choices=["teacher", "random"],
                     help="who acts: the teacher (BASELINE config) or uniform random actions (off-policy variant)")
     args = ap.parse_args()

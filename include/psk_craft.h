@@ -146,6 +146,18 @@ int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episo
                    uint8_t *done_out, uint8_t *success_out, unsigned long long *stats,
                    int32_t *err_flags, int fused, void *stream);
 
+/* `ticks` consecutive rollout ticks in ONE launch (same per-tick semantics as psk_craft_tick):
+ * every CTA keeps its envs' state in shared memory across the ticks, so HBM sees one state read,
+ * one state write and `ticks` output frames.  For rollouts whose actions do not depend on
+ * anything outside the kernel: teacher-driven (action_in NULL) or replay of action_in u8[ticks][n].
+ * expert_out u8[ticks][n]; done_out / success_out u8[ticks][n] (may be NULL); features_out
+ * f32[feat_ring][n][n_features] (may be NULL), tick t writes slot t % feat_ring. */
+int psk_craft_rollout(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
+                      int32_t ticks, const uint8_t *action_in, float *features_out,
+                      int32_t feat_ring, uint8_t *expert_out, uint8_t *done_out,
+                      uint8_t *success_out, unsigned long long *stats, int32_t *err_flags,
+                      void *stream);
+
 /* Scenario sampling (make_data.py:74-144, `random_free` / `sample_scenario`) with a counter-based
  * Philox4x32-10 generator: boundary ring, then place_kinds[0..n_place) in order, then the agent,
  * each at a uniformly random free cell that keeps all free cells connected and every occupied

@@ -75,7 +75,15 @@ def main():
     def k_tick_nofeat():
         env.tick(want_features=False, fused=True, out=out)
 
-    kernels = [("features_tma", k_features_tma, 1712), ("features_plain", k_features_plain, 1712),
+    T = 8
+    rfeat = torch.empty((max(ring, 2), n, nf), dtype=torch.float32, device=env.device)
+    rout = {}
+
+    def k_rollout8():
+        env.rollout(T, features_out=rfeat, out=rout)
+
+    kernels = [("rollout8_per_tick", k_rollout8, 1815 * T),
+               ("features_tma", k_features_tma, 1712), ("features_plain", k_features_plain, 1712),
                ("expert", k_expert, 97), ("step", k_step, 198), ("tick_fused", k_tick, 1815),
                ("tick_fused_nofeat", k_tick_nofeat, 199)]
     if args.only:
@@ -93,8 +101,12 @@ def main():
         for name, fn, b in kernels:
             env.restore(snap)
             dt = graph_time(fn, reps=20, inner=max(ring, 10) if "feat" in name or name == "tick_fused" else 10)
+            if name.startswith("rollout"):
+                dt /= T
             print("%-18s n=%d  %8.2f us  %7.1f GB/s (algorithmic %d B/env)  %.3e env/s  frac_of_6542.7=%.3f"
-                  % (name, n, dt * 1e6, b * n / dt / 1e9, b, n / dt, b * n / dt / 1e9 / 6542.7))
+                  % (name, n, dt * 1e6, (b / (T if name.startswith("rollout") else 1)) * n / dt / 1e9,
+                     b // (T if name.startswith("rollout") else 1), n / dt,
+                     (b / (T if name.startswith("rollout") else 1)) * n / dt / 1e9 / 6542.7))
     else:
         for name, fn, b in kernels:
             env.restore(snap)

@@ -22,7 +22,7 @@ CRAFT_EXPORTS = (
     "psk_craft_reset", "psk_craft_tick", "psk_host_alloc", "psk_host_free",
     "psk_craft_host_create", "psk_craft_host_destroy", "psk_craft_host_set_episodes",
     "psk_craft_host_tick", "psk_craft_sample_scenarios", "psk_craft_sample_positions",
-    "psk_random_actions",
+    "psk_random_actions", "psk_craft_rollout",
 )
 
 
@@ -82,6 +82,7 @@ def load():
     lib.psk_craft_tick.argtypes = [tp, CraftStateC, CraftEpisodesC, vp, vp, vp, vp, vp, vp, vp,
                                    i32, vp]
     i64 = ctypes.c_int64
+    lib.psk_craft_rollout.argtypes = [tp, CraftStateC, CraftEpisodesC, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.psk_host_alloc.argtypes = [ctypes.c_size_t]
     lib.psk_host_alloc.restype = ctypes.c_void_p
     lib.psk_host_free.argtypes = [vp]

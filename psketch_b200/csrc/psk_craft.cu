@@ -1269,6 +1269,157 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
 }
 
 // =============================================================================================
+// multi-tick rollout: the fused tick with the tick loop inside the kernel
+// =============================================================================================
+// Environments never interact, so a CTA can keep its NE envs for `ticks` consecutive ticks: the
+// state lives in shared memory (double-buffered: the feature warps read the state of tick t while
+// the env warps write the state of tick t+1) and in the env threads' registers; HBM sees one
+// state read, one state write and `ticks` feature/action frames per launch.  This removes the
+// per-tick launch, table staging and state reload, which is what bounds the single-tick kernel
+// at 65,536 envs.  Valid whenever the actions do not depend on anything outside the kernel:
+// teacher-driven rollouts (action_in == NULL) or replay of given action sequences.
+//   action_in   u8[ticks][n] or NULL;  expert_out u8[ticks][n];  done_out/success_out u8[ticks][n] or NULL
+//   features_out f32[feat_ring][n][nf] or NULL: tick t writes slot t % feat_ring
+template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA>
+__global__ void __launch_bounds__(NE + NFW * 32)
+craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
+                     uint8_t *__restrict__ agent, const uint8_t *__restrict__ action_in,
+                     const uint8_t *__restrict__ scen_grid, const int32_t *__restrict__ scen_idx,
+                     const uint8_t *__restrict__ init_agent, float *__restrict__ features_out,
+                     int feat_ring, uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
+                     uint8_t *__restrict__ success_out, unsigned long long *stats,
+                     int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int ticks) {
+    constexpr int NT = NE + NFW * 32;
+    constexpr int TPE = 8, EPW = 32 / TPE;
+    constexpr int SPW = NE / NFW;
+    static_assert(SPW % EPW == 0, "feature warps take whole chunks");
+    constexpr int CP = ((W * H + 63) / 64) * 64;
+    constexpr int NW4 = (W * H + 15) / 16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ SharedTables st;
+    __shared__ __align__(16) uint8_t s_rows[2][NE * CP];
+    __shared__ __align__(16) uint32_t s_agent[2][NE * 8];
+    asm volatile("griddepcontrol.launch_dependents;");
+    stage_tables(st, T);
+    const int tid = threadIdx.x;
+    const bool env_warp = tid < NE;
+    if (!USE_TMA && !env_warp && features_out)
+        feature_buffer_init<8, KC, USE_TMA>(
+            smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(4, nf), nf);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t flags = 0;
+    int it = 0;
+    const int64_t n_super = (n + NE - 1) / NE;
+    for (int64_t sp = blockIdx.x; sp < n_super; sp += gridDim.x) {
+        const int64_t e_base = sp * NE;
+        const int ne_sp = (int)((n - e_base) < NE ? (n - e_base) : NE);
+        {   // ---- state super-tile -> shared memory (buffer 0)
+            const uint4 *grow = reinterpret_cast<const uint4 *>(grid + e_base * CP);
+            uint4 *srow = reinterpret_cast<uint4 *>(s_rows[0]);
+            for (int i = tid; i < ne_sp * (CP / 16); i += NT) srow[i] = grow[i];
+            const uint4 *gag = reinterpret_cast<const uint4 *>(agent + e_base * PSK_AGENT_BYTES);
+            uint4 *sag = reinterpret_cast<uint4 *>(s_agent[0]);
+            for (int i = tid; i < ne_sp * 2; i += NT) sag[i] = gag[i];
+        }
+        __syncthreads();
+        const bool live = env_warp && tid < ne_sp;
+        const int slot = (env_warp && tid < ne_sp) ? tid : 0;
+        const int64_t e = e_base + slot;
+        Agent a;
+        const uint8_t *scen_row = nullptr;
+        int n_done = 0, n_succ = 0;
+        if (env_warp) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const uint4 v = reinterpret_cast<const uint4 *>(s_agent[0])[slot * 2 + i];
+                a.w[4 * i] = v.x; a.w[4 * i + 1] = v.y; a.w[4 * i + 2] = v.z; a.w[4 * i + 3] = v.w;
+            }
+            scen_row = scen_grid + (int64_t)scen_idx[e] * CP;
+        }
+        for (int t = 0; t < ticks; t++) {
+            const int cur = t & 1, nxt = cur ^ 1;
+            if (env_warp) {
+                const uint8_t *srow = s_rows[cur] + slot * CP;
+                uint8_t *nrow = s_rows[nxt] + slot * CP;
+                uint32_t words[NW4 * 4];
+#pragma unroll
+                for (int i = 0; i < NW4; i++) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(srow)[i];
+                    words[4 * i] = v.x; words[4 * i + 1] = v.y; words[4 * i + 2] = v.z; words[4 * i + 3] = v.w;
+                    if (live) reinterpret_cast<uint4 *>(nrow)[i] = v;     // next state starts as a copy
+                }
+                const int facing = facing_kind<W, H>(a, srow);
+                int dist;
+                uint32_t fl = 0;
+                int act = expert_env<W, H>(st, a, a.task(), words, facing, dist, fl);
+                if (live) {
+                    flags |= fl;
+                    const int64_t o = (int64_t)t * n + e;
+                    expert_out[o] = (uint8_t)act;
+                    if (action_in) act = action_in[o];
+                    bool success;
+                    const bool done = advance_env<W, H>(st, a, nrow, srow, act, scen_row,
+                                                        init_agent + e * PSK_AGENT_BYTES, CP,
+                                                        success, flags);
+                    if (done_out) done_out[o] = done;
+                    if (success_out) success_out[o] = success;
+                    n_done += done;
+                    n_succ += success;
+                    uint4 *sag = reinterpret_cast<uint4 *>(s_agent[nxt]) + slot * 2;
+                    sag[0] = make_uint4(a.w[0], a.w[1], a.w[2], a.w[3]);
+                    sag[1] = make_uint4(a.w[4], a.w[5], a.w[6], a.w[7]);
+                }
+            } else if (features_out) {
+                const int fw = (tid - NE) >> 5, lane = tid & 31;
+                const uint32_t wbuf_s = smem_u32(smem_raw) +
+                                        (uint32_t)fw * (USE_TMA ? 2 : 1) * feature_buffer_bytes(EPW, nf);
+                float *fout = features_out + (int64_t)(t % feat_ring) * n * nf;
+                for (int c = 0; c < SPW / EPW; c++) {
+                    const int s0 = fw * SPW + c * EPW;
+                    if (s0 >= ne_sp) break;
+                    const int ne = (ne_sp - s0) < EPW ? (ne_sp - s0) : EPW;
+                    int se = s0 + lane / TPE;
+                    if (se >= ne_sp) se = s0;
+                    Agent b;
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const uint4 v = reinterpret_cast<const uint4 *>(s_agent[cur])[se * 2 + i];
+                        b.w[4 * i] = v.x; b.w[4 * i + 1] = v.y; b.w[4 * i + 2] = v.z; b.w[4 * i + 3] = v.w;
+                    }
+                    RowChunks<W, H, TPE> cells;
+                    cells.load(s_rows[cur] + se * CP, lane % TPE);
+                    warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA>(
+                        wbuf_s, it, fout + (e_base + s0) * nf, ne, cells, b, K, nf);
+                    it++;
+                }
+            }
+            __syncthreads();   // state of tick t+1 complete, state of tick t no longer read
+        }
+        // ---- final state -> HBM, statistics
+        if (env_warp) {
+            if (live) {
+                store_agent(agent, e, a);
+                const uint8_t *frow = s_rows[ticks & 1] + slot * CP;
+#pragma unroll
+                for (int i = 0; i < NW4; i++)
+                    reinterpret_cast<uint4 *>(grid + e * CP)[i] = reinterpret_cast<const uint4 *>(frow)[i];
+            }
+            const int d = __reduce_add_sync(0xffffffffu, n_done);
+            const int sc = __reduce_add_sync(0xffffffffu, n_succ);
+            const int lv = __reduce_add_sync(0xffffffffu, live ? ticks : 0);
+            if (stats && (tid & 31) == 0) {
+                if (d) atomicAdd(stats + 0, (unsigned long long)d);
+                if (sc) atomicAdd(stats + 1, (unsigned long long)sc);
+                if (lv) atomicAdd(stats + 2, (unsigned long long)lv);
+            }
+        }
+        __syncthreads();
+    }
+    if (USE_TMA && !env_warp && (tid & 31) == 0) bulk_wait_read<0>();
+    if (flags && err_flags) atomicOr(err_flags, (int)flags);
+}
+
+// =============================================================================================
 // host side: dispatch on (width, height, window)
 // =============================================================================================
 static int g_num_sms = 0;
@@ -1468,6 +1619,63 @@ template <int W, int H, int WIN> struct Config {
                                         ep.scen_idx, ep.init_agent, features_out, expert_out, done,
                                         success, stats, err, s.n, cell_stride, K, f));
     }
+    template <int NE, int NFW, bool TMA>
+    static int rollout_variant(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
+                               int ticks, const uint8_t *action_in, float *features_out,
+                               int feat_ring, uint8_t *expert_out, uint8_t *done,
+                               uint8_t *success, unsigned long long *stats, int32_t *err,
+                               cudaStream_t st) {
+        constexpr int EPW = 32 / TPE;
+        const int f = nf(t);
+        const size_t smem = (size_t)NFW * (TMA ? 2 : 1) * feature_buffer_bytes(EPW, f);
+        auto kern = t->n_kinds == 21 ? craft_rollout_kernel<W, H, WIN, NE, NFW, 21, TMA>
+                                     : craft_rollout_kernel<W, H, WIN, NE, NFW, 0, TMA>;
+        static size_t configured = 0;
+        if (configured != smem) {
+            if (cudaFuncSetAttribute(craft_rollout_kernel<W, H, WIN, NE, NFW, 21, TMA>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaFuncSetAttribute(craft_rollout_kernel<W, H, WIN, NE, NFW, 0, TMA>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return PSK_ERR_CUDA;
+            configured = smem;
+        }
+        const int64_t tiles = (s.n + NE - 1) / NE;
+        PSK_DT(dt);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(tiles > 0 ? tiles : 1));
+        cfg.blockDim = dim3(NE + NFW * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int cell_stride = s.cell_stride, K = t->n_kinds;
+        return check(cudaLaunchKernelEx(&cfg, kern, dt, s.grid, s.agent, action_in, ep.scen_grid,
+                                        ep.scen_idx, ep.init_agent, features_out, feat_ring,
+                                        expert_out, done, success, stats, err, s.n, cell_stride, K,
+                                        f, ticks));
+    }
+    static int rollout(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep, int ticks,
+                       const uint8_t *action_in, float *features_out, int feat_ring,
+                       uint8_t *expert_out, uint8_t *done, uint8_t *success,
+                       unsigned long long *stats, int32_t *err, cudaStream_t st) {
+        if constexpr (!BITBOARD || WIN != 3) {
+            return PSK_ERR_UNSUPPORTED;
+        } else {
+            static int env_tma = -2;
+            if (env_tma == -2) {
+                const char *m = getenv("PSK_ROLLOUT_TMA");
+                env_tma = m ? atoi(m) : -1;
+            }
+            const int tma = env_tma >= 0 ? env_tma : (s.n > 262144 ? 1 : 0);
+            return tma ? rollout_variant<64, 2, true>(t, s, ep, ticks, action_in, features_out, feat_ring,
+                                                      expert_out, done, success, stats, err, st)
+                       : rollout_variant<64, 2, false>(t, s, ep, ticks, action_in, features_out, feat_ring,
+                                                       expert_out, done, success, stats, err, st);
+        }
+    }
     static int tick_fused(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
                           const uint8_t *action_in, float *features_out, uint8_t *expert_out,
                           uint8_t *done, uint8_t *success, unsigned long long *stats,
@@ -1621,6 +1829,34 @@ int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episo
     }
     const uint8_t *act = action_in ? action_in : expert_out;
     PSK_DISPATCH(t, advance(t, s, ep, act, done_out, success_out, stats, err_flags, st));
+}
+
+int psk_craft_rollout(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
+                      int32_t ticks, const uint8_t *action_in, float *features_out,
+                      int32_t feat_ring, uint8_t *expert_out, uint8_t *done_out,
+                      uint8_t *success_out, unsigned long long *stats, int32_t *err_flags,
+                      void *stream) {
+    if (!state_ok(t, s) || ticks < 0 || (features_out && feat_ring <= 0)) return PSK_ERR_BADARG;
+    if (s.n == 0 || ticks == 0) return PSK_OK;
+    if (!expert_out || !ep.scen_grid || !ep.scen_idx || !ep.init_agent) return PSK_ERR_BADARG;
+    if (features_out && (reinterpret_cast<uintptr_t>(features_out) & 15)) return PSK_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = PSK_ERR_UNSUPPORTED;
+    if (Medium::matches(t))
+        rc = Medium::rollout(t, s, ep, ticks, action_in, features_out, feat_ring, expert_out, done_out,
+                             success_out, stats, err_flags, st);
+    if (rc != PSK_ERR_UNSUPPORTED) return rc;
+    // other geometries: one fused / pipelined tick per iteration, same outputs
+    const int nfeat = psk_craft_n_features(t);
+    for (int k = 0; k < ticks; k++) {
+        const int64_t o = (int64_t)k * s.n;
+        rc = psk_craft_tick(t, s, ep, action_in ? action_in + o : nullptr,
+                            features_out ? features_out + (int64_t)(k % feat_ring) * s.n * nfeat : nullptr,
+                            expert_out + o, done_out ? done_out + o : nullptr,
+                            success_out ? success_out + o : nullptr, stats, err_flags, 1, stream);
+        if (rc) return rc;
+    }
+    return PSK_OK;
 }
 
 }  // extern "C"

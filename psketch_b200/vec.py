@@ -209,6 +209,30 @@ class VecCraft(object):
         _lib.check(rc, "psk_craft_tick")
         return out
 
+    def rollout(self, ticks, actions=None, features_out=None, out=None, want_flags=True):
+        """``ticks`` rollout ticks in one launch (psk_craft_rollout).  actions: u8[ticks, N] or None
+        (follow the teacher); features_out: f32[R, N, n_features] ring or None.  Returns
+        dict(expert u8[ticks, N], done, success)."""
+        actions = self._u8(actions)
+        if out is None:
+            out = {}
+        keys = ("expert", "done", "success") if want_flags else ("expert",)
+        for k in keys:
+            if k not in out or out[k].shape[0] != ticks:
+                out[k] = torch.empty((ticks, self.n), dtype=torch.uint8, device=self.device)
+        ring = 0
+        if features_out is not None:
+            assert features_out.dim() == 3 and features_out.is_contiguous()
+            ring = features_out.shape[0]
+        with torch.cuda.device(self.device):
+            rc = self.lib.psk_craft_rollout(ctypes.byref(self.ct), self._state(), self._episodes(),
+                                            int(ticks), _ptr(actions), _ptr(features_out), ring,
+                                            _ptr(out["expert"]), _ptr(out.get("done")),
+                                            _ptr(out.get("success")), _ptr(self.stats),
+                                            _ptr(self.err_flags), self._stream())
+        _lib.check(rc, "psk_craft_rollout")
+        return out
+
     def random_actions(self, t=0, seed=123, out=None, device_clock=False):
         """u8[N] uniform actions from Philox(seed, counter=(env, t)) — off-policy rollouts.
         device_clock=True adds the env-step counter (stats[2]) to t on the device, so a captured

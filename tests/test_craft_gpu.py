@@ -324,3 +324,49 @@ def test_random_actions_are_uniform_and_reproducible(medium_tables, medium_state
     big = np.concatenate([env.random_actions(t).cpu().numpy() for t in range(50)])
     hist = np.bincount(big, minlength=6) / len(big)
     assert np.abs(hist - 1 / 6).max() < 0.005
+
+
+@pytest.mark.parametrize("n,with_actions", [(6007, False), (4099, True), (65, False)])
+def test_multi_tick_rollout_equals_single_ticks(n, with_actions, splits, medium_tables):
+    """psk_craft_rollout (tick loop inside the kernel, state in shared memory) against the same
+    number of psk_craft_tick launches: every per-tick output, the final state and the counters."""
+    from psketch_b200.vec import VecCraft
+    rng = np.random.RandomState(n)
+    idx = rng.randint(0, 2200, size=n)
+    grids = splits["dev_grids"]
+    args = (medium_tables, grids, splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
+            splits["dev_inst_task"][idx])
+    T = 23
+    a = VecCraft.from_instances(*args, max_timesteps=15)
+    b = VecCraft.from_instances(*args, max_timesteps=15)
+    acts = None
+    if with_actions:
+        acts = torch.from_numpy(rng.choice(6, size=(T, n), p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8)).to(a.device)
+    feats = torch.empty((T, n, 404), dtype=torch.float32, device=a.device)
+    out = a.rollout(T, actions=acts, features_out=feats)
+    for t in range(T):
+        o = b.tick(actions=None if acts is None else acts[t], fused=bool(t % 2))
+        assert torch.equal(out["expert"][t], o["expert"]), t
+        assert torch.equal(out["done"][t], o["done"]), t
+        assert torch.equal(out["success"][t], o["success"]), t
+        assert torch.equal(feats[t], o["features"]), t
+    assert torch.equal(a.grid, b.grid) and torch.equal(a.agent, b.agent)
+    assert torch.equal(a.stats, b.stats) and int(a.stats[2]) == T * n and int(a.stats[0]) > 0
+    # ring of two feature slots: the last two ticks survive
+    c = VecCraft.from_instances(*args, max_timesteps=15)
+    ring = torch.empty((2, n, 404), dtype=torch.float32, device=a.device)
+    c.rollout(T, actions=acts, features_out=ring, want_flags=False)
+    assert torch.equal(ring[(T - 1) % 2], feats[T - 1]) and torch.equal(ring[(T - 2) % 2], feats[T - 2])
+    a.check_errors()
+
+
+def test_multi_tick_rollout_other_geometry_falls_back(large_tables, large_states):
+    """craft_large has no multi-tick kernel: psk_craft_rollout loops over single ticks."""
+    S = {k: large_states[k][:300] for k in ("grid", "inv", "pos", "dir")}
+    a = _env_from_states(large_tables, S, task=np.full(300, 24))
+    b = _env_from_states(large_tables, S, task=np.full(300, 24))
+    out = a.rollout(5)
+    for t in range(5):
+        o = b.tick(want_features=False)
+        assert torch.equal(out["expert"][t], o["expert"])
+    assert torch.equal(a.grid, b.grid) and torch.equal(a.agent, b.agent)
