@@ -363,8 +363,9 @@ def run_ours(args):
     # ---- roofline of the dominant kernel
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["craft_tick_kernel"]
-        if tr["n_envs"] == n:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tr = tr["craft_rollout_kernel" if T > 1 else "craft_tick_kernel"]
+        if tr["n_envs"] == n and tr.get("ticks_per_launch", 1) == T:
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass
@@ -376,7 +377,7 @@ def run_ours(args):
         achieved = bytes_per_tick * ticks_per_launch_eff * n / launch_s / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": "craft_rollout_kernel" if T > 1 else "craft_tick_kernel",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": traffic if T == 1 else None, "peak_source": peak_src,
+                            "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_env_step": bytes_per_tick,
                             "launch_us": launch_s * 1e6, "ticks_per_launch": ticks_per_launch_eff}
     # per-kernel numbers (north star: step and features as a fraction of the HBM roofline)
