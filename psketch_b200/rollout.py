@@ -10,26 +10,22 @@ from .tables import STOP
 
 def teacher_rollouts(env, max_len=64):
     """make_data.py:146-152 for every env at once: follow the teacher until it says STOP.
+    One psk_craft_rollout launch of ``max_len`` ticks (the envs auto-reset after their first
+    episode; only that first episode is kept).
     Returns (ref_actions u8[N, L] padded with 255, ref_len i32[N], satisfied bool[N])."""
     n = env.n
     env.reset()
-    alive = torch.ones(n, dtype=torch.uint8, device=env.device)
-    acts = torch.full((n, max_len), 255, dtype=torch.uint8, device=env.device)
-    length = torch.zeros(n, dtype=torch.int32, device=env.device)
-    ok = torch.zeros(n, dtype=torch.bool, device=env.device)
-    for t in range(max_len):
-        a = env.expert()
-        live = alive.bool()
-        acts[:, t] = torch.where(live, a, acts[:, t])
-        length += live.to(torch.int32)
-        stop = live & (a == STOP)
-        if bool(stop.any()):
-            ok |= stop & (env.satisfies() == 1)
-        alive = (live & ~stop).to(torch.uint8)
-        if not bool(alive.any()):
-            break
-        env.step(a, active=alive)
+    out = env.rollout(max_len)
     env.check_errors()
+    expert, done, success = out["expert"], out["done"].bool(), out["success"].bool()
+    ticks = torch.arange(max_len, device=env.device).unsqueeze(1)
+    first = torch.where(done, ticks, torch.full_like(ticks, max_len)).min(dim=0).values      # [N]
+    finished = first < max_len
+    length = torch.where(finished, first + 1, torch.full_like(first, max_len)).to(torch.int32)
+    idx = first.clamp(max=max_len - 1).unsqueeze(0)
+    ok = finished & success.gather(0, idx)[0] & (expert.gather(0, idx)[0] == STOP)
+    acts = torch.where(ticks < length.unsqueeze(0), expert, torch.full_like(expert, 255)).t().contiguous()
+    env.reset()
     L = int(length.max().item())
     return acts[:, :L].cpu().numpy(), length.cpu().numpy(), ok.cpu().numpy()
 
