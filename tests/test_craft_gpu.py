@@ -370,3 +370,31 @@ def test_multi_tick_rollout_other_geometry_falls_back(large_tables, large_states
         o = b.tick(want_features=False)
         assert torch.equal(out["expert"][t], o["expert"])
     assert torch.equal(a.grid, b.grid) and torch.equal(a.agent, b.agent)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_tick_craft_large_matches_oracle(fused, large_tables, large_oracle, large_states):
+    """craft_large (10x10, window 5, 128-bit boards, 1,076 features): rollout ticks vs the oracle."""
+    from psketch_b200.vec import VecCraft
+    S = large_states
+    n = 1500
+    rng = np.random.RandomState(2)
+    task = rng.choice([13, 14, 15, 19, 20, 21, 22, 23, 24, 25, 26], size=n).astype(np.int32)
+    grid, pos = S["grid"][:n], S["pos"][:n].astype(np.int32)
+    # episode starts: the exported layouts with empty inventory and dir 0 (what the oracle resets to)
+    env = VecCraft.from_instances(large_tables, grid, np.arange(n), pos, task, max_timesteps=25)
+    state = None
+    tot = np.zeros(4, np.int64)
+    for t in range(40):
+        out = env.tick(fused=fused)
+        state, stats, feats, act = large_oracle.rollout(1, 25, grid, pos, task, state=state,
+                                                        want_features=True)
+        tot += stats
+        assert np.array_equal(_np(out["expert"]).astype(np.int32), act), t
+        assert np.array_equal(_np(out["features"]), feats), t
+        assert np.array_equal(_np(env.cells), state["grid"]), t
+        assert np.array_equal(_np(env.inventory).astype(np.int32), state["inv"]), t
+        assert np.array_equal(_np(env.pos).astype(np.int32), state["pos"]), t
+    st = _np(env.stats)
+    assert st[0] == tot[0] and st[1] == tot[1] and st[0] > 0
+    env.check_errors()
