@@ -237,48 +237,83 @@ def run_ours(args):
             env.random_actions(0, seed=123, out=rand_act, device_clock=True)
         env.tick(actions=rand_act, features_out=feats[i % ring], fused=fused, out=outs[i % ring])
 
-    def launch_rollout():
-        env.rollout(T, features_out=feat_ring, out=rout, want_flags=True)
+    routs = {}
+
+    def launch_rollout(ticks=None):
+        ticks = ticks or T
+        env.rollout(ticks, features_out=feat_ring, out=routs.setdefault(ticks, {}), want_flags=True)
 
     for i in range(ring):           # allocate output tensors outside the graph
         tick(i)
     if T > 1:
         launch_rollout()
     torch.cuda.synchronize()
-    # CUDA graph of consecutive launches (launch-bound otherwise: ~20 us of work per tick)
-    per_graph = ring if T == 1 else 4          # launches per graph replay
-    graph = None
-    if not args.no_graph:
+    per_tick_launches = (1 if fused else 3) + (1 if rand_act is not None else 0)
+    launches = [0]
+    graphs = {}
+
+    def capture(plan):
+        """CUDA graph of a list of launches; plan entries are tick counts (T > 1) or tick indices."""
+        for tc in set(plan) if T > 1 else ():
+            launch_rollout(tc)                      # output tensors exist before the capture
+        torch.cuda.synchronize()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                for i in range(per_graph):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for j, tc in enumerate(plan):
                     if T > 1:
-                        launch_rollout()
+                        launch_rollout(tc)
                     else:
-                        tick(i)
+                        tick(j)
         torch.cuda.current_stream().wait_stream(side)
-    launches = [0]
-    per_tick_launches = (1 if fused else 3) + (1 if rand_act is not None else 0)
+        return g
+
+    # main graph: a fixed number of full launches; tail graphs: the exact remainder of a request
+    per_graph = ring if T == 1 else 4
+    chunk = per_graph * T
+
+    def plan_for(r):
+        return ([T] * (r // T) + ([r % T] if r % T else [])) if T > 1 else list(range(r))
+
+    def prepare(k):
+        if args.no_graph:
+            return
+        if k >= chunk and "main" not in graphs:
+            graphs["main"] = capture(plan_for(chunk))
+        r = k % chunk
+        if r and r not in graphs:
+            graphs[r] = capture(plan_for(r))
+
+    def n_launches(plan):
+        return len(plan) * (1 if T > 1 else per_tick_launches)
 
     def run_steps(k):
-        """Exactly k ticks: graph replays of per_graph launches of T ticks, then single launches."""
-        done = 0
-        if graph is not None:
-            while k - done >= per_graph * T:
-                graph.replay()
-                done += per_graph * T
-                launches[0] += per_graph * (1 if T > 1 else per_tick_launches)
-        while T > 1 and k - done >= T:
-            launch_rollout()
-            done += T
-            launches[0] += 1
-        while done < k:
-            tick(done)
-            done += 1
-            launches[0] += per_tick_launches
+        """Exactly k ticks."""
+        if args.no_graph:
+            done = 0
+            while T > 1 and k - done >= T:
+                launch_rollout()
+                done += T
+                launches[0] += 1
+            while done < k:
+                tick(done)
+                done += 1
+                launches[0] += per_tick_launches
+            return
+        prepare(k)
+        for _ in range(k // chunk):
+            graphs["main"].replay()
+            launches[0] += n_launches(plan_for(chunk))
+        if k % chunk:
+            graphs[k % chunk].replay()
+            launches[0] += n_launches(plan_for(k % chunk))
+
+    graph = None if args.no_graph else True
+    prepare(max(W, 3))
+    prepare(K)
+    prepare(ring * 8)
 
     sampler = ClockSampler(local) if rank == 0 else None
     run_steps(max(W, 3))

@@ -52,20 +52,7 @@ void psk_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
 
-int psk_craft_host_create(const psk_craft_tables *t, int64_t max_envs, int64_t chunk_envs,
-                          psk_craft_host_ctx **out) {
-    if (!t || !out || max_envs <= 0) return PSK_ERR_BADARG;
-    if (!psk_craft_supported(t)) return PSK_ERR_UNSUPPORTED;
-    psk_craft_host_ctx *c = new (std::nothrow) psk_craft_host_ctx();
-    if (!c) return PSK_ERR_BADARG;
-    memset(c, 0, sizeof(*c));
-    c->tables = *t;
-    c->max_envs = max_envs;
-    if (chunk_envs <= 0) chunk_envs = 16384;
-    if (chunk_envs > max_envs) chunk_envs = max_envs;
-    c->chunk = (chunk_envs + 127) / 128 * 128;
-    c->cell_stride = ((t->width * t->height + 63) / 64) * 64;
-    c->nf = psk_craft_n_features(t);
+static int host_ctx_alloc(psk_craft_host_ctx *c) {
     CK(cudaGetDevice(&c->device));
     for (int i = 0; i < PSK_HOST_STREAMS; i++) {
         CK(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
@@ -81,6 +68,30 @@ int psk_craft_host_create(const psk_craft_tables *t, int64_t max_envs, int64_t c
     CK(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
     CK(cudaMalloc(&c->d_err, sizeof(int32_t)));
     CK(cudaMemset(c->d_err, 0, sizeof(int32_t)));
+    return PSK_OK;
+}
+
+void psk_craft_host_destroy(psk_craft_host_ctx *c);
+
+int psk_craft_host_create(const psk_craft_tables *t, int64_t max_envs, int64_t chunk_envs,
+                          psk_craft_host_ctx **out) {
+    if (!t || !out || max_envs <= 0) return PSK_ERR_BADARG;
+    if (!psk_craft_supported(t)) return PSK_ERR_UNSUPPORTED;
+    psk_craft_host_ctx *c = new (std::nothrow) psk_craft_host_ctx();
+    if (!c) return PSK_ERR_BADARG;
+    memset(c, 0, sizeof(*c));
+    c->tables = *t;
+    c->max_envs = max_envs;
+    if (chunk_envs <= 0) chunk_envs = 16384;
+    if (chunk_envs > max_envs) chunk_envs = max_envs;
+    c->chunk = (chunk_envs + 127) / 128 * 128;
+    c->cell_stride = ((t->width * t->height + 63) / 64) * 64;
+    c->nf = psk_craft_n_features(t);
+    const int rc = host_ctx_alloc(c);
+    if (rc != PSK_OK) {             // release whatever was allocated before the failure
+        psk_craft_host_destroy(c);
+        return rc;
+    }
     *out = c;
     return PSK_OK;
 }
