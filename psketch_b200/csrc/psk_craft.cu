@@ -968,13 +968,16 @@ __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, floa
     }
     if (le < ne) scatter_features<W, H, WIN, TPE>(buf_s + le * nf * 4, trash_s, cells, a, K, j);
     const uint32_t bytes = (uint32_t)ne * (uint32_t)nf * 4u;
-    if (USE_TMA && (bytes & 15u) == 0) {
+    // 16-byte paths need the chunk size AND its destination aligned (a frame of a feature ring
+    // starts at slot*n*nf floats, which is not a multiple of 16 bytes for every n and nf)
+    const bool vec_ok = (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(gdst) & 15) == 0;
+    if (USE_TMA && vec_ok) {
         fence_async_smem();  // generic-proxy writes -> visible to the async proxy
         __syncwarp();
         if (lane == 0) bulk_store(gdst, buf_s, bytes);
     } else {
         __syncwarp();
-        if ((bytes & 15u) == 0) {
+        if (vec_ok) {
             float4 *g4 = reinterpret_cast<float4 *>(gdst);
             const int m16 = (int)(bytes / 16);
             auto move16 = [&](int i) {

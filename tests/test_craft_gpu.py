@@ -398,3 +398,84 @@ def test_tick_craft_large_matches_oracle(fused, large_tables, large_oracle, larg
     st = _np(env.stats)
     assert st[0] == tot[0] and st[1] == tot[1] and st[0] > 0
     env.check_errors()
+
+
+def test_custom_cookbook_runtime_kind_count(tmp_path):
+    """A cookbook / hint file other than the default one (K = 14 kinds, 271 features: rows are not
+    a whole number of float4) goes through the kernels' runtime-K code paths."""
+    import yaml
+    from oracle.craft_oracle import CraftOracle
+    from psketch_b200.tables import Cookbook, CraftTables, TaskManager
+    from psketch_b200.vec import VecCraft
+    recipes = {
+        "environment": ["boundary", "workshop0", "workshop1", "workshop2", "water", "stone"],
+        "primitives": ["iron", "grass", "wood"],
+        "recipes": {
+            "plank": {"wood": 1, "_at": "workshop0"},
+            "stick": {"wood": 1, "_at": "workshop1"},
+            "bridge": {"wood": 1, "iron": 1, "_at": "workshop2"},
+            "axe": {"stick": 1, "iron": 1, "_at": "workshop0"},
+        },
+    }
+    hints = {
+        "use[none]": [], "go[wood]": [], "go[iron]": [], "go[workshop0]": [], "go[workshop1]": [],
+        "go[workshop2]": [],
+        "get[wood]": ["go[wood]", "use[none]"], "get[iron]": ["go[iron]", "use[none]"],
+        "makeat[workshop0]": ["go[workshop0]", "use[none]"],
+        "makeat[workshop1]": ["go[workshop1]", "use[none]"],
+        "makeat[workshop2]": ["go[workshop2]", "use[none]"],
+        "make[plank]": ["get[wood]", "makeat[workshop0]"],
+        "make[stick]": ["get[wood]", "makeat[workshop1]"],
+        "make[bridge]": ["get[iron]", "get[wood]", "makeat[workshop2]"],
+        "make[axe]": ["make[stick]", "get[iron]", "makeat[workshop0]"],
+    }
+    rp, hp = str(tmp_path / "recipes.yaml"), str(tmp_path / "hints.yaml")
+    yaml.safe_dump(recipes, open(rp, "w"), sort_keys=False)
+    yaml.safe_dump(hints, open(hp, "w"), sort_keys=False)
+    tables = CraftTables(Cookbook(rp), TaskManager(hp), "craft_medium")
+    assert tables.K == 14 and tables.n_features == 271
+    tm = tables.task_manager
+    task_ids = [tm[g].task_id for g in ("get[wood]", "get[iron]", "make[plank]", "make[stick]",
+                                        "make[bridge]", "make[axe]")]
+    o = CraftOracle(tables)
+    rng = np.random.RandomState(9)
+    n = 2051
+    cb = tables.cookbook
+    grid = np.zeros((n, 8, 8), np.uint8)
+    grid[:, 0, :] = grid[:, 7, :] = grid[:, :, 0] = grid[:, :, 7] = 1
+    pos = np.zeros((n, 2), np.int32)
+    for i in range(n):
+        cells = rng.permutation(36)
+        k = 0
+        for name, cnt in (("iron", 2), ("grass", 1), ("wood", 2), ("workshop0", 1), ("workshop1", 1),
+                          ("workshop2", 1), ("water", rng.randint(0, 2)), ("stone", rng.randint(0, 3))):
+            for _ in range(cnt):
+                grid[i, 1 + cells[k] // 6, 1 + cells[k] % 6] = cb.index[name]
+                k += 1
+        pos[i] = (1 + cells[k] // 6, 1 + cells[k] % 6)
+    grid = grid.reshape(n, 64)
+    inv = np.zeros((n, 14), np.int32)
+    inv[np.arange(n), rng.randint(7, 14, size=n)] = rng.randint(0, 3, size=n)
+    dirs = rng.randint(0, 4, size=n).astype(np.int32)
+    task = rng.choice(task_ids, size=n).astype(np.int32)
+    env = VecCraft.from_states(tables, grid, inv, pos, dirs, task=task)
+    for impl in (0, 1, 2):
+        assert np.array_equal(_np(env.features(impl=impl)), o.features(grid, inv, pos, dirs)), impl
+    act = env.expert()
+    assert np.array_equal(_np(act).astype(np.int32), o.expert(grid, inv, pos, dirs, task)[0])
+    # teacher-driven ticks (fused and pipelined) and the multi-tick kernel
+    twin = VecCraft.from_states(tables, grid, inv, pos, dirs, task=task)
+    out = twin.rollout(6, features_out=torch.empty((6, n, 271), dtype=torch.float32, device=env.device))
+    g, iv, p, d = grid.copy(), inv.copy(), pos.copy(), dirs.copy()
+    for t in range(6):
+        tick = env.tick(fused=bool(t % 2))
+        a = o.expert(g, iv, p, d, task)[0]
+        assert np.array_equal(_np(tick["expert"]).astype(np.int32), a), t
+        assert np.array_equal(_np(out["expert"][t]).astype(np.int32), a), t
+        assert np.array_equal(_np(tick["features"]), o.features(g, iv, p, d)), t
+        done = _np(tick["done"]).astype(bool)
+        if done.any():
+            break
+        g, iv, p, d, _ = o.step(g, iv, p, d, a)
+        assert np.array_equal(_np(env.cells), g) and np.array_equal(_np(env.inventory).astype(np.int32), iv)
+    env.check_errors()
