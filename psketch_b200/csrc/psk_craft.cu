@@ -1283,8 +1283,11 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
 // teacher-driven rollouts (action_in == NULL) or replay of given action sequences.
 //   action_in   u8[ticks][n] or NULL;  expert_out u8[ticks][n];  done_out/success_out u8[ticks][n] or NULL
 //   features_out f32[feat_ring][n][nf] or NULL: tick t writes slot t % feat_ring
+// 65,536 envs = 1,024 CTAs of 128 threads = 6.92 per SM: all of them must be resident at once
+// (a second wave of long-lived multi-tick CTAs would run at a fraction of the occupancy), hence
+// the register cap of 7 CTAs per SM.
 template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA>
-__global__ void __launch_bounds__(NE + NFW * 32)
+__global__ void __launch_bounds__(NE + NFW * 32, (NE + NFW * 32) <= 128 ? 7 : 1)
 craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                      uint8_t *__restrict__ agent, const uint8_t *__restrict__ action_in,
                      const uint8_t *__restrict__ scen_grid, const int32_t *__restrict__ scen_idx,
