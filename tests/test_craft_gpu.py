@@ -479,3 +479,36 @@ def test_custom_cookbook_runtime_kind_count(tmp_path):
         g, iv, p, d, _ = o.step(g, iv, p, d, a)
         assert np.array_equal(_np(env.cells), g) and np.array_equal(_np(env.inventory).astype(np.int32), iv)
     env.check_errors()
+
+
+def test_million_env_rollout_kernel(splits, medium_tables, medium_oracle):
+    """The large-batch variant of the multi-tick kernel (TMA feature stores, n > 262,144): a
+    strided sample of envs against the oracle, and the counters."""
+    from psketch_b200.vec import VecCraft
+    n = (1 << 20) + 37                       # not a multiple of the 64-env tile
+    idx = np.arange(n) % 17600
+    grids = splits["train_grids"]
+    ienv, ipos, itask = (splits["train_inst_env"][idx], splits["train_inst_pos"][idx],
+                         splits["train_inst_task"][idx])
+    env = VecCraft.from_instances(medium_tables, grids, ienv, ipos, itask, max_timesteps=40)
+    T = 11
+    ring = torch.empty((2, n, 404), dtype=torch.float32, device=env.device)
+    out = env.rollout(T, features_out=ring)
+    sample = np.concatenate([np.arange(0, n, 1009), np.arange(n - 40, n)])
+    ds = torch.from_numpy(sample).to(env.device)
+    state = None
+    for t in range(T):
+        state, _, f, a = medium_oracle.rollout(1, 40, grids[ienv[sample].astype(np.int64)],
+                                               ipos[sample].astype(np.int32),
+                                               itask[sample].astype(np.int32), state=state,
+                                               want_features=True)
+        assert np.array_equal(out["expert"][t][ds].cpu().numpy().astype(np.int32), a), t
+        if t >= T - 2:
+            assert np.array_equal(ring[t % 2][ds].cpu().numpy(), f), t
+    assert np.array_equal(env.cells[ds].cpu().numpy(), state["grid"])
+    assert np.array_equal(env.pos[ds].cpu().numpy().astype(np.int32), state["pos"])
+    s = env.stats.cpu().numpy()
+    ref_len = splits["train_ref_len"][idx].astype(np.int64)
+    assert s[2] == T * n and s[0] == s[1] == int((T // ref_len).sum())
+    assert int(out["done"].sum()) == s[0] and int(out["success"].sum()) == s[1]
+    env.check_errors()
