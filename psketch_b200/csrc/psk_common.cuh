@@ -157,4 +157,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// Host-side per-device caches (SM count, shared-memory attributes, table copies) are indexed by this.
+#define PSK_MAX_DEVICES 32
+static inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PSK_MAX_DEVICES) dev = 0;
+    return dev;
+}
+
 }  // namespace psk

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "psk_common.cuh"
 
@@ -1428,19 +1429,19 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
 // =============================================================================================
 // host side: dispatch on (width, height, window)
 // =============================================================================================
-static int g_num_sms = 0;
 static int num_sms() {
-    if (!g_num_sms) {
-        if (const char *m = getenv("PSK_STORE_MODE")) {
+    static int sms[PSK_MAX_DEVICES] = {0};
+    const int dev = current_device();
+    if (!sms[dev]) {
+        if (const char *m = getenv("PSK_STORE_MODE")) {      // experiment knob, profiles/README.md
             const int mode = atoi(m);
             cudaMemcpyToSymbol(g_store_mode, &mode, sizeof(int));
         }
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
     }
-    return g_num_sms;
+    return sms[dev];
 }
 
 static inline int grid_for(int64_t n, int block, int ctas_per_sm) {
@@ -1451,26 +1452,51 @@ static inline int grid_for(int64_t n, int block, int ctas_per_sm) {
 
 static inline int check(cudaError_t e) { return e == cudaSuccess ? PSK_OK : PSK_ERR_CUDA; }
 
-// Device copy of the caller's tables, one slot per device, refreshed when the content changes.
-// The refresh is a pageable H2D copy: it must not happen inside a CUDA-graph capture, so call any
-// entry point once with new tables before capturing (every caller's warm-up does).
+// Device copies of the callers' tables: a small per-device cache keyed by content, so that batches
+// with different tables (or on different streams) never share a slot that is being rewritten.
+// Filling a slot is a pageable H2D copy: it must not happen inside a CUDA-graph capture, so call any
+// entry point once with new tables before capturing (every caller's warm-up does).  When more than
+// SLOTS distinct tables are alive on a device the oldest slot is recycled after a device-wide sync.
 static const psk_craft_tables *device_tables(const psk_craft_tables *t, cudaStream_t st) {
-    constexpr int MAX_DEV = 32;
-    static psk_craft_tables host_copy[MAX_DEV];
-    static psk_craft_tables *dev_copy[MAX_DEV] = {nullptr};
+    constexpr int MAX_DEV = PSK_MAX_DEVICES, SLOTS = 8;
+    struct Slot {
+        psk_craft_tables host;
+        psk_craft_tables *dev = nullptr;
+    };
+    struct PerDevice {
+        Slot slot[SLOTS];
+        int used = 0, last = 0, next_victim = 0;
+    };
+    static PerDevice cache[MAX_DEV];
+    static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
-    if (!dev_copy[dev]) {
-        if (cudaMalloc(&dev_copy[dev], sizeof(psk_craft_tables)) != cudaSuccess) return nullptr;
-        memset(&host_copy[dev], 0xFF, sizeof(psk_craft_tables));
+    std::lock_guard<std::mutex> lock(mu);
+    PerDevice &c = cache[dev];
+    if (c.used && memcmp(&c.slot[c.last].host, t, sizeof(psk_craft_tables)) == 0) return c.slot[c.last].dev;
+    for (int i = 0; i < c.used; ++i)
+        if (memcmp(&c.slot[i].host, t, sizeof(psk_craft_tables)) == 0) {
+            c.last = i;
+            return c.slot[i].dev;
+        }
+    int i;
+    if (c.used < SLOTS) {
+        i = c.used;
+        if (cudaMalloc(&c.slot[i].dev, sizeof(psk_craft_tables)) != cudaSuccess) return nullptr;
+        ++c.used;
+    } else {
+        i = c.next_victim;
+        c.next_victim = (c.next_victim + 1) % SLOTS;
+        if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;   // nobody may still read the slot
     }
-    if (memcmp(&host_copy[dev], t, sizeof(psk_craft_tables)) != 0) {
-        if (cudaMemcpyAsync(dev_copy[dev], t, sizeof(psk_craft_tables), cudaMemcpyHostToDevice, st) !=
-            cudaSuccess)
-            return nullptr;
-        host_copy[dev] = *t;
-    }
-    return dev_copy[dev];
+    memset(&c.slot[i].host, 0xFF, sizeof(psk_craft_tables));           // invalid until the copy is queued
+    if (cudaMemcpyAsync(c.slot[i].dev, t, sizeof(psk_craft_tables), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return nullptr;
+    // kernels on other streams may use this slot later: make the copy visible to them as well
+    if (cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
+    c.slot[i].host = *t;
+    c.last = i;
+    return c.slot[i].dev;
 }
 #define PSK_DT(var)                                   \
     const psk_craft_tables *var = device_tables(t, st); \
@@ -1535,7 +1561,8 @@ template <int W, int H, int WIN> struct Config {
         auto kern = t->n_kinds == 21 ? craft_features_kernel<W, H, WIN, WPB, TPE, 21, TMA>
                                      : craft_features_kernel<W, H, WIN, WPB, TPE, 0, TMA>;
         // opt in to > 48 KB dynamic smem (both instantiations, once per size)
-        static size_t configured = 0;
+        static size_t configured_on[PSK_MAX_DEVICES] = {0};   // the attribute is per device
+        size_t &configured = configured_on[current_device()];
         if (configured != smem) {
             if (cudaFuncSetAttribute(craft_features_kernel<W, H, WIN, WPB, TPE, 21, TMA>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
@@ -1583,7 +1610,8 @@ template <int W, int H, int WIN> struct Config {
         const size_t smem = (size_t)NFW * (TMA ? 2 : 1) * feature_buffer_bytes(EPW, f);
         auto kern = t->n_kinds == 21 ? craft_tick_kernel<W, H, WIN, NE, NFW, 21, TMA>
                                      : craft_tick_kernel<W, H, WIN, NE, NFW, 0, TMA>;
-        static size_t configured = 0;
+        static size_t configured_on[PSK_MAX_DEVICES] = {0};   // the attribute is per device
+        size_t &configured = configured_on[current_device()];
         if (configured != smem) {
             if (cudaFuncSetAttribute(craft_tick_kernel<W, H, WIN, NE, NFW, 21, TMA>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
@@ -1636,7 +1664,8 @@ template <int W, int H, int WIN> struct Config {
         const size_t smem = (size_t)NFW * (TMA ? 2 : 1) * feature_buffer_bytes(EPW, f);
         auto kern = t->n_kinds == 21 ? craft_rollout_kernel<W, H, WIN, NE, NFW, 21, TMA>
                                      : craft_rollout_kernel<W, H, WIN, NE, NFW, 0, TMA>;
-        static size_t configured = 0;
+        static size_t configured_on[PSK_MAX_DEVICES] = {0};   // the attribute is per device
+        size_t &configured = configured_on[current_device()];
         if (configured != smem) {
             if (cudaFuncSetAttribute(craft_rollout_kernel<W, H, WIN, NE, NFW, 21, TMA>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||

@@ -128,7 +128,6 @@ light_satisfies_kernel(const psk_light_scenario *__restrict__ scen, const int32_
 // cell k in m whose lower layer R[m \ {k}] already contains it (USE).  The first level at which
 // the agent's cell enters R[alive] is the distance; the action is the smallest a whose successor
 // state was in R one level earlier.
-constexpr int LIGHT_MAX_LAYERS = 1 << PSK_LIGHT_MAX_KEYS;
 
 __global__ void __launch_bounds__(128)
 light_expert_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
@@ -313,7 +312,8 @@ int psk_light_expert(const psk_light_scenario *scen, const int32_t *scen_idx,
     int wpb = (int)((48 * 1024) / per_warp);
     wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
     const size_t smem = (size_t)wpb * per_warp;
-    static size_t configured = 0;
+    static size_t configured_on[PSK_MAX_DEVICES] = {0};   // the attribute is per device
+    size_t &configured = configured_on[current_device()];
     if (smem > configured) {
         if (cudaFuncSetAttribute(light_expert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem) != cudaSuccess)

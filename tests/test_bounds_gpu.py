@@ -204,3 +204,36 @@ def test_large_and_rows_entry_points_stay_inside_their_buffers(n, large_tables, 
         assert _same(env.grid, ref.grid) and _same(env.agent, ref.agent)
         assert arena.guards_intact(), "%dx%d" % (tables.W, tables.H)
         env.check_errors()
+
+
+def test_batches_with_different_tables_on_two_streams(splits, medium_tables, large_tables, large_states):
+    """Two batches with different tables interleaved on two CUDA streams: each keeps its own device
+    copy of the tables (a single shared slot would be rewritten under a running kernel)."""
+    from psketch_b200.vec import VecCraft
+    n = 20000
+    grids, env_idx, pos, task = _instances(splits, n, seed=5)
+    S = large_states
+    m = len(S["grid"])
+    task_l = np.random.RandomState(3).choice([13, 14, 15, 19, 20, 21], size=m)
+
+    def run(two_streams):
+        a = VecCraft.from_instances(medium_tables, grids, env_idx, pos, task)
+        b = VecCraft.from_states(large_tables, S["grid"], S["inv"], S["pos"], S["dir"], task=task_l)
+        torch.cuda.synchronize()
+        sa = torch.cuda.Stream() if two_streams else torch.cuda.current_stream()
+        sb = torch.cuda.Stream() if two_streams else torch.cuda.current_stream()
+        ea, eb = [], []
+        for _ in range(30):
+            with torch.cuda.stream(sa):
+                ea.append(a.tick(want_features=False)["expert"].clone())
+            with torch.cuda.stream(sb):
+                eb.append(b.tick(want_features=False)["expert"].clone())
+        torch.cuda.synchronize()
+        a.check_errors()
+        b.check_errors()
+        return torch.stack(ea).cpu(), torch.stack(eb).cpu(), a.agent.cpu(), b.agent.cpu()
+
+    one = run(False)
+    two = run(True)
+    for x, y in zip(one, two):
+        assert torch.equal(x, y)
