@@ -40,6 +40,19 @@ struct psk_craft_host_ctx {
         if ((x) != cudaSuccess) return PSK_ERR_CUDA; \
     } while (0)
 
+// A context belongs to the device that was current when it was created; calls made while another
+// device is current switch to it for their duration.
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 extern "C" {
 
 void *psk_host_alloc(size_t bytes) {
@@ -98,6 +111,7 @@ int psk_craft_host_create(const psk_craft_tables *t, int64_t max_envs, int64_t c
 
 void psk_craft_host_destroy(psk_craft_host_ctx *c) {
     if (!c) return;
+    DeviceScope scope(c->device);
     for (int i = 0; i < PSK_HOST_STREAMS; i++) {
         if (c->streams[i]) cudaStreamSynchronize(c->streams[i]);
         cudaFree(c->d_grid[i]); cudaFree(c->d_agent[i]); cudaFree(c->d_action[i]);
@@ -116,6 +130,7 @@ int psk_craft_host_set_episodes(psk_craft_host_ctx *c, const uint8_t *host_scen_
     if (!c || !host_scen_grid || !host_scen_idx || !host_init_agent || n <= 0 || n_scen <= 0 ||
         n > c->max_envs)
         return PSK_ERR_BADARG;
+    DeviceScope scope(c->device);
     cudaFree(c->d_scen_grid); cudaFree(c->d_init_agent); cudaFree(c->d_scen_idx);
     c->d_scen_grid = nullptr; c->d_init_agent = nullptr; c->d_scen_idx = nullptr;
     CK(cudaMalloc(&c->d_scen_grid, (size_t)n_scen * c->cell_stride));
@@ -135,6 +150,7 @@ int psk_craft_host_tick(psk_craft_host_ctx *c, uint8_t *host_grid, uint8_t *host
                         int64_t n, unsigned long long *host_stats, int32_t *host_err_flags) {
     if (!c || !host_grid || !host_agent || !host_expert || n < 0 || n > c->n_eps)
         return PSK_ERR_BADARG;
+    DeviceScope scope(c->device);
     const int cs = c->cell_stride;
     int k = 0;
     for (int64_t off = 0; off < n; off += c->chunk, k++) {

@@ -39,19 +39,18 @@ class BaseTeacher(object):
         be = world.backend()
         torch = be.torch
         kind = world.cookbook.index[task.goal_arg] or 0
-        be._reserve(1)
-        hg, ha = be.h_grid.numpy(), be.h_agent.numpy()
-        hg[0, :be.C] = state.cells
-        ha[0] = state._agent
+        grid = np.zeros((1, be.cs), np.uint8)
+        grid[0, :be.C] = state.cells
+        agent = np.array(state._agent, np.uint8).reshape(1, _lib.AGENT_BYTES)
         with torch.cuda.device(be.device):
             stream = ctypes.c_void_p(torch.cuda.current_stream(be.device).cuda_stream)
-            be.d_grid[:1].copy_(be.h_grid[:1], non_blocking=True)
-            be.d_agent[:1].copy_(be.h_agent[:1], non_blocking=True)
+            d_grid = torch.from_numpy(grid).to(be.device)
+            d_agent = torch.from_numpy(agent).to(be.device)
             d_kind = torch.full((1,), kind, dtype=torch.uint8, device=be.device)
             d_goal = torch.empty((1, 2), dtype=torch.uint8, device=be.device)
             d_len = torch.empty(1, dtype=torch.int16, device=be.device)
             d_seq = torch.empty((1, seq_cap), dtype=torch.uint8, device=be.device)
-            st = _lib.CraftStateC(be.d_grid.data_ptr(), be.d_agent.data_ptr(), 1, be.cs, 0)
+            st = _lib.CraftStateC(d_grid.data_ptr(), d_agent.data_ptr(), 1, be.cs, 0)
             rc = be.lib.psk_craft_find_closest(ctypes.byref(be.ct), st,
                                                ctypes.c_void_p(d_kind.data_ptr()),
                                                ctypes.c_void_p(d_goal.data_ptr()),

@@ -82,6 +82,7 @@ class CraftWorld(object):
         self._pending = []          # states whose transition has not been computed yet
         self._fresh = []            # initial states whose derived values are not cached yet
         self._grid_cache = {}
+        self._task_ids = {}         # (goal_name, goal_arg) -> task id
 
     # -- reference API -----------------------------------------------------------------------
     def make_scenario(self, grid, pos, dir=0):
@@ -175,6 +176,7 @@ class CraftState(object):
         self._task_hint = parent._task_hint if parent is not None else 0
         self._expert = {}           # task id -> action
         self._sat = {}              # task id -> 0 / 1 / 2
+        self._all = None            # (expert u8[T, m], sat u8[T, m], column): every task, see _run
         self._evaluated = False     # features / teacher / satisfies cached for the hinted task
 
     # -- materialisation ---------------------------------------------------------------------
@@ -225,14 +227,18 @@ class CraftState(object):
 
     def _invalidate(self):
         self._cached_features = None
-        self._expert, self._sat, self._evaluated = {}, {}, False
+        self._expert, self._sat, self._all, self._evaluated = {}, {}, None, False
 
     def _task_id(self, task):
-        tm = self.world.task_manager
-        t = tm.tasks_by_goal.get("%s[%s]" % (task.goal_name, task.goal_arg))
-        if t is None:
-            raise KeyError("unknown task %r" % (task,))
-        return t.task_id
+        w = self.world
+        key = (task.goal_name, task.goal_arg)
+        tid = w._task_ids.get(key)
+        if tid is None:
+            t = w.task_manager.tasks_by_goal.get("%s[%s]" % key)
+            if t is None:
+                raise KeyError("unknown task %r" % (task,))
+            tid = w._task_ids[key] = t.task_id
+        return tid
 
     def _evaluate(self, task_id=None):
         self._need()
@@ -241,12 +247,24 @@ class CraftState(object):
             self._evaluated = False
         if not self._evaluated:
             w = self.world
-            w.flush()
-            if not self._evaluated:
-                # evaluate together with every other initial state that is still waiting
-                batch = [self] + [s for s in w._fresh if s is not self and not s._evaluated]
-                w._fresh = []
-                w.backend().evaluate(batch, step=False)
+            # evaluate together with every other initial state that is still waiting
+            batch = [self] + [s for s in w._fresh if s is not self and not s._evaluated]
+            w._fresh = []
+            w.backend().evaluate(batch, step=False)
+
+    def _lookup(self, cache, which, tid):
+        """Teacher action / satisfies code for task ``tid``: from the per-task cache, from the
+        all-task table computed while the state's task was unknown, else by evaluating now.
+        Remembers the task so that the states stepped from this one are evaluated for it."""
+        v = cache.get(tid)
+        if v is None:
+            if self._all is not None:
+                v = cache[tid] = int(self._all[which][tid - 1, self._all[2]])
+                self._task_hint = tid
+            else:
+                self._evaluate(tid)
+                v = cache[tid]
+        return v
 
     # -- reference API -----------------------------------------------------------------------
     def step(self, action):
@@ -263,17 +281,11 @@ class CraftState(object):
         return self._cached_features
 
     def satisfies(self, task):
-        tid = self._task_id(task)
-        if tid not in self._sat:
-            self._evaluate(tid)
-        v = self._sat[tid]
+        v = self._lookup(self._sat, 1, self._task_id(task))
         return None if v == 2 else bool(v)
 
     def expert_action(self, task):
-        tid = self._task_id(task)
-        if tid not in self._expert:
-            self._evaluate(tid)
-        a = self._expert[tid]
+        a = self._lookup(self._expert, 0, self._task_id(task))
         if a == 255:
             raise AssertionError("subtask is neither 'use' nor 'go'")   # demonstration.py:18
         return a
@@ -330,21 +342,23 @@ class _Backend(object):
         self.nf = world.tables.n_features
         self.K = world.tables.K
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.T = world.tables.n_tasks - 1                      # task ids 1..T
+        self.task_ids = torch.arange(1, self.T + 1, dtype=torch.uint8, device=self.device)
 
     def _reserve(self, n):
         if n <= self.cap:
             return
         torch = self.torch
         cap = max(64, 1 << (n - 1).bit_length())
-        dev = self.device
-        self.h_grid = torch.zeros((cap, self.cs), dtype=torch.uint8).pin_memory()
-        self.h_agent = torch.zeros((cap, _lib.AGENT_BYTES), dtype=torch.uint8).pin_memory()
-        self.h_small = torch.zeros((4, cap), dtype=torch.uint8).pin_memory()   # action, task, expert, sat
-        self.h_feat = torch.zeros((cap, self.nf), dtype=torch.float32).pin_memory()
-        self.d_grid = torch.zeros((cap, self.cs), dtype=torch.uint8, device=dev)
-        self.d_agent = torch.zeros((cap, _lib.AGENT_BYTES), dtype=torch.uint8, device=dev)
-        self.d_small = torch.zeros((4, cap), dtype=torch.uint8, device=dev)
-        self.d_feat = torch.zeros((cap, self.nf), dtype=torch.float32, device=dev)
+        # one pinned blob and one device blob per direction: grid rows | agent records | four byte
+        # rows (action, task, teacher action, satisfies), laid out per call for the batch at hand
+        # so that a timestep is ONE host->device copy and two device->host copies
+        per_env = self.cs + _lib.AGENT_BYTES + 4
+        self.h_blob = torch.zeros(cap * per_env, dtype=torch.uint8).pin_memory()
+        self.d_blob = torch.zeros(cap * per_env, dtype=torch.uint8, device=self.device)
+        self.h_feat = torch.zeros(cap * self.nf, dtype=torch.float32).pin_memory()
+        self.d_feat = torch.zeros(cap * self.nf, dtype=torch.float32, device=self.device)
+        self.h_np, self.h_feat_np = self.h_blob.numpy(), self.h_feat.numpy()
         self.cap = cap
 
     def evaluate(self, states, step=True):
@@ -367,52 +381,95 @@ class _Backend(object):
         self._run(states, False)
 
     def _run(self, states, step):
+        import contextlib
         import ctypes
         torch = self.torch
         n = len(states)
         self._reserve(n)
-        hg, ha, hs = self.h_grid.numpy(), self.h_agent.numpy(), self.h_small.numpy()
-        for i, s in enumerate(states):
-            src = s._parent if step else s
-            hg[i, :self.C] = src._cells
-            ha[i] = src._agent
-            hs[0, i] = s._action if step else STOP
-            hs[1, i] = s._task_hint
-        with torch.cuda.device(self.device):
-            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-            self.d_grid[:n].copy_(self.h_grid[:n], non_blocking=True)
-            self.d_agent[:n].copy_(self.h_agent[:n], non_blocking=True)
-            self.d_small[:2, :n].copy_(self.h_small[:2, :n], non_blocking=True)
-            st = _lib.CraftStateC(self.d_grid.data_ptr(), self.d_agent.data_ptr(), n, self.cs, 0)
+        C, cs, AB, nf = self.C, self.cs, _lib.AGENT_BYTES, self.nf
+        n64 = (n + 63) & ~63
+        off_a = n64 * cs
+        off_s = off_a + n64 * AB
+        end_in, end = off_s + 2 * n64, off_s + 4 * n64
+        hb = self.h_np
+        hg = hb[:n * cs].reshape(n, cs)
+        ha = hb[off_a:off_a + n * AB].reshape(n, AB)
+        hs = hb[off_s:end].reshape(4, n64)
+        # gather with a handful of numpy calls for the whole batch (the per-state Python work of
+        # this function is what bounds the object API, not the GPU)
+        src = [s._parent for s in states] if step else states
+        parent_cells = np.concatenate([q._cells for q in src]).reshape(n, C)
+        hg[:, :C] = parent_cells
+        if cs > C:
+            hg[:, C:] = 0
+        ha[:] = np.concatenate([q._agent for q in src]).reshape(n, AB)
+        hs[0, :n] = [s._action for s in states] if step else STOP
+        hs[1, :n] = [s._task_hint for s in states]
+        same_device = torch.cuda.current_device() == self.device.index
+        with (contextlib.nullcontext() if same_device else torch.cuda.device(self.device)):
+            cur = torch.cuda.current_stream(self.device)
+            stream = ctypes.c_void_p(cur.cuda_stream)
+            self.d_blob[:end_in].copy_(self.h_blob[:end_in], non_blocking=True)
+            base = self.d_blob.data_ptr()
+            row = [ctypes.c_void_p(base + off_s + k * n64) for k in range(4)]
+            st = _lib.CraftStateC(base, base + off_a, n, cs, 0)
             tb = ctypes.byref(self.ct)
+            feat = ctypes.c_void_p(self.d_feat.data_ptr())
             p = lambda t: ctypes.c_void_p(t.data_ptr())
             if step:
-                _lib.check(self.lib.psk_craft_step(tb, st, p(self.d_small[0]), None, None,
-                                                   p(self.err), stream), "psk_craft_step")
-            _lib.check(self.lib.psk_craft_features(tb, st, p(self.d_feat), 0, stream),
-                       "psk_craft_features")
-            _lib.check(self.lib.psk_craft_expert(tb, st, p(self.d_small[1]), p(self.d_small[2]),
-                                                 None, None, stream), "psk_craft_expert")
-            _lib.check(self.lib.psk_craft_satisfies(tb, st, p(self.d_small[1]), p(self.d_small[3]),
-                                                    stream), "psk_craft_satisfies")
-            if step:
-                self.h_grid[:n].copy_(self.d_grid[:n], non_blocking=True)
-                self.h_agent[:n].copy_(self.d_agent[:n], non_blocking=True)
-            self.h_small[2:, :n].copy_(self.d_small[2:, :n], non_blocking=True)
-            self.h_feat[:n].copy_(self.d_feat[:n], non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-        hf = self.h_feat.numpy()
+                _lib.check(self.lib.psk_craft_step(tb, st, row[0], None, None, p(self.err), stream),
+                           "psk_craft_step")
+            _lib.check(self.lib.psk_craft_features(tb, st, feat, 0, stream), "psk_craft_features")
+            _lib.check(self.lib.psk_craft_expert(tb, st, row[1], row[2], None, None, stream),
+                       "psk_craft_expert")
+            _lib.check(self.lib.psk_craft_satisfies(tb, st, row[1], row[3], stream),
+                       "psk_craft_satisfies")
+            # States whose task is not known yet (initial states; every state of an evaluation
+            # rollout, where the teacher is never asked): teacher action and satisfies for EVERY
+            # task, on T replicas of those states, so that the per-env teacher(task, state) /
+            # satisfies(task) calls that follow are cache hits instead of one launch each.
+            hintless = [i for i, s in enumerate(states) if not s._task_hint]
+            all_tasks = None
+            if hintless:
+                m, T = len(hintless), self.T
+                g = self.d_blob[:n * cs].view(n, cs)
+                a = self.d_blob[off_a:off_a + n * AB].view(n, AB)
+                if m < n:
+                    idx = torch.as_tensor(hintless, dtype=torch.int64).to(self.device)
+                    g, a = g.index_select(0, idx), a.index_select(0, idx)
+                g, a = g.repeat(T, 1), a.repeat(T, 1)
+                tasks = self.task_ids.repeat_interleave(m)
+                all_tasks = torch.empty((2, T * m), dtype=torch.uint8, device=self.device)
+                st_all = _lib.CraftStateC(g.data_ptr(), a.data_ptr(), T * m, cs, 0)
+                _lib.check(self.lib.psk_craft_expert(tb, st_all, p(tasks), p(all_tasks[0]), None,
+                                                     None, stream), "psk_craft_expert")
+                _lib.check(self.lib.psk_craft_satisfies(tb, st_all, p(tasks), p(all_tasks[1]),
+                                                        stream), "psk_craft_satisfies")
+            lo = 0 if step else off_s + 2 * n64
+            self.h_blob[lo:end].copy_(self.d_blob[lo:end], non_blocking=True)
+            self.h_feat[:n * nf].copy_(self.d_feat[:n * nf], non_blocking=True)
+            cur.synchronize()
+            if all_tasks is not None:
+                all_tasks = all_tasks.cpu().numpy().reshape(2, self.T, len(hintless))
+                for col, i in enumerate(hintless):
+                    states[i]._all = (all_tasks[0], all_tasks[1], col)
+        feats = self.h_feat_np[:n * nf].reshape(n, nf).astype(np.float64)   # one row view per state
+        expert, sat = hs[2, :n].tolist(), hs[3, :n].tolist()
+        if step:
+            cells, agents = hg[:, :C].copy(), ha.copy()
+            unchanged = (cells == parent_cells).all(axis=1).tolist()
         for i, s in enumerate(states):
             if step:
                 parent = s._parent
-                cells = hg[i, :self.C]
-                s._cells = parent._cells if np.array_equal(cells, parent._cells) else cells.copy()
-                if s._cells is parent._cells:
-                    s._grid = parent._grid
-                s._agent = ha[i].copy()
+                if unchanged[i]:                 # share the grid (and its one-hot view) with the parent
+                    s._cells, s._grid = parent._cells, parent._grid
+                else:
+                    s._cells = cells[i]
+                s._agent = agents[i]
                 s._parent = None
-            s._cached_features = hf[i].astype(np.float64)
-            if s._task_hint:
-                s._expert[s._task_hint] = int(hs[2, i])
-                s._sat[s._task_hint] = int(hs[3, i])
+            s._cached_features = feats[i]
+            hint = s._task_hint
+            if hint:
+                s._expert[hint] = expert[i]
+                s._sat[hint] = sat[i]
             s._evaluated = True
