@@ -50,28 +50,30 @@ def policy_rollouts(env, policy, max_timesteps=40, is_eval=True, mix=None):
     acts = torch.full((n, max_timesteps), 255, dtype=torch.uint8, device=dev)
     refs = torch.full((n, max_timesteps), 255, dtype=torch.uint8, device=dev)
     feats = torch.empty((n, env.n_features), dtype=torch.float32, device=dev)
-    num_steps = num_inter = 0
-    t = 0
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)      # interactions, env steps (on device:
+    t = 0                                                       # one host sync per timestep)
     while not bool(done.all()):
         env.features(out=feats)
         a = policy(feats, t).to(device=dev, dtype=torch.uint8)
         if not is_eval:
             ref = env.expert()
             refs[:, t] = torch.where(done, refs[:, t], ref)
-            num_inter += int((~done).sum())
+            counts[0] += (~done).sum()
             if mix is not None:
                 a = torch.where(mix & ~done, ref, a)
         acts[:, t] = torch.where(done, acts[:, t], a)
         timer -= 1
         newly = ~done & ((a == STOP) | (timer <= 0))
-        if bool(newly.any()):
-            success |= newly & (env.satisfies() == 1)
+        success |= newly & (env.satisfies() == 1)
         done |= newly
         active = (~done).to(torch.uint8)
         env.step(a, active=active)
-        num_steps += int(active.sum()) * (not is_eval)
+        counts[1] += active.sum()
         t += 1
     env.check_errors()
+    num_inter, num_steps = (int(v) for v in counts.tolist())
+    if is_eval:
+        num_steps = 0
     # distances for get-tasks that failed: closest resource from the final pose, original grid
     tm = env.tables.task_manager
     is_get = torch.from_numpy(env.tables.task_is_get.astype(np.bool_)).to(dev)[env.task.long()]
