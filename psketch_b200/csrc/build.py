@@ -36,13 +36,15 @@ def needs_build():
     return False
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, extra=()):
+    """``out`` / ``extra``: experiment builds (another file name, extra -D flags) for A/B runs."""
+    if not force and not needs_build() and out is None:
         return LIB
     srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    cmd = ([nvcc_path()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) +
+           ["-o", out or LIB] + srcs)
     subprocess.check_call(cmd, cwd=HERE)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -777,6 +777,31 @@ __device__ __forceinline__ void store_out16(float4 *p, const float4 &t) {
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// The feature tile in shared memory holds one element of ESZ bytes per feature: f32 (ESZ 4, the
+// TMA path copies the tile to HBM as it is) or u8 (ESZ 1, the vector path widens u8 -> f32 on the
+// way out: every feature is a small exact integer, and a byte tile costs a quarter of the
+// shared-memory wavefronts for zero-fill and read-out — the L1/LSU data pipe, not HBM, was the
+// busiest unit of the rollout kernel with an f32 tile, profiles/README.md).
+template <int ESZ> __device__ __forceinline__ void sts_feat(uint32_t addr, uint32_t count) {
+    if (ESZ == 4) sts_f32(addr, (float)count);
+    else sts_u8(addr, count);
+}
+// element := 1 iff k != 0, as a predicated store (never a branch)
+template <int ESZ> __device__ __forceinline__ void sts_one_if(uint32_t addr, uint32_t k) {
+    if (ESZ == 4)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p st.shared.f32 [%0], %2;\n\t}" ::"r"(addr),
+            "r"(k), "f"(1.0f)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p st.shared.u8 [%0], %2;\n\t}" ::"r"(addr),
+            "r"(k), "r"(1)
+            : "memory");
+}
 __device__ __forceinline__ void sts_zero16(uint32_t addr) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0) : "memory");
 }
@@ -793,21 +818,23 @@ template <int W, int H, int TPE> struct RowChunks {
     // thread j of the env reads cells [j*NCH*8, (j+1)*NCH*8) (global or shared, 8-byte aligned)
     __device__ __forceinline__ void load(const uint8_t *r, int j) {
         row = r;
-        if (WINDOWED) return;
+        if constexpr (!WINDOWED) {
 #pragma unroll
-        for (int c = 0; c < NCH; c++)
-            v[c] = *reinterpret_cast<const uint2 *>(r + (j * NCH + c) * 8);
+            for (int c = 0; c < NCH; c++)
+                v[c] = *reinterpret_cast<const uint2 *>(r + (j * NCH + c) * 8);
+        }
     }
     // same from global memory, as volatile asm: the load is issued where it is written (the
     // prefetch of the next chunk), not sunk by the compiler to its first use an iteration later
     __device__ __forceinline__ void prefetch(const uint8_t *r, int j) {
         row = r;
-        if (WINDOWED) return;
+        if constexpr (!WINDOWED) {
 #pragma unroll
-        for (int c = 0; c < NCH; c++)
-            asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];"
-                         : "=r"(v[c].x), "=r"(v[c].y)
-                         : "l"(r + (j * NCH + c) * 8));
+            for (int c = 0; c < NCH; c++)
+                asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];"
+                             : "=r"(v[c].x), "=r"(v[c].y)
+                             : "l"(r + (j * NCH + c) * 8));
+        }
     }
 };
 
@@ -815,7 +842,7 @@ template <int W, int H, int TPE> struct RowChunks {
 // the TPE threads of the env; thread j owns the cells in `cells`.  K is the number of kinds.
 // The centre block of the pooled WIN^2 x WIN^2 window is exactly the local WIN x WIN window
 // (bhw = hw*WIN + hw), so one pass over the cells writes both feature groups.
-template <int W, int H, int WIN, int TPE>
+template <int W, int H, int WIN, int TPE, int ESZ>
 __device__ __forceinline__ void scatter_features(uint32_t frow_s, uint32_t trash_s,
                                                  const RowChunks<W, H, TPE> &cells,
                                                  const Agent &a, int K, int j) {
@@ -823,7 +850,7 @@ __device__ __forceinline__ void scatter_features(uint32_t frow_s, uint32_t trash
     constexpr int WW = WIN * WIN;
     constexpr int NCH = RowChunks<W, H, TPE>::NCH;
     const int px = a.x(), py = a.y();
-    const int K4 = K * 4;
+    const int K4 = K * ESZ;   // bytes per cell of the tile
     const uint32_t big_s = frow_s + WW * K4;
     if (RowChunks<W, H, TPE>::WINDOWED) {
         // gather the WW x WW window cells (thread j takes every TPE-th)
@@ -833,9 +860,9 @@ __device__ __forceinline__ void scatter_features(uint32_t frow_s, uint32_t trash
             if (x < 0 || y < 0 || x >= W || y >= H) continue;
             const int k = __ldg(cells.row + x * H + y);
             if (k == 0) continue;
-            sts_f32(big_s + (((bx / WIN) * WIN + (by / WIN)) * K + k) * 4, 1.0f);
+            sts_feat<ESZ>(big_s + (((bx / WIN) * WIN + (by / WIN)) * K + k) * ESZ, 1);
             if (bx / WIN == HW && by / WIN == HW)
-                sts_f32(frow_s + (((bx - HW * WIN) * WIN + (by - HW * WIN)) * K + k) * 4, 1.0f);
+                sts_feat<ESZ>(frow_s + (((bx - HW * WIN) * WIN + (by - HW * WIN)) * K + k) * ESZ, 1);
         }
     } else
 #pragma unroll
@@ -843,7 +870,42 @@ __device__ __forceinline__ void scatter_features(uint32_t frow_s, uint32_t trash
         const int cc = (j * NCH + ch) * 8;
         const uint2 v = cells.v[ch];
         if (cc >= W * H || (v.x | v.y) == 0) continue;
-        if (H % 8 == 0) {
+        if (H == 8 && WIN == 3) {
+            // 8x8 grid, 3x3 window (craft_medium): the thread's 8 cells are column x.  The column
+            // is shifted so that byte `by` of (z2:z1:z0) is the kind at window row by
+            // (y = py - BHW + by; rows outside the grid and columns outside the window read 0);
+            // the 9 window rows then sit at compile-time byte positions and every store is one
+            // byte extract, one address add and one predicated st.shared (no branches, no
+            // per-cell range checks).
+            const int x = cc / 8;
+            const int bx = x - px + BHW;
+            const bool bx_ok = (unsigned)bx < (unsigned)WW;
+            const int bi = bx / WIN;
+            const uint32_t vx = bx_ok ? v.x : 0u, vy = bx_ok ? v.y : 0u;
+            const int sh = 8 * py;                       // = 8 * (py - BHW + 4): 0..56
+            const bool hi_word = sh >= 32;
+            const uint32_t a0 = hi_word ? vx : 0u, a1 = hi_word ? vy : vx, a2 = hi_word ? 0u : vy;
+            const uint32_t z0 = __funnelshift_r(a0, a1, sh & 31);
+            const uint32_t z1 = __funnelshift_r(a1, a2, sh & 31);
+            const uint32_t z2 = a2 >> (sh & 31);
+            const uint32_t big_col = big_s + bi * (WIN * K4);
+#pragma unroll
+            for (int by = 0; by < 9; by++) {             // pooled window, block (bi, by / 3)
+                const uint32_t z = by < 4 ? z0 : (by < 8 ? z1 : z2);
+                const uint32_t k = (z >> ((by & 3) * 8)) & 0xFF;
+                sts_one_if<ESZ>(big_col + (by / WIN) * K4 + k * ESZ, k);
+            }
+            // local window = centre block; ravel order (dx, dy, kind)  (craft.py:304-305)
+            const bool centre_col = bx_ok && bi == HW;
+            const uint32_t c0 = centre_col ? z0 : 0u, c1 = centre_col ? z1 : 0u;
+            const uint32_t loc_col = frow_s + (bx - HW * WIN) * (WIN * K4);
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++) {
+                const int by = HW * WIN + dy;
+                const uint32_t k = ((by < 4 ? c0 : c1) >> ((by & 3) * 8)) & 0xFF;
+                sts_one_if<ESZ>(loc_col + dy * K4 + k * ESZ, k);
+            }
+        } else if (H % 8 == 0) {
             // the 8 cells share one column x; y = y0 + b.  Stores are unconditional: a cell that
             // contributes nothing writes into the warp's trash slot instead (no branches).
             const int x = cc / H, y0 = cc % H;
@@ -860,11 +922,11 @@ __device__ __forceinline__ void scatter_features(uint32_t frow_s, uint32_t trash
                 const int by = by0 + b;
                 const bool ok = bx_ok && (unsigned)by < (unsigned)WW && k != 0;
                 const int bj = by / WIN;
-                const uint32_t off = by * K4 + k * 4;
+                const uint32_t off = by * K4 + k * ESZ;
                 // pooled window, block (bi, bj)  (craft.py:306-310)
-                sts_f32(ok ? big_col + bj * K4 + k * 4 : trash_s, 1.0f);
+                sts_feat<ESZ>(ok ? big_col + bj * K4 + k * ESZ : trash_s, 1);
                 // local window, ravel order (dx, dy, kind)  (craft.py:304-305)
-                sts_f32((ok && centre_col && bj == HW) ? loc_col + off : trash_s, 1.0f);
+                sts_feat<ESZ>((ok && centre_col && bj == HW) ? loc_col + off : trash_s, 1);
             }
         } else {
 #pragma unroll
@@ -874,10 +936,10 @@ __device__ __forceinline__ void scatter_features(uint32_t frow_s, uint32_t trash
                 if (k == 0 || c >= W * H) continue;
                 const int dx = c / H - px, dy = c % H - py;
                 if ((unsigned)(dx + HW) < (unsigned)WIN && (unsigned)(dy + HW) < (unsigned)WIN)
-                    sts_f32(frow_s + (((dx + HW) * WIN + (dy + HW)) * K + k) * 4, 1.0f);
+                    sts_feat<ESZ>(frow_s + (((dx + HW) * WIN + (dy + HW)) * K + k) * ESZ, 1);
                 const int bx = dx + BHW, by = dy + BHW;
                 if ((unsigned)bx < (unsigned)WW && (unsigned)by < (unsigned)WW)
-                    sts_f32(big_s + (((bx / WIN) * WIN + (by / WIN)) * K + k) * 4, 1.0f);
+                    sts_feat<ESZ>(big_s + (((bx / WIN) * WIN + (by / WIN)) * K + k) * ESZ, 1);
             }
         }
     }
@@ -889,10 +951,10 @@ __device__ __forceinline__ void scatter_features(uint32_t frow_s, uint32_t trash
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int cnt = (w >> (8 * b)) & 0xFF;
-            if (cnt && wi * 4 + b < K) sts_f32(tail_s + (wi * 4 + b) * 4, (float)cnt);
+            if (cnt && wi * 4 + b < K) sts_feat<ESZ>(tail_s + (wi * 4 + b) * ESZ, cnt);
         }
     }
-    if (j == TPE - 1) sts_f32(tail_s + (K + a.dir()) * 4, 1.0f);  // craft.py:321-322; last stays 0
+    if (j == TPE - 1) sts_feat<ESZ>(tail_s + (K + a.dir()) * ESZ, 1);  // craft.py:321-322; last stays 0
 }
 
 // TMA helpers (cp.async.bulk, shared::cta -> global)
@@ -910,73 +972,104 @@ __device__ __forceinline__ void fence_async_smem() {
 }
 
 // One warp builds the feature rows of up to EPW = 32/TPE consecutive envs in its own shared-
-// memory buffer(s) and sends each finished chunk to HBM; no CTA-level barrier is involved: warps
+// memory tile(s) and sends each finished chunk to HBM; no CTA-level barrier is involved: warps
 // are autonomous pipelines.  Two ways out of shared memory:
-//   USE_TMA  one cp.async.bulk (UBLKCP) per chunk, issued by lane 0, two buffers per warp so the
-//            store of chunk i overlaps the build of chunk i+1; the buffer is zero-filled per chunk;
-//   else     coalesced 128-bit st.global.cs by all lanes; every word read out is zeroed in the
-//            same pass, so one buffer per warp stays clean (feature_buffer_init zeroes it once).
-//   wbuf_s  shared address of this warp's buffer(s); it = this warp's chunk counter (parity)
+//   USE_TMA  f32 tile; one cp.async.bulk (UBLKCP) per chunk, issued by lane 0, two tiles per warp
+//            so the store of chunk i overlaps the build of chunk i+1; the tile is zero-filled per
+//            chunk;
+//   else     u8 tile (see sts_feat); all lanes read one 32-bit word (4 features), widen it to a
+//            float4 and write coalesced 128-bit st.global.cs; every word read out is zeroed in
+//            the same pass, so one tile per warp stays clean (feature_buffer_init zeroes it once).
+//   wbuf_s  shared address of this warp's tile(s); it = this warp's chunk counter (parity)
 //   gdst    where the chunk's rows go; ne = live envs in the chunk (<= EPW)
 //   cells/a the lane's share of its env's grid row and the env's agent record
 // KC > 0 fixes the number of kinds at compile time (KC == K) so that the loops unroll.
-// Each buffer is EPW*nf floats + one 16-byte trash slot for the scatter's no-op stores.
-__host__ __device__ constexpr int feature_buffer_bytes(int epw, int nf) { return epw * nf * 4 + 16; }
+// Each tile is EPW*nf elements (rounded up to 16 bytes) + one 16-byte trash slot for the
+// scatter's no-op stores.
+// Element size of the tile on the vector-store path, measured on one box (profiles/README.md):
+// the stand-alone features kernel is 4 % faster with the u8 tile (it is bound by the L1/LSU data
+// pipe), the fused kernels are 3 % slower with it (their feature warps share the issue slots
+// with the teacher, and widening costs 8 more instructions per 16 bytes), so they keep f32.
+#define PSK_ESZ_FEATURES_KERNEL 1
+#define PSK_ESZ_FUSED_KERNELS 4
+__host__ __device__ constexpr int feature_tile_bytes(bool tma, int epw, int nf, int vec_esz) {
+    return ((epw * nf * (tma ? 4 : vec_esz) + 15) / 16) * 16 + 16;
+}
+// all tiles of one warp
+__host__ __device__ constexpr int feature_buffer_bytes(bool tma, int epw, int nf, int vec_esz) {
+    return (tma ? 2 : 1) * feature_tile_bytes(tma, epw, nf, vec_esz);
+}
 
-template <int TPE, int KC, bool USE_TMA>
+template <int TPE, int KC, bool USE_TMA, int VEC_ESZ>
 __device__ __forceinline__ void feature_buffer_init(uint32_t wbuf_s, int nf) {
     constexpr int EPW = 32 / TPE;
     const int lane = threadIdx.x & 31;
-    const int bytes = (USE_TMA ? 2 : 1) * feature_buffer_bytes(EPW, nf);
-    if ((bytes & 15) == 0 && (wbuf_s & 15) == 0) {
-        for (int i = lane; i < bytes / 16; i += 32) sts_zero16(wbuf_s + i * 16);
-    } else {
-        for (int i = lane; i < bytes / 4; i += 32) sts_f32(wbuf_s + i * 4, 0.f);
-    }
+    const int bytes = feature_buffer_bytes(USE_TMA, EPW, nf, VEC_ESZ);      // a multiple of 16
+    for (int i = lane; i < bytes / 16; i += 32) sts_zero16(wbuf_s + i * 16);
     __syncwarp();
 }
 
-template <int W, int H, int WIN, int TPE, int KC, bool USE_TMA>
+// u8 x4 -> float4, exact: byte b of the word is merged under the exponent of 2^23 (one PRMT) and
+// 2^23 is subtracted (one FADD)
+__device__ __forceinline__ float4 widen_u8x4(uint32_t w) {
+    float4 t;
+    t.x = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440)) - 8388608.0f;
+    t.y = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7441)) - 8388608.0f;
+    t.z = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7442)) - 8388608.0f;
+    t.w = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7443)) - 8388608.0f;
+    return t;
+}
+
+template <int W, int H, int WIN, int TPE, int KC, bool USE_TMA, int VEC_ESZ>
 __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, float *gdst, int ne,
                                                    const RowChunks<W, H, TPE> &cells,
                                                    const Agent &a, int K, int nf) {
     constexpr int EPW = 32 / TPE;
+    constexpr int ESZ = USE_TMA ? 4 : VEC_ESZ;
     if (KC > 0) {
         K = KC;
         nf = 2 * WIN * WIN * KC + KC + 5;
     }
     const int lane = threadIdx.x & 31;
     const int le = lane / TPE, j = lane % TPE;
-    const uint32_t buf_s = wbuf_s + (USE_TMA ? (uint32_t)(it & 1) * feature_buffer_bytes(EPW, nf) : 0u);
-    const uint32_t trash_s = buf_s + EPW * nf * 4;
-    const int n16 = EPW * nf / 4;
+    const uint32_t buf_s = wbuf_s + (USE_TMA ? (uint32_t)(it & 1) * feature_tile_bytes(true, EPW, nf, 4) : 0u);
+    const uint32_t trash_s = buf_s + feature_tile_bytes(USE_TMA, EPW, nf, VEC_ESZ) - 16;
+    const int n16 = EPW * nf / 4;        // float4s of a full chunk (EPW is a multiple of 4)
     if (USE_TMA) {
-        // the buffer was handed to the TMA two chunks ago: wait until it has been read, re-zero
+        // the tile was handed to the TMA two chunks ago: wait until it has been read, re-zero
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
-        if ((nf & 3) == 0) {
-            if (KC > 0) {
+        if (KC > 0) {
 #pragma unroll
-                for (int i = 0; i < (n16 + 31) / 32; i++)
-                    if (i * 32 + lane < n16) sts_zero16(buf_s + (i * 32 + lane) * 16);
-            } else {
-                for (int i = lane; i < n16; i += 32) sts_zero16(buf_s + i * 16);
-            }
+            for (int i = 0; i < (n16 + 31) / 32; i++)
+                if (i * 32 + lane < n16) sts_zero16(buf_s + (i * 32 + lane) * 16);
         } else {
-            for (int i = lane; i < EPW * nf; i += 32) sts_f32(buf_s + i * 4, 0.f);
+            for (int i = lane; i < n16; i += 32) sts_zero16(buf_s + i * 16);
         }
         __syncwarp();
     }
-    if (le < ne) scatter_features<W, H, WIN, TPE>(buf_s + le * nf * 4, trash_s, cells, a, K, j);
+    if (le < ne)
+        scatter_features<W, H, WIN, TPE, ESZ>(buf_s + le * nf * ESZ, trash_s, cells, a, K, j);
     const uint32_t bytes = (uint32_t)ne * (uint32_t)nf * 4u;
     // 16-byte paths need the chunk size AND its destination aligned (a frame of a feature ring
     // starts at slot*n*nf floats, which is not a multiple of 16 bytes for every n and nf)
     const bool vec_ok = (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(gdst) & 15) == 0;
-    if (USE_TMA && vec_ok) {
-        fence_async_smem();  // generic-proxy writes -> visible to the async proxy
-        __syncwarp();
-        if (lane == 0) bulk_store(gdst, buf_s, bytes);
-    } else {
+    if (USE_TMA) {
+        if (vec_ok) {
+            fence_async_smem();  // generic-proxy writes -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) bulk_store(gdst, buf_s, bytes);
+        } else {
+            __syncwarp();
+            for (int i = lane; i < ne * nf; i += 32) {
+                float t;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(buf_s + i * 4));
+                gdst[i] = t;
+            }
+            __syncwarp();
+        }
+    } else if (ESZ == 4) {
+        // f32 tile, 128-bit read-out
         __syncwarp();
         if (vec_ok) {
             float4 *g4 = reinterpret_cast<float4 *>(gdst);
@@ -986,7 +1079,7 @@ __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, floa
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                              : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
                              : "r"(buf_s + i * 16));
-                if (!USE_TMA) sts_zero16(buf_s + i * 16);
+                sts_zero16(buf_s + i * 16);
                 store_out16(g4 + i, t);
             };
             if (KC > 0 && m16 == n16) {
@@ -995,8 +1088,7 @@ __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, floa
                     if (i * 32 + lane < n16) move16(i * 32 + lane);
             } else {
                 for (int i = lane; i < m16; i += 32) move16(i);
-                if (!USE_TMA)   // rows of dead lanes may have been touched by nobody, but stay safe
-                    for (int i = m16 + lane; i < n16; i += 32) sts_zero16(buf_s + i * 16);
+                for (int i = m16 + lane; i < n16; i += 32) sts_zero16(buf_s + i * 16);
             }
         } else {
             for (int i = lane; i < ne * nf; i += 32) {
@@ -1005,8 +1097,39 @@ __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, floa
                 gdst[i] = t;
             }
             __syncwarp();
-            if (!USE_TMA)
-                for (int i = lane; i < EPW * nf; i += 32) sts_f32(buf_s + i * 4, 0.f);
+            for (int i = lane; i < n16; i += 32) sts_zero16(buf_s + i * 16);
+        }
+        __syncwarp();
+    } else {
+        __syncwarp();
+        if (vec_ok) {
+            float4 *g4 = reinterpret_cast<float4 *>(gdst);
+            const int m16 = (int)(bytes / 16);
+            auto move16 = [&](int i) {            // features 4i .. 4i+3 of the chunk
+                uint32_t w;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(buf_s + i * 4));
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(buf_s + i * 4), "r"(0) : "memory");
+                store_out16(g4 + i, widen_u8x4(w));
+            };
+            if (KC > 0 && m16 == n16) {
+#pragma unroll
+                for (int i = 0; i < (n16 + 31) / 32; i++)
+                    if (i * 32 + lane < n16) move16(i * 32 + lane);
+            } else {
+                for (int i = lane; i < m16; i += 32) move16(i);
+                // rows of dead lanes were touched by nobody, but stay safe
+                for (int i = m16 + lane; i < n16; i += 32)
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(buf_s + i * 4), "r"(0) : "memory");
+            }
+        } else {
+            for (int i = lane; i < ne * nf; i += 32) {
+                uint32_t b;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(buf_s + i));
+                gdst[i] = (float)b;
+            }
+            __syncwarp();
+            for (int i = lane; i < n16; i += 32)
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(buf_s + i * 4), "r"(0) : "memory");
         }
         __syncwarp();
     }
@@ -1022,8 +1145,8 @@ craft_features_kernel(const uint8_t *__restrict__ grid, const uint8_t *__restric
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int le = lane / TPE, j = lane % TPE;
-    const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)warp * (USE_TMA ? 2 : 1) * feature_buffer_bytes(EPW, nf);
-    if (!USE_TMA) feature_buffer_init<TPE, KC, USE_TMA>(wbuf_s, nf);
+    const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)warp * feature_buffer_bytes(USE_TMA, EPW, nf, PSK_ESZ_FEATURES_KERNEL);
+    if (!USE_TMA) feature_buffer_init<TPE, KC, USE_TMA, PSK_ESZ_FEATURES_KERNEL>(wbuf_s, nf);
     const int64_t n_chunks = (n + EPW - 1) / EPW;
     const int64_t stride = (int64_t)gridDim.x * WPB;
     int64_t ch = (int64_t)blockIdx.x * WPB + warp;
@@ -1041,7 +1164,8 @@ craft_features_kernel(const uint8_t *__restrict__ grid, const uint8_t *__restric
         if (more) fetch(ch + stride, a_next, cells_next);
         const int64_t e0 = ch * EPW;
         const int ne = (int)((n - e0) < EPW ? (n - e0) : EPW);
-        warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA>(wbuf_s, it, out + e0 * nf, ne, cells, a, K, nf);
+        warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA, PSK_ESZ_FEATURES_KERNEL>(wbuf_s, it, out + e0 * nf, ne, cells, a,
+                                                                                 K, nf);
         if (more) {
             a = a_next;
             cells = cells_next;
@@ -1188,8 +1312,9 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
     const int tid = threadIdx.x;
     const bool env_warp = tid < NE;
     if (!USE_TMA && !env_warp && features_out)
-        feature_buffer_init<8, KC, USE_TMA>(
-            smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(4, nf), nf);
+        feature_buffer_init<8, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
+            smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
+            nf);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     uint32_t flags = 0;
     int it = 0;  // this feature warp's chunk counter
@@ -1246,7 +1371,7 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
             add_stats(stats, done, success, live);
         } else if (features_out) {
             const int fw = (tid - NE) >> 5, lane = tid & 31;
-            const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)fw * (USE_TMA ? 2 : 1) * feature_buffer_bytes(EPW, nf);
+            const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)fw * feature_buffer_bytes(USE_TMA, EPW, nf, PSK_ESZ_FUSED_KERNELS);
             for (int c = 0; c < SPW / EPW; c++) {
                 const int s0 = fw * SPW + c * EPW;      // first env slot of the chunk
                 if (s0 >= ne_sp) break;
@@ -1261,7 +1386,7 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
                 }
                 RowChunks<W, H, TPE> cells;
                 cells.load(s_rows + se * CP, lane % TPE);
-                warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA>(
+                warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
                     wbuf_s, it, features_out + (e_base + s0) * nf, ne, cells, b, K, nf);
                 it++;
             }
@@ -1311,8 +1436,9 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
     const int tid = threadIdx.x;
     const bool env_warp = tid < NE;
     if (!USE_TMA && !env_warp && features_out)
-        feature_buffer_init<8, KC, USE_TMA>(
-            smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(4, nf), nf);
+        feature_buffer_init<8, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
+            smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
+            nf);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     uint32_t flags = 0;
     int it = 0;
@@ -1379,7 +1505,7 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
             } else if (features_out) {
                 const int fw = (tid - NE) >> 5, lane = tid & 31;
                 const uint32_t wbuf_s = smem_u32(smem_raw) +
-                                        (uint32_t)fw * (USE_TMA ? 2 : 1) * feature_buffer_bytes(EPW, nf);
+                                        (uint32_t)fw * feature_buffer_bytes(USE_TMA, EPW, nf, PSK_ESZ_FUSED_KERNELS);
                 float *fout = features_out + (int64_t)(t % feat_ring) * n * nf;
                 for (int c = 0; c < SPW / EPW; c++) {
                     const int s0 = fw * SPW + c * EPW;
@@ -1395,7 +1521,7 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
                     }
                     RowChunks<W, H, TPE> cells;
                     cells.load(s_rows[cur] + se * CP, lane % TPE);
-                    warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA>(
+                    warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
                         wbuf_s, it, fout + (e_base + s0) * nf, ne, cells, b, K, nf);
                     it++;
                 }
@@ -1556,7 +1682,7 @@ template <int W, int H, int WIN> struct Config {
                              cudaStream_t st) {
         constexpr int WPB = 4, EPW = 32 / TPE;
         const int f = nf(t);
-        const size_t smem = (size_t)WPB * (TMA ? 2 : 1) * feature_buffer_bytes(EPW, f);
+        const size_t smem = (size_t)WPB * feature_buffer_bytes(TMA, EPW, f, PSK_ESZ_FEATURES_KERNEL);
         // the default cookbook has 21 kinds: that case is compiled with K fixed
         auto kern = t->n_kinds == 21 ? craft_features_kernel<W, H, WIN, WPB, TPE, 21, TMA>
                                      : craft_features_kernel<W, H, WIN, WPB, TPE, 0, TMA>;
@@ -1607,7 +1733,7 @@ template <int W, int H, int WIN> struct Config {
                             int32_t *err, cudaStream_t st) {
         constexpr int EPW = 32 / TPE;
         const int f = nf(t);
-        const size_t smem = (size_t)NFW * (TMA ? 2 : 1) * feature_buffer_bytes(EPW, f);
+        const size_t smem = (size_t)NFW * feature_buffer_bytes(TMA, EPW, f, PSK_ESZ_FUSED_KERNELS);
         auto kern = t->n_kinds == 21 ? craft_tick_kernel<W, H, WIN, NE, NFW, 21, TMA>
                                      : craft_tick_kernel<W, H, WIN, NE, NFW, 0, TMA>;
         static size_t configured_on[PSK_MAX_DEVICES] = {0};   // the attribute is per device
@@ -1661,7 +1787,7 @@ template <int W, int H, int WIN> struct Config {
                                cudaStream_t st) {
         constexpr int EPW = 32 / TPE;
         const int f = nf(t);
-        const size_t smem = (size_t)NFW * (TMA ? 2 : 1) * feature_buffer_bytes(EPW, f);
+        const size_t smem = (size_t)NFW * feature_buffer_bytes(TMA, EPW, f, PSK_ESZ_FUSED_KERNELS);
         auto kern = t->n_kinds == 21 ? craft_rollout_kernel<W, H, WIN, NE, NFW, 21, TMA>
                                      : craft_rollout_kernel<W, H, WIN, NE, NFW, 0, TMA>;
         static size_t configured_on[PSK_MAX_DEVICES] = {0};   // the attribute is per device
@@ -1704,7 +1830,8 @@ template <int W, int H, int WIN> struct Config {
                 const char *m = getenv("PSK_ROLLOUT_TMA");
                 env_tma = m ? atoi(m) : -1;
             }
-            const int tma = env_tma >= 0 ? env_tma : (s.n > 262144 ? 1 : 0);
+            // one wave of CTAs (<= 65,536 envs): vector stores; more: TMA stores (sweep in profiles/README.md)
+            const int tma = env_tma >= 0 ? env_tma : (s.n > 65536 ? 1 : 0);
             return tma ? rollout_variant<64, 2, true>(t, s, ep, ticks, action_in, features_out, feat_ring,
                                                       expert_out, done, success, stats, err, st)
                        : rollout_variant<64, 2, false>(t, s, ep, ticks, action_in, features_out, feat_ring,
