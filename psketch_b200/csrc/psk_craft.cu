@@ -764,14 +764,10 @@ craft_find_closest_rows_kernel(const uint8_t *__restrict__ grid, const uint8_t *
 // =============================================================================================
 // features  (worlds/craft.py:296-330)
 // =============================================================================================
-// Experiment knob for the vector-store path (PSK_STORE_MODE): 0 st.global.cs, 1 st.global,
-// 2 st.global.wt.  Set once from the environment by the host wrappers.
-__constant__ int g_store_mode = 0;
-__device__ __forceinline__ void store_out16(float4 *p, const float4 &t) {
-    if (g_store_mode == 0) __stcs(p, t);
-    else if (g_store_mode == 1) *p = t;
-    else __stwt(p, t);
-}
+// Streaming store of the vector path: st.global.cs (evict-first).  Plain st.global and
+// st.global.wt were tried through a run-time knob and were never faster (profiles/README.md);
+// the knob cost a branch per store and is gone.
+__device__ __forceinline__ void store_out16(float4 *p, const float4 &t) { __stcs(p, t); }
 
 // Shared-space stores by 32-bit address (no generic-address conversion in the hot loop).
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
@@ -1083,9 +1079,32 @@ __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, floa
                 store_out16(g4 + i, t);
             };
             if (KC > 0 && m16 == n16) {
+                // the shared-memory instructions are volatile asm and keep their source order, so
+                // the order is written out: four loads in flight, then their re-zeroing, then the
+                // four global stores (one load latency per four 16-byte pieces instead of one each)
+                constexpr int NIT = (EPW * (2 * WIN * WIN * KC + KC + 5) / 4 + 31) / 32;
 #pragma unroll
-                for (int i = 0; i < (n16 + 31) / 32; i++)
-                    if (i * 32 + lane < n16) move16(i * 32 + lane);
+                for (int i0 = 0; i0 < NIT; i0 += 4) {
+                    float4 t[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = (i0 + u) * 32 + lane;
+                        if (i0 + u < NIT && i < n16)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                         : "=f"(t[u].x), "=f"(t[u].y), "=f"(t[u].z), "=f"(t[u].w)
+                                         : "r"(buf_s + i * 16));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = (i0 + u) * 32 + lane;
+                        if (i0 + u < NIT && i < n16) sts_zero16(buf_s + i * 16);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = (i0 + u) * 32 + lane;
+                        if (i0 + u < NIT && i < n16) store_out16(g4 + i, t[u]);
+                    }
+                }
             } else {
                 for (int i = lane; i < m16; i += 32) move16(i);
                 for (int i = m16 + lane; i < n16; i += 32) sts_zero16(buf_s + i * 16);
@@ -1112,9 +1131,28 @@ __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, floa
                 store_out16(g4 + i, widen_u8x4(w));
             };
             if (KC > 0 && m16 == n16) {
+                constexpr int NIT = (EPW * (2 * WIN * WIN * KC + KC + 5) / 4 + 31) / 32;
 #pragma unroll
-                for (int i = 0; i < (n16 + 31) / 32; i++)
-                    if (i * 32 + lane < n16) move16(i * 32 + lane);
+                for (int i0 = 0; i0 < NIT; i0 += 4) {      // same ordering as the f32 read-out
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = (i0 + u) * 32 + lane;
+                        if (i0 + u < NIT && i < n16)
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[u]) : "r"(buf_s + i * 4));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = (i0 + u) * 32 + lane;
+                        if (i0 + u < NIT && i < n16)
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(buf_s + i * 4), "r"(0) : "memory");
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i = (i0 + u) * 32 + lane;
+                        if (i0 + u < NIT && i < n16) store_out16(g4 + i, widen_u8x4(w[u]));
+                    }
+                }
             } else {
                 for (int i = lane; i < m16; i += 32) move16(i);
                 // rows of dead lanes were touched by nobody, but stay safe
@@ -1559,10 +1597,6 @@ static int num_sms() {
     static int sms[PSK_MAX_DEVICES] = {0};
     const int dev = current_device();
     if (!sms[dev]) {
-        if (const char *m = getenv("PSK_STORE_MODE")) {      // experiment knob, profiles/README.md
-            const int mode = atoi(m);
-            cudaMemcpyToSymbol(g_store_mode, &mode, sizeof(int));
-        }
         int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         sms[dev] = n > 0 ? n : 148;
