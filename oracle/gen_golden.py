@@ -358,6 +358,14 @@ def export_sampler_stats(R, path, n_scen=3000, seed=4242):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--custom" in sys.argv:
+        # a non-default cookbook / hint file through the unmodified reference
+        cdir = os.path.join(OUT, "custom")
+        RC = ref_shim.Reference(recipes=os.path.join(cdir, "recipes.yaml"),
+                                hints=os.path.join(cdir, "hints.yaml"))
+        states = collect_states(RC, None, 0, 0, 2000, seed=31337)
+        export_states(RC, states, os.path.join(OUT, "craft_custom_states.npz"))
+        return
     if "--sampler-only" in sys.argv:
         export_sampler_stats(ref_shim.Reference(), os.path.join(OUT, "sampler_stats.npz"))
         return

@@ -78,12 +78,16 @@ def reference_cwd():
         os.chdir(old)
 
 
-def make_config(experiment="imitation", seed=123, world_config=None):
+def make_config(experiment="imitation", seed=123, world_config=None, recipes=None, hints=None):
     from misc.util import Struct  # reference module
     with open(os.path.join(REF_ROOT, "configs", "experiments", experiment + ".yaml")) as f:
         raw = yaml.safe_load(f)
     if world_config is not None:
         raw["world"]["config"] = world_config
+    if recipes is not None:                 # another cookbook (absolute path), worlds/craft.py:61
+        raw["recipes"] = os.path.abspath(recipes)
+    if hints is not None:                   # another hint file, data/task.py:36
+        raw["trainer"]["hints"] = os.path.abspath(hints)
     config = Struct(**raw)
     config.random = np.random.RandomState(seed)
     return config
@@ -92,7 +96,7 @@ def make_config(experiment="imitation", seed=123, world_config=None):
 class Reference(object):
     """Handle on the live reference objects (world, teacher, task manager)."""
 
-    def __init__(self, experiment="imitation", seed=123, world_config=None):
+    def __init__(self, experiment="imitation", seed=123, world_config=None, recipes=None, hints=None):
         if not reference_available():
             raise RuntimeError("reference tree not found at %s" % REF_ROOT)
         _install_shims()
@@ -103,7 +107,7 @@ class Reference(object):
             import worlds.light as ref_light
             import teachers.demonstration as ref_demo
             import data.task as ref_task
-            self.config = make_config(experiment, seed, world_config)
+            self.config = make_config(experiment, seed, world_config, recipes, hints)
             self.task_manager = ref_task.TaskManager(self.config)
             self.world = ref_craft.CraftWorld(self.config)
             self.teacher = ref_demo.DemonstrationTeacher(self.config)

@@ -45,6 +45,26 @@ def large_states():
 
 
 @pytest.fixture(scope="session")
+def custom_states():
+    """2,000 states exported from the unmodified reference running tests/golden/custom/*.yaml."""
+    return np.load(os.path.join(GOLDEN, "craft_custom_states.npz"))
+
+
+@pytest.fixture(scope="session")
+def custom_tables():
+    from psketch_b200.tables import Cookbook, CraftTables, TaskManager
+    cdir = os.path.join(GOLDEN, "custom")
+    return CraftTables(Cookbook(os.path.join(cdir, "recipes.yaml")),
+                       TaskManager(os.path.join(cdir, "hints.yaml")), "craft_medium")
+
+
+@pytest.fixture(scope="session")
+def custom_oracle(custom_tables):
+    from oracle.craft_oracle import CraftOracle
+    return CraftOracle(custom_tables)
+
+
+@pytest.fixture(scope="session")
 def light_states():
     return np.load(os.path.join(GOLDEN, "light_states.npz"))
 

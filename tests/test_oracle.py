@@ -113,6 +113,17 @@ def test_oracle_matches_reference_states_large(large_oracle, large_states):
     _check_states(large_oracle, large_states)
 
 
+def test_oracle_matches_reference_states_custom_cookbook(custom_oracle, custom_tables, custom_states):
+    """Another cookbook and hint file (tests/golden/custom/): kind ids in a different order
+    (boundary is 2, water 1), forward references, _yield 2 and 3, input counts of 2 — the table
+    builder and the oracle against 2,000 states exported from the reference running those files."""
+    cb = custom_tables.cookbook
+    assert cb.index["water"] == 1 and cb.index["boundary"] == 2 and cb.index["plank"] == 13
+    assert custom_tables.K == 20 and custom_tables.n_features == 385
+    assert int(custom_states["K"]) == 20 and custom_states["features"].shape[1] == 385
+    _check_states(custom_oracle, custom_states)
+
+
 def test_feature_check_vector(medium_oracle, medium_tables):
     """SURVEY Appendix A.3 check vector (probed on the reference)."""
     cb = medium_tables.cookbook
