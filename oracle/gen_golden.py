@@ -356,8 +356,74 @@ def export_sampler_stats(R, path, n_scen=3000, seed=4242):
     print("wrote", path)
 
 
+class ScriptedStudent(object):
+    """Stands in for students/imitation.py in the reference's own ImitationTrainer.do_rollout:
+    reads the features of every state like the real student (students/imitation.py:72), plays a
+    fixed action script and records what the trainer hands back."""
+
+    def __init__(self, script):
+        self.script = script
+        self.features, self.received = [], []
+
+    def init(self, tasks, states, is_eval):
+        self.t = 0
+
+    def act(self, states):
+        self.features.append(np.stack([s.features() for s in states]))
+        actions = [int(a) for a in self.script[self.t]]
+        self.t += 1
+        return actions
+
+    def receive(self, ref_actions):
+        self.received.append(list(ref_actions))
+
+
+def export_trainer_rollouts(R, splits, path, batch_size=32, seed=77):
+    """Runs the UNMODIFIED trainers/imitation.py:ImitationTrainer.do_rollout (training mode with a
+    behaviour-cloning mix of 0.3, and evaluation mode) on the reference world and teacher and
+    stores everything it produced."""
+    with ref_shim.reference_cwd():
+        from trainers.imitation import ImitationTrainer
+    rng = np.random.RandomState(seed)
+    world, teacher, tm = R.world, R.teacher, R.task_manager
+    K = world.cookbook.n_kinds
+    idx = rng.choice(len(splits["dev_inst_env"]), size=batch_size, replace=False)
+    script = rng.choice(6, size=(64, batch_size), p=[.2, .2, .2, .2, .17, .03]).astype(np.uint8)
+    batch = []
+    for i in idx:
+        ids = splits["dev_grids"][splits["dev_inst_env"][i]].reshape(world.WIDTH, world.HEIGHT)
+        batch.append(dict(grid=to_onehot(ids, K), init_pos=tuple(int(v) for v in splits["dev_inst_pos"][i]),
+                          task=tm.tasks.get(int(splits["dev_inst_task"][i]))))
+    out = dict(inst=idx.astype(np.int32), script=script, mix_rate=np.float64(0.3), mix_seed=np.int64(5))
+    trainer = ImitationTrainer(R.config)
+    trainer.policy_mix_rate = 0.3
+    for mode, is_eval in (("train", False), ("eval", True)):
+        R.config.random = np.random.RandomState(5)
+        student = ScriptedStudent(script)
+        info = trainer.do_rollout(batch, world, student, teacher, is_eval)
+        T = len(student.features)
+        acts = np.full((batch_size, T), 255, np.uint8)
+        for i, seq in enumerate(info["action_seqs"]):
+            acts[i, :len(seq)] = seq
+        out[mode + "_action_seqs"] = acts
+        out[mode + "_success"] = np.asarray([bool(v) for v in info["success"]])
+        out[mode + "_distances"] = np.asarray(info["distances"], np.int32)
+        out[mode + "_num_interactions"] = np.int64(info["num_interactions"])
+        out[mode + "_num_steps"] = np.int64(info["num_steps"])
+        out[mode + "_features"] = np.stack(student.features).astype(np.uint8)
+        if student.received:
+            out[mode + "_ref_actions"] = np.asarray(student.received, np.int16)
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--trainer" in sys.argv:
+        R = ref_shim.Reference()
+        export_trainer_rollouts(R, np.load(os.path.join(OUT, "craft_medium_splits.npz")),
+                                os.path.join(OUT, "trainer_rollouts.npz"))
+        return
     if "--custom" in sys.argv:
         # a non-default cookbook / hint file through the unmodified reference
         cdir = os.path.join(OUT, "custom")

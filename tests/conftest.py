@@ -65,6 +65,12 @@ def custom_oracle(custom_tables):
 
 
 @pytest.fixture(scope="session")
+def trainer_rollouts():
+    """Outputs of the reference's own ImitationTrainer.do_rollout driven by a scripted student."""
+    return np.load(os.path.join(GOLDEN, "trainer_rollouts.npz"))
+
+
+@pytest.fixture(scope="session")
 def light_states():
     return np.load(os.path.join(GOLDEN, "light_states.npz"))
 

@@ -148,3 +148,30 @@ def test_state_api_details(splits, medium_tables):
     with pytest.raises(Exception, match="No such world"):
         cfg.world.name = "NoWorld"
         worlds.load(cfg)
+
+
+def test_facade_under_the_reference_trainer_protocol(splits, trainer_rollouts):
+    """The CUDA-backed CraftWorld / DemonstrationTeacher driven by the trainer's rollout protocol
+    (training mode with a behaviour-cloning mix, and evaluation mode): action sequences, teacher
+    labels, success, distances, counters and every feature vector the student saw are those the
+    reference's own ImitationTrainer.do_rollout produced with the reference world and teacher
+    (tests/golden/trainer_rollouts.npz, oracle/gen_golden.py --trainer)."""
+    import psketch_b200.teachers as teachers
+    import psketch_b200.worlds as worlds
+    from trainer_loop import check_against_fixture
+    cfg = _config()
+    world = worlds.load(cfg)
+    teacher = teachers.load(cfg)
+    K = world.cookbook.n_kinds
+
+    def make_batch(inst):
+        out = []
+        for i in inst:
+            ids = splits["dev_grids"][splits["dev_inst_env"][i]].reshape(8, 8)
+            onehot = np.zeros((8, 8, K))
+            xs, ys = np.nonzero(ids)
+            onehot[xs, ys, ids[xs, ys]] = 1
+            out.append(dict(grid=onehot, init_pos=tuple(int(v) for v in splits["dev_inst_pos"][i]),
+                            task=world.task_manager.by_id(int(splits["dev_inst_task"][i]))))
+        return out
+    check_against_fixture(trainer_rollouts, make_batch, world, teacher)

@@ -42,3 +42,26 @@ def test_port_matches_reference_states(medium_states, medium_tables):
             except TypeError:
                 a = 254
             assert a == S["expert"][i, tid]
+
+
+def test_port_under_the_trainer_protocol(splits, medium_tables, trainer_rollouts):
+    """The Python port (the CPU baseline) driven by the trainer's rollout protocol equals what the
+    reference's own ImitationTrainer.do_rollout produced with the reference world and teacher."""
+    from oracle import craft_ref_port as port
+    from trainer_loop import check_against_fixture
+    world = port.PortWorld(medium_tables)
+    pteacher = port.PortTeacher()
+
+    class Teacher(object):
+        def __call__(self, task, state):
+            return pteacher(task, state)
+
+        def find_closest_resources(self, task, state):
+            return pteacher.closest(task, state)
+
+    def make_batch(inst):
+        tm = medium_tables.task_manager
+        return [dict(grid=world.onehot(splits["dev_grids"][splits["dev_inst_env"][i]]),
+                     init_pos=tuple(int(v) for v in splits["dev_inst_pos"][i]),
+                     task=tm.by_id(int(splits["dev_inst_task"][i]))) for i in inst]
+    check_against_fixture(trainer_rollouts, make_batch, world, Teacher())

@@ -1,0 +1,90 @@
+"""Test helper: the rollout protocol of the reference's trainer (trainers/imitation.py:18-101),
+restated so that it can drive any (world, teacher) pair that has the reference's object API —
+the CUDA-backed facade, or the pure-Python port — with a scripted student.  The expected outputs
+in tests/golden/trainer_rollouts.npz come from the reference's own, unmodified
+``ImitationTrainer.do_rollout`` (oracle/gen_golden.py --trainer)."""
+import numpy as np
+
+STOP = 5
+
+
+class ScriptedStudent(object):
+    def __init__(self, script):
+        self.script = script
+        self.features, self.received = [], []
+        self.t = 0
+
+    def act(self, states):
+        self.features.append(np.stack([np.asarray(s.features()) for s in states]))
+        row = [int(a) for a in self.script[self.t]]
+        self.t += 1
+        return row
+
+
+def run_protocol(batch, world, teacher, student, is_eval, max_timesteps, mix_rate, rng):
+    n = len(batch)
+    tasks = [item["task"] for item in batch]
+    states = [world.init_state(item["grid"], item["init_pos"]) for item in batch]
+    clock = [max_timesteps] * n
+    finished = [False] * n
+    solved = [False] * n
+    taken = [[] for _ in range(n)]
+    interactions = steps = 0
+    clone = None if is_eval else rng.binomial(1, mix_rate, size=n)
+    while not all(finished):
+        chosen = student.act(states)
+        labels = [None] * n
+        for i in range(n):
+            if not is_eval:
+                if finished[i]:
+                    labels[i] = -1
+                else:
+                    labels[i] = teacher(tasks[i], states[i])
+                    interactions += 1
+                if clone[i]:
+                    chosen[i] = labels[i]
+            if not finished[i]:
+                taken[i].append(chosen[i])
+            clock[i] -= 1
+            if chosen[i] == STOP or clock[i] <= 0:
+                finished[i] = True
+            if finished[i]:
+                solved[i] = states[i].satisfies(tasks[i])
+            else:
+                states[i] = states[i].step(chosen[i])[1]
+                steps += 0 if is_eval else 1
+        if not is_eval:
+            student.received.append(labels)
+    gaps = []
+    for i in range(n):
+        if tasks[i].goal_name != "get":
+            continue
+        if solved[i]:
+            gaps.append(0)
+        else:
+            probe = world.init_state(batch[i]["grid"], states[i].pos, states[i].dir)
+            gaps.append(len(teacher.find_closest_resources(tasks[i], probe)[1]))
+    return dict(action_seqs=taken, success=solved, distances=gaps, num_interactions=interactions,
+                num_steps=steps)
+
+
+def check_against_fixture(fx, make_batch, world, teacher):
+    """``make_batch(instance_ids) -> list of dict(grid, init_pos, task)`` for the given world."""
+    batch = make_batch(fx["inst"])
+    for mode, is_eval in (("train", False), ("eval", True)):
+        student = ScriptedStudent(fx["script"])
+        rng = np.random.RandomState(int(fx["mix_seed"]))
+        got = run_protocol(batch, world, teacher, student, is_eval, 40, float(fx["mix_rate"]), rng)
+        want = fx[mode + "_action_seqs"]
+        for i, seq in enumerate(got["action_seqs"]):
+            L = int((want[i] != 255).sum())
+            assert seq == want[i, :L].tolist(), (mode, i)
+        assert [bool(v) for v in got["success"]] == fx[mode + "_success"].tolist(), mode
+        assert got["distances"] == fx[mode + "_distances"].tolist(), mode
+        assert got["num_interactions"] == int(fx[mode + "_num_interactions"]), mode
+        assert got["num_steps"] == int(fx[mode + "_num_steps"]), mode
+        feats = np.stack(student.features)
+        assert feats.dtype == np.float64
+        assert np.array_equal(feats, fx[mode + "_features"].astype(np.float64)), mode
+        if not is_eval:
+            assert np.array_equal(np.asarray(student.received, np.int16), fx["train_ref_actions"])
