@@ -441,8 +441,8 @@ def run_ours(args):
                             "peak": peak, "unit": "GB/s", "frac": k["frac"], "traffic": None,
                             "peak_source": peak_src, "algorithmic_bytes_per_env_step": BYTES_FEATURES}
     line["kernels"] = kern
-    # ---- CPU baselines on this box's host cores (bounded samples)
-    if not args.no_cpu:
+    # ---- CPU baselines on this box's host cores (bounded samples; single-GPU runs only)
+    if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_python_port(budget_s=12.0)[0]
         try:
             line["cpu_baseline_native"] = cpu_native_oracle()
