@@ -216,17 +216,20 @@ def run_ours(args):
                                   max_timesteps=40, device=dev)
     nf = env.n_features
     feat_bytes = n * nf * 4
-    ring = max(2, int(np.ceil(1.5 * 126e6 / feat_bytes)) + 1)     # ring of outputs > L2 (126 MB)
-    ring = min(ring, 64)
-    feats = [torch.empty((n, nf), dtype=torch.float32, device=dev) for _ in range(ring)]
-    outs = [dict() for _ in range(ring)]
     fused = not args.unfused
-
     rand_act = torch.empty(n, dtype=torch.uint8, device=dev) if args.policy == "random" else None
     # Teacher-driven rollouts need nothing from outside the kernel, so T ticks run per launch
     # (psk_craft_rollout: state stays in shared memory between ticks).  T = 1, the random policy
     # and --unfused use one psk_craft_tick launch per step.
     T = max(1, args.ticks_per_launch) if (fused and rand_act is None) else 1
+    # Ring of output frames: larger than L2 (126 MB), and at least T + 1 frames so that no frame is
+    # written twice within one launch — a CTA that came back to the same lines a few ticks later
+    # would find them still dirty in L2, the writes would merge there and never reach HBM, and the
+    # "bandwidth" would exceed what HBM can do (seen: 8.3 TB/s with a ring of 2 at 1 M envs).
+    ring = max(2, int(np.ceil(1.5 * 126e6 / feat_bytes)) + 1, T + 1 if T > 1 else 0)
+    ring = min(ring, 64)
+    feats = [torch.empty((n, nf), dtype=torch.float32, device=dev) for _ in range(ring)]
+    outs = [dict() for _ in range(ring)]
     feat_ring = torch.stack(feats) if T > 1 else None
     if T > 1:
         feats = [feat_ring[i] for i in range(ring)]

@@ -1447,11 +1447,11 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
 // teacher-driven rollouts (action_in == NULL) or replay of given action sequences.
 //   action_in   u8[ticks][n] or NULL;  expert_out u8[ticks][n];  done_out/success_out u8[ticks][n] or NULL
 //   features_out f32[feat_ring][n][nf] or NULL: tick t writes slot t % feat_ring
-// 65,536 envs = 1,024 CTAs of 128 threads = 6.92 per SM: all of them must be resident at once
-// (a second wave of long-lived multi-tick CTAs would run at a fraction of the occupancy), hence
-// the register cap of 7 CTAs per SM.
+// Register cap: 896 threads per SM at 72 registers, i.e. 7 CTAs of 64 + 2 warps (128 threads) or
+// 9 CTAs of 32 + 2 warps (96 threads); one register more and a CTA less fits per SM (17.5 -> 21 us
+// per tick at 65,536 envs when a change pushed the kernel to 80 registers).
 template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA>
-__global__ void __launch_bounds__(NE + NFW * 32, (NE + NFW * 32) <= 128 ? 7 : 1)
+__global__ void __launch_bounds__(NE + NFW * 32, (NE + NFW * 32) <= 128 ? 896 / (NE + NFW * 32) : 1)
 craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                      uint8_t *__restrict__ agent, const uint8_t *__restrict__ action_in,
                      const uint8_t *__restrict__ scen_grid, const int32_t *__restrict__ scen_idx,
@@ -1859,17 +1859,29 @@ template <int W, int H, int WIN> struct Config {
         if constexpr (!BITBOARD || WIN != 3) {
             return PSK_ERR_UNSUPPORTED;
         } else {
-            static int env_tma = -2;
+            // CTA shape and store path by batch size (bench.py sweeps, profiles/README.md):
+            //   < 65,536 envs   64 env threads + 2 feature warps, one wave of CTAs, vector stores;
+            //   65,536 and up   32 env threads + 2 feature warps (96 threads, 9 CTAs per SM): at
+            //                   65,536 envs that is 2,048 CTAs on 1,332 slots, so CTAs that finish
+            //                   early are replaced instead of leaving their SM idle (16.75 vs
+            //                   17.66 us per tick); vector stores up to 196,608 envs, TMA above.
+            // PSK_ROLLOUT_VARIANT (0 / 2) and PSK_ROLLOUT_TMA (0 / 1) override for experiments.
+            static int env_tma = -2, env_variant = -2;
             if (env_tma == -2) {
                 const char *m = getenv("PSK_ROLLOUT_TMA");
                 env_tma = m ? atoi(m) : -1;
+                m = getenv("PSK_ROLLOUT_VARIANT");
+                env_variant = m ? atoi(m) : -1;
             }
-            // one wave of CTAs (<= 65,536 envs): vector stores; more: TMA stores (sweep in profiles/README.md)
-            const int tma = env_tma >= 0 ? env_tma : (s.n > 65536 ? 1 : 0);
-            return tma ? rollout_variant<64, 2, true>(t, s, ep, ticks, action_in, features_out, feat_ring,
-                                                      expert_out, done, success, stats, err, st)
-                       : rollout_variant<64, 2, false>(t, s, ep, ticks, action_in, features_out, feat_ring,
-                                                       expert_out, done, success, stats, err, st);
+            const int tma = env_tma >= 0 ? env_tma : (s.n > 196608 ? 1 : 0);
+            const int variant = env_variant >= 0 ? env_variant : (s.n >= 65536 ? 2 : 0);
+#define PSK_ROLLOUT_ARGS t, s, ep, ticks, action_in, features_out, feat_ring, expert_out, done, success, stats, err, st
+            if (variant == 2)
+                return tma ? rollout_variant<32, 2, true>(PSK_ROLLOUT_ARGS)
+                           : rollout_variant<32, 2, false>(PSK_ROLLOUT_ARGS);
+            return tma ? rollout_variant<64, 2, true>(PSK_ROLLOUT_ARGS)
+                       : rollout_variant<64, 2, false>(PSK_ROLLOUT_ARGS);
+#undef PSK_ROLLOUT_ARGS
         }
     }
     static int tick_fused(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
