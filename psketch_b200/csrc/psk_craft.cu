@@ -1891,9 +1891,10 @@ template <int W, int H, int WIN> struct Config {
         if constexpr (!BITBOARD) {
             return PSK_ERR_UNSUPPORTED;   // psk_craft_tick falls back to the three-kernel pipeline
         } else {
-        // Defaults from the sweep in profiles/README.md: small batches are latency-bound and
-        // prefer big CTAs with plain vector stores; large batches prefer many small CTAs whose
-        // feature warps stream through the TMA.  PSK_TICK_VARIANT / PSK_TICK_TMA override.
+        // Defaults from the sweeps in profiles/README.md: 32 env threads + 2 feature warps at
+        // every batch size measured (65,536: 20.4 vs 20.9 us for 64 + 2; 262,144: 71.2 vs 72.9),
+        // vector stores up to 262,144 envs, TMA stores above (1 M: 294 vs 318 us).
+        // PSK_TICK_VARIANT / PSK_TICK_TMA override.
         static int env_variant = -2, env_tma = -2;
         if (env_variant == -2) {
             const char *v = getenv("PSK_TICK_VARIANT");
@@ -1902,7 +1903,7 @@ template <int W, int H, int WIN> struct Config {
             env_tma = m ? atoi(m) : -1;
         }
         const bool big = s.n > 262144;
-        const int variant = env_variant >= 0 ? env_variant : (big ? 4 : 0);
+        const int variant = env_variant >= 0 ? env_variant : 4;
         const int tma = env_tma >= 0 ? env_tma : (big ? 1 : 0);
 #define PSK_TV(NE, NFW)                                                                          \
     return tma ? tick_variant<NE, NFW, true>(t, s, ep, action_in, features_out, expert_out, done, \
