@@ -92,6 +92,13 @@ def test_generated_dataset_is_solvable_and_round_trips(medium_tables, tmp_path):
     for k in np.unique(key)[:50]:
         p = packed["inst_pos"][key == k]
         assert len({tuple(q) for q in p}) == 20
+    # the recorded ref_actions are what the (reference-pinned) CPU oracle's teacher does on the
+    # generated scenarios, step by step, and every trajectory ends satisfied (make_data.py:146-152)
+    from oracle.craft_oracle import CraftOracle
+    from test_oracle import _replay
+    pad = np.where(ref == 255, 5, ref).astype(np.int32)
+    assert _replay(CraftOracle(medium_tables), packed["grids"], packed["inst_env"], packed["inst_task"],
+                   packed["inst_pos"], pad, ln) == 0
     # wire format round trip (data/dataset.py:39-67)
     path = str(tmp_path / "craft_medium_gen.json")
     data.save_json(path, packed, medium_tables)
