@@ -26,8 +26,32 @@ def init_from_env(backend=None):
         if backend == "nccl":
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
+            if os.environ.get("PSK_BIND_CPUS", "1") != "0":
+                bind_to_gpu_cpus(local)
         dist.init_process_group(backend, rank=rank, world_size=world, **kw)
     return rank, world, local
+
+
+def bind_to_gpu_cpus(device_index):
+    """Restricts this process to the CPUs that NVML reports as local to its GPU (same NUMA node /
+    PCIe root), so that pinned host buffers allocated afterwards — the host-buffer path moves
+    112 MB per step and GPU through them — land in memory next to the GPU instead of behind the
+    socket interconnect.  Best effort: returns the CPU list, or None when NVML / the affinity call
+    is unavailable or the box exposes a single node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpus = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed or len(allowed) == len(os.sched_getaffinity(0)):
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def shard_range(n_total, rank, world):
