@@ -41,7 +41,12 @@ def bind_to_gpu_cpus(device_index):
     try:
         import pynvml
         pynvml.nvmlInit()
-        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        try:        # CUDA and NVML may number the devices differently (CUDA_VISIBLE_DEVICES)
+            pr = torch.cuda.get_device_properties(int(device_index))
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:  # noqa: BLE001
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
         n_cpus = os.cpu_count() or 1
         words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
         cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
