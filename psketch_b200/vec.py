@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .tables import CraftTables, STOP
+from .tables import CraftTables
 
 
 def _ptr(t):

@@ -4,7 +4,6 @@ import os
 import sys
 
 import numpy as np
-import pytest
 import torch
 import torch.multiprocessing as mp
 
