@@ -191,6 +191,56 @@ def time_kernel(fn, torch, inner=10, reps=20):
     return s.elapsed_time(e) * 1e-3 / (reps * inner)
 
 
+# Port-vs-reference calibration of the CPU arm, measured in the build container (the unmodified
+# reference cannot travel to the GPU box): same 660 dev instances, one core, unmodified reference
+# 5,117 env-steps/s vs oracle/craft_ref_port.py 6,993 — the port is 1.37x FASTER, so every ratio
+# against the port understates the ratio against the reference by that factor.
+PORT_VS_REFERENCE = {"factor": 1.37, "reference_env_steps_per_s_per_core": 5117,
+                     "port_env_steps_per_s_per_core": 6993,
+                     "how": "build container, one core, 660 dev instances, unmodified /root/reference "
+                            "(oracle/ref_shim.py) vs oracle/craft_ref_port.py; VERDICT r1 item 10"}
+
+
+def oracle_parity_sample(env, tables, wl_arrays, snap, out, feat_ring, ticks, first_slot, sample):
+    """Bit-exact check of one launch against the CPU oracle on a strided sample of envs: the oracle
+    starts from the sampled envs' state before the launch (``snap``) and is advanced tick by tick;
+    teacher action of every tick, every feature frame still in the ring, and the final state."""
+    import torch
+    from oracle.craft_oracle import CraftOracle
+    o = CraftOracle(tables)
+    grids, ienv, ipos, itask = wl_arrays
+    ds = torch.from_numpy(sample).to(env.device)
+    g0, a0 = snap[0][ds].cpu().numpy(), snap[1][ds].cpu().numpy()
+    C, K = env.C, env.K
+    state = dict(grid=np.ascontiguousarray(g0[:, :C]), inv=a0[:, :K].astype(np.int32),
+                 pos=a0[:, 24:26].astype(np.int32), dir=a0[:, 26].astype(np.int32),
+                 timer=a0[:, 28].astype(np.int32))
+    init_grid = np.ascontiguousarray(grids[ienv[sample].astype(np.int64)])
+    init_pos, task = ipos[sample].astype(np.int32), itask[sample].astype(np.int32)
+    ring = feat_ring.shape[0]
+    frames = 0
+    for t in range(ticks):
+        state, _, f, a = o.rollout(1, env.max_timesteps, init_grid, init_pos, task, state=state,
+                                   want_features=True)
+        got = out["expert"][t][ds].cpu().numpy().astype(np.int32)
+        if not np.array_equal(got, a):
+            raise AssertionError("parity: teacher action differs from the oracle at tick %d" % t)
+        if t >= ticks - ring:                       # frame not overwritten later in the launch
+            if not np.array_equal(feat_ring[(first_slot + t) % ring][ds].cpu().numpy(), f):
+                raise AssertionError("parity: features differ from the oracle at tick %d" % t)
+            frames += 1
+    fin = env.agent[ds].cpu().numpy()
+    ok = (np.array_equal(env.cells[ds].cpu().numpy(), state["grid"]) and
+          np.array_equal(fin[:, :K].astype(np.int32), state["inv"]) and
+          np.array_equal(fin[:, 24:26].astype(np.int32), state["pos"]) and
+          np.array_equal(fin[:, 26].astype(np.int32), state["dir"]) and
+          np.array_equal(fin[:, 28].astype(np.int32), state["timer"]))
+    if not ok:
+        raise AssertionError("parity: final state differs from the oracle")
+    return {"sample_envs": int(len(sample)), "ticks": int(ticks), "feature_frames": frames,
+            "against": "oracle/craft_oracle.c, advanced tick by tick from the pre-launch state"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -211,9 +261,9 @@ def run_ours(args):
     wl = load_workload(n)
     # each rank owns its own slice of the batch: rotate the instance tiling by rank
     shift = (rank * n) % wl["n_instances"]
-    env = VecCraft.from_instances(tables, wl["grids"], np.roll(wl["env"], -shift),
-                                  np.roll(wl["pos"], -shift, axis=0), np.roll(wl["task"], -shift),
-                                  max_timesteps=40, device=dev)
+    wl_arrays = (wl["grids"], np.roll(wl["env"], -shift), np.roll(wl["pos"], -shift, axis=0),
+                 np.roll(wl["task"], -shift))
+    env = VecCraft.from_instances(tables, *wl_arrays, max_timesteps=40, device=dev)
     nf = env.n_features
     feat_bytes = n * nf * 4
     fused = not args.unfused
@@ -228,12 +278,9 @@ def run_ours(args):
     # "bandwidth" would exceed what HBM can do (seen: 8.3 TB/s with a ring of 2 at 1 M envs).
     ring = max(2, int(np.ceil(1.5 * 126e6 / feat_bytes)) + 1, T + 1 if T > 1 else 0)
     ring = min(ring, 64)
-    feats = [torch.empty((n, nf), dtype=torch.float32, device=dev) for _ in range(ring)]
+    feat_ring = torch.empty((ring, n, nf), dtype=torch.float32, device=dev)
+    feats = [feat_ring[i] for i in range(ring)]
     outs = [dict() for _ in range(ring)]
-    feat_ring = torch.stack(feats) if T > 1 else None
-    if T > 1:
-        feats = [feat_ring[i] for i in range(ring)]
-    rout = {}
 
     def tick(i):
         if rand_act is not None:        # off-policy variant: U{0..5} actions from Philox(123, (env, t))
@@ -243,6 +290,8 @@ def run_ours(args):
     routs = {}
 
     def launch_rollout(ticks=None):
+        # tick t of a launch writes ring slot t % ring: nothing is written twice within a launch,
+        # and between two launches' writes to the same line >= 850 MB pass through the 126 MB L2
         ticks = ticks or T
         env.rollout(ticks, features_out=feat_ring, out=routs.setdefault(ticks, {}), want_flags=True)
 
@@ -254,6 +303,9 @@ def run_ours(args):
     per_tick_launches = (1 if fused else 3) + (1 if rand_act is not None else 0)
     launches = [0]
     graphs = {}
+
+    def plan_for(r):
+        return ([T] * (r // T) + ([r % T] if r % T else [])) if T > 1 else list(range(r))
 
     def capture(plan):
         """CUDA graph of a list of launches; plan entries are tick counts (T > 1) or tick indices."""
@@ -273,12 +325,9 @@ def run_ours(args):
         torch.cuda.current_stream().wait_stream(side)
         return g
 
-    # main graph: a fixed number of full launches; tail graphs: the exact remainder of a request
-    per_graph = ring if T == 1 else 4
-    chunk = per_graph * T
-
-    def plan_for(r):
-        return ([T] * (r // T) + ([r % T] if r % T else [])) if T > 1 else list(range(r))
+    # A request of k ticks = (k // chunk) replays of the main graph (4 full launches, or one ring
+    # of single ticks) + one tail graph with the exact remainder.
+    chunk = (ring if T == 1 else 4) * T
 
     def prepare(k):
         if args.no_graph:
@@ -301,9 +350,14 @@ def run_ours(args):
                 done += T
                 launches[0] += 1
             while done < k:
-                tick(done)
-                done += 1
-                launches[0] += per_tick_launches
+                if T > 1:
+                    launch_rollout(k - done)
+                    launches[0] += 1
+                    done = k
+                else:
+                    tick(done)
+                    done += 1
+                    launches[0] += per_tick_launches
             return
         prepare(k)
         for _ in range(k // chunk):
@@ -320,29 +374,52 @@ def run_ours(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     run_steps(max(W, 3))
+    run_steps(K)                                    # one untimed pass of the K-step plan: graph upload
+    torch.cuda.synchronize()
+    # ---- how many times the K-step plan is repeated so that the timed region lasts >= 50 ms
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    run_steps(K)
+    s1.record()
+    torch.cuda.synchronize()
+    est = torch.tensor([s0.elapsed_time(s1) * 1e-3], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(est, op=dist.ReduceOp.MIN)          # same R on every rank
+    R = int(min(4000, max(1, np.ceil(args.min_seconds / max(float(est.item()), 1e-7)))))
+    if args.repeats > 0:
+        R = args.repeats
     env.stats.zero_()
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
     torch.cuda.synchronize()
     t0 = time.time()
     launches[0] = 0
-    start.record()
-    run_steps(K)
-    end.record()
+    marks[0].record()
+    for r in range(R):                              # exactly K steps per repeat, events in between
+        run_steps(K)
+        marks[r + 1].record()
     timed_launches = launches[0]
     torch.cuda.synchronize()
     t1 = time.time()
     if distributed:
         dist.barrier()
-    elapsed = start.elapsed_time(end) * 1e-3
-    el = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+    per_rep = torch.tensor([marks[r].elapsed_time(marks[r + 1]) * 1e-3 for r in range(R)],
+                           dtype=torch.float64, device=dev)
+    total = torch.tensor([marks[0].elapsed_time(marks[R]) * 1e-3], dtype=torch.float64, device=dev)
     stats = env.stats.clone()
     if distributed:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rep, op=dist.ReduceOp.MAX)      # MAX over ranks, repeat by repeat
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar0.record()
     pdist.allreduce_stats(stats)                            # the path's only collective (NCCL)
-    elapsed = float(el.item())
+    ar1.record()
+    torch.cuda.synchronize()
+    stats_allreduce_us = ar0.elapsed_time(ar1) * 1e3
+    elapsed = float(per_rep.median().item())                # seconds per K steps (median of R)
+    total_s = float(total.item())
     clocks = None
     if sampler:
         t1c, window = t1, "timed region"
@@ -356,20 +433,37 @@ def run_ours(args):
             t1c, window = time.time(), "timed region + 0.8 s untimed continuation of the same step"
         clocks = sampler.stop(t0, t1c)
         clocks["window"] = window
-    stats_after = None
     env.check_errors()
     total_steps = n * K * world
     value = total_steps / elapsed
     st = stats.cpu().numpy()
-    assert int(st[2]) == total_steps, "kernel step counter disagrees with the host's"
+    assert int(st[2]) == total_steps * R, "kernel step counter disagrees with the host's"
+
+    # ---- parity of the timed kernel: one more replay of the SAME K-step plan, the last launch of
+    # it checked against the CPU oracle on a strided sample (untimed)
+    parity = None
+    if not args.no_parity and T > 1 and rand_act is None:
+        torch.cuda.synchronize()
+        plan = plan_for(K)
+        if len(plan) > 1:
+            run_steps(K - plan[-1])                 # everything but the last launch
+        snap = env.snapshot()
+        torch.cuda.synchronize()
+        launch_rollout(plan[-1])                    # same entry point, arguments and dispatch as the graph node
+        torch.cuda.synchronize()
+        sample = np.unique(np.concatenate([np.arange(0, n, max(1, n // 2048)), np.arange(max(0, n - 64), n)]))
+        parity = oracle_parity_sample(env, tables, wl_arrays, snap, routs[plan[-1]], feat_ring,
+                                      plan[-1], 0, sample)
+        parity["launch"] = "psk_craft_rollout(ticks=%d) on %d envs, same dispatch as the timed launches" % (plan[-1], n)
+        env.check_errors()
 
     # ---- end to end through the public API with host buffers (rank-local, then aggregated)
-    e2e = measure_e2e(torch, tables, wl, n, dev, args)
-    if distributed:
-        ev = torch.tensor([e2e["elapsed"]], dtype=torch.float64, device=dev)
-        dist.all_reduce(ev, op=dist.ReduceOp.MAX)
-        e2e["elapsed"] = float(ev.item())
-    e2e_value = n * e2e["steps"] * world / e2e["elapsed"]
+    e2e = measure_e2e(torch, dist if distributed else None, tables, wl, n, dev, args, world)
+
+    # ---- BASELINE config 3 (8 M envs over the ranks): world > 1 only
+    config3 = None
+    if distributed and not args.no_config3:
+        config3 = measure_config3(torch, dist, pdist, tables, rank, world, dev, args)
 
     if rank != 0:
         if distributed:
@@ -377,10 +471,11 @@ def run_ours(args):
         return
 
     peak, peak_src = measured_peaks()
-    per_launch_s = elapsed / K          # seconds per tick (= per step)
+    per_tick_s = elapsed / K             # seconds per tick (= per step)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": per_launch_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "repeats": R, "timed_region_ms": total_s * 1e3,
+        "ms_per_step": per_tick_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {
             "workload": "craft_medium train tasks (17,600 instances tiled), %d parallel envs per GPU, "
@@ -389,19 +484,26 @@ def run_ours(args):
             "kernel": ("craft_rollout_kernel (fused tick, %d ticks per launch)" % T if T > 1 else
                        "craft_tick_kernel (fused, warp-specialised)") if fused else "expert+features+advance",
             "cuda_graph": graph is not None,
-            "l2": "feature outputs rotate through a ring of %d buffers (%.0f MB > 126 MB L2)"
-                  % (ring, ring * feat_bytes / 1e6),
+            "timing": "the K-step plan is replayed `repeats` times back to back with CUDA events in "
+                      "between (one untimed replay first); value = envs x K / median per-K time, MAX over "
+                      "ranks per repeat; timed_region_ms is the whole window",
+            "l2": "feature outputs rotate through a ring of %d frames (%.0f MB > 126 MB L2), every "
+                  "launch continuing where the previous one stopped" % (ring, ring * feat_bytes / 1e6),
         },
         "clocks": clocks,
-        "gpu_launches": timed_launches,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
-                "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"], "how": e2e["how"]},
+        "gpu_launches": timed_launches // R,
+        "gpu_launches_timed_region": timed_launches,
+        "parity_checked": parity is not None, "parity": parity,
+        "stats_allreduce_us": stats_allreduce_us if distributed else None,
+        "e2e": e2e["headline"], "e2e_variants": e2e["variants"],
         "episodes": int(st[0]), "successes": int(st[1]),
     }
+    if config3 is not None:
+        line["config3"] = config3
     # ---- roofline of the dominant kernel
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         tr = tr["craft_rollout_kernel" if T > 1 else "craft_tick_kernel"]
         if tr["n_envs"] == n and tr.get("ticks_per_launch", 1) == T:
             traffic = tr["dram_bytes_per_launch"]
@@ -410,8 +512,8 @@ def run_ours(args):
     if fused:
         # per env: T x (404 f32 features + action + done + success) + one state read and write
         bytes_per_tick = BYTES_FUSED if T == 1 else (1616 + 3) + (2 * 96 + 4) / T
-        launch_s = elapsed / max(1, timed_launches)
-        ticks_per_launch_eff = K / max(1, timed_launches)
+        launch_s = elapsed * R / max(1, timed_launches)
+        ticks_per_launch_eff = K * R / max(1, timed_launches)
         achieved = bytes_per_tick * ticks_per_launch_eff * n / launch_s / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": "craft_rollout_kernel" if T > 1 else "craft_tick_kernel",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -419,34 +521,30 @@ def run_ours(args):
                             "algorithmic_bytes_per_env_step": bytes_per_tick,
                             "launch_us": launch_s * 1e6, "ticks_per_launch": ticks_per_launch_eff}
     # per-kernel numbers (north star: step and features as a fraction of the HBM roofline)
-    kern = {}
-    act = env.expert()
-    big = [torch.empty((n, nf), dtype=torch.float32, device=dev) for _ in range(min(ring, 8))]
-    cnt = [0]
-
-    def f_feat(impl):
-        def g():
-            env.features(out=big[cnt[0] % len(big)], impl=impl)
-            cnt[0] += 1
-        return g
-
-    snap = env.snapshot()
-    for name, fn, b in (("features_tma", f_feat(2), BYTES_FEATURES), ("features_plain", f_feat(1), BYTES_FEATURES),
-                        ("expert", lambda: env.expert(out=act), BYTES_EXPERT),
-                        ("step", lambda: env.step(act), BYTES_STEP)):
-        dt = time_kernel(fn, torch, inner=len(big) if name.startswith("features") else 10)
-        kern[name] = {"us": dt * 1e6, "GBps": b * n / dt / 1e9, "frac": b * n / dt / 1e9 / peak,
-                      "env_per_s": n / dt}
-    env.restore(snap)
+    line["kernels"] = per_kernel_table(torch, env, n, nf, dev, peak, min(ring, 8))
     if not fused:
-        k = kern["features_tma"]
+        k = line["kernels"]["features_tma"]
         line["roofline"] = {"bound": "hbm", "kernel": "craft_features_kernel", "achieved": k["GBps"],
                             "peak": peak, "unit": "GB/s", "frac": k["frac"], "traffic": None,
                             "peak_source": peak_src, "algorithmic_bytes_per_env_step": BYTES_FEATURES}
-    line["kernels"] = kern
+    line["single_tick"] = dict(line["kernels"].pop("tick_fused"), kernel="craft_tick_kernel (one tick per "
+                               "launch: the student-in-the-loop path)", algorithmic_bytes_per_env_step=BYTES_FUSED)
+    del env, feat_ring, feats
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_1m:
+        n1 = 1 << 20
+        w1 = load_workload(n1)
+        env1 = VecCraft.from_instances(tables, w1["grids"], w1["env"], w1["pos"], w1["task"],
+                                       max_timesteps=40, device=dev)
+        k1 = per_kernel_table(torch, env1, n1, nf, dev, peak, 3)
+        k1["tick"] = k1.pop("tick_fused")
+        k1["n_envs"] = n1
+        line["kernels_1m"] = k1
+        del env1
+        torch.cuda.empty_cache()
     # ---- CPU baselines on this box's host cores (bounded samples; single-GPU runs only)
     if not args.no_cpu and world == 1:
-        line["cpu_baseline"] = cpu_python_port(budget_s=12.0)[0]
+        line["cpu_baseline"] = dict(cpu_python_port(budget_s=12.0)[0], port_vs_reference=PORT_VS_REFERENCE)
         try:
             line["cpu_baseline_native"] = cpu_native_oracle()
         except Exception as ex:  # noqa: BLE001
@@ -456,32 +554,155 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def measure_e2e(torch, tables, wl, n, dev, args):
-    """Same tick through the reference-facing C ABI with HOST buffers (psk_craft_host_tick):
-    every step copies the states in from pinned host memory, runs the fused tick, and reads
-    features, teacher actions, done/success and the new states back to pinned host memory."""
+def per_kernel_table(torch, env, n, nf, dev, peak, n_bufs):
+    """Stand-alone kernels of the path at this batch size (CUDA-graph-timed, outputs rotating over
+    n_bufs frames): µs per launch, GB/s on the algorithmic bytes, fraction of the measured peak."""
+    kern = {}
+    act = env.expert()
+    big = [torch.empty((n, nf), dtype=torch.float32, device=dev) for _ in range(n_bufs)]
+    cnt = [0]
+    tout = {}
+
+    def f_feat(impl):
+        def g():
+            env.features(out=big[cnt[0] % len(big)], impl=impl)
+            cnt[0] += 1
+        return g
+
+    def f_tick():
+        env.tick(features_out=big[cnt[0] % len(big)], fused=True, out=tout)
+        cnt[0] += 1
+
+    snap = env.snapshot()
+    for name, fn, b in (("features_tma", f_feat(2), BYTES_FEATURES), ("features_plain", f_feat(1), BYTES_FEATURES),
+                        ("expert", lambda: env.expert(out=act), BYTES_EXPERT),
+                        ("step", lambda: env.step(act), BYTES_STEP),
+                        ("tick_fused", f_tick, BYTES_FUSED)):
+        dt = time_kernel(fn, torch, inner=len(big) if name != "expert" and name != "step" else 10)
+        kern[name] = {"us": dt * 1e6, "GBps": b * n / dt / 1e9, "frac": b * n / dt / 1e9 / peak,
+                      "env_per_s": n / dt}
+    env.restore(snap)
+    del big
+    return kern
+
+
+def measure_config3(torch, dist, pdist, tables, rank, world, dev, args):
+    """BASELINE configs[2]: 8,388,608 envs sharded over the ranks (contiguous slices), T ticks per
+    launch, one NCCL all-reduce of the episode statistics per 40-tick rollout."""
+    from psketch_b200.vec import VecCraft
+    total = 1 << 23
+    n = total // world
+    wl = load_workload(n)
+    shift = (rank * n) % wl["n_instances"]
+    env = VecCraft.from_instances(tables, wl["grids"], np.roll(wl["env"], -shift),
+                                  np.roll(wl["pos"], -shift, axis=0), np.roll(wl["task"], -shift),
+                                  max_timesteps=40, device=dev)
+    nf = env.n_features
+    T = max(1, args.ticks_per_launch)
+    ring = T + 1
+    feat_ring = torch.empty((ring, n, nf), dtype=torch.float32, device=dev)
+    out = {}
+
+    def launch():
+        env.rollout(T, features_out=feat_ring, out=out, want_flags=True)
+
+    per_rollout = 40 // T                           # launches per 40-tick rollout
+    for _ in range(2):
+        launch()
+    env.stats.zero_()
+    torch.cuda.synchronize()
+    dist.barrier()
+    rounds = 3
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ar_ms = []
+    s.record()
+    for _ in range(rounds):
+        for _ in range(per_rollout):
+            launch()
+        st = env.stats.clone()
+        a0.record()
+        pdist.allreduce_stats(st)                   # NCCL SUM of {episodes, successes, env_steps}
+        a1.record()
+        a1.synchronize()
+        ar_ms.append(a0.elapsed_time(a1))
+    e.record()
+    torch.cuda.synchronize()
+    el = torch.tensor([s.elapsed_time(e) * 1e-3], dtype=torch.float64, device=dev)
+    dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    env.check_errors()
+    steps = rounds * per_rollout * T
+    peak, _ = measured_peaks()
+    bytes_per_tick = (1616 + 3) + (2 * 96 + 4) / T
+    value = total * steps / float(el.item())
+    res = {"workload": "BASELINE configs[2]: craft_medium, 8,388,608 envs sharded over %d GPUs (%d per GPU), "
+                       "%d ticks per launch, NCCL all-reduce of the statistics every 40 ticks" % (world, n, T),
+           "value": value, "unit": UNIT, "envs_total": total, "envs_per_gpu": n, "steps": steps,
+           "ms_per_step": float(el.item()) / steps * 1e3,
+           "roofline_frac_per_gpu": bytes_per_tick * n * steps / float(el.item()) / 1e9 / peak,
+           "stats_allreduce_ms": ar_ms, "env_steps_counted": int(st[2])}
+    del env, feat_ring
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
+    """The same tick through the reference-facing C ABI with HOST buffers, copies inside the timed
+    region, MAX over ranks.  Three forms, all checked against the step counter:
+      resident_f32 (headline)  psk_craft_host_tick_resident: environments stay in HBM; per step the
+                               f32[n,404] frame + teacher actions + done/success come down
+      roundtrip_f32            psk_craft_host_tick: additionally the states go up and come back
+      resident_u8              the compact u8[n,404] frame instead of f32 (opt-in format)
+    plus pcie_ceiling: a plain pinned D2H copy of the f32 frame's bytes, all ranks concurrently."""
     from psketch_b200.host import HostCraft
     env = HostCraft(tables, wl["grids"], wl["env"], wl["pos"], wl["task"], max_timesteps=40,
                     chunk_envs=args.e2e_chunk)
     steps = max(3, min(args.steps, 30))
-    for _ in range(3):
-        env.tick()
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    s.record()
-    for _ in range(steps):
-        env.tick()                      # returns after the D2H copies have landed
-    e.record()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    assert int(env.stats[2]) == (steps + 3) * n
-    res = {"elapsed": max(s.elapsed_time(e) * 1e-3, wall), "steps": steps, "h2d": env.h2d_bytes,
-           "d2h": env.d2h_bytes,
-           "how": "psk_craft_host_tick (C ABI, pinned host numpy buffers): per step H2D states, fused "
-                  "tick, D2H features+actions+flags+states in %d-env chunks over 3 streams" % args.e2e_chunk}
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()                        # returns after the D2H copies have landed
+        wall = time.perf_counter() - t0
+        if dist is not None:
+            w = torch.tensor([wall], dtype=torch.float64, device=dev)
+            dist.all_reduce(w, op=dist.ReduceOp.MAX)
+            wall = float(w.item())
+        return wall
+
+    variants = {}
+    before = int(env.stats[2])
+    wall = timed(env.tick, steps)
+    assert int(env.stats[2]) - before == (steps + 3) * n
+    variants["roundtrip_f32"] = {"value": n * steps * world / wall, "unit": UNIT,
+                                 "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
+    env.reset_resident()
+    for name, fmt in (("resident_f32", "f32"), ("resident_u8", "u8")):
+        before = int(env.stats[2])
+        wall = timed(lambda: env.tick_resident(features=fmt), steps)
+        assert int(env.stats[2]) - before == (steps + 3) * n
+        variants[name] = {"value": n * steps * world / wall, "unit": UNIT,
+                          "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
+    # PCIe ceiling for the f32 frame: the same bytes, pinned, nothing else
+    frame = torch.empty((n, env.n_features), dtype=torch.float32, device=dev)
+    host = torch.empty((n, env.n_features), dtype=torch.float32, pin_memory=True)
+    wall = timed(lambda: (host.copy_(frame, non_blocking=True), torch.cuda.synchronize()), steps)
+    gbs = frame.numel() * 4 * steps / wall / 1e9
+    ceiling = {"d2h_GBps_per_gpu": gbs, "env_steps_per_s": n * steps * world / wall,
+               "how": "pinned cudaMemcpy D2H of one f32[%d,%d] frame per step, all %d ranks at once" % (n, env.n_features, world)}
+    head = dict(variants["resident_f32"])
+    head.update({"steps": steps, "pcie_ceiling": ceiling,
+                 "frac_of_pcie_ceiling": head["value"] / ceiling["env_steps_per_s"],
+                 "how": "psk_craft_host_tick_resident (C ABI, pinned host numpy buffers): per step fused tick in "
+                        "%d-env chunks over 3 streams, D2H f32 features + teacher actions + done/success; the "
+                        "environments stay in HBM" % args.e2e_chunk})
     env.close()
-    return res
+    return {"headline": head, "variants": variants}
 
 
 def main():
@@ -497,6 +718,12 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=16384)
     ap.add_argument("--ticks-per-launch", type=int, default=8,
                     help="teacher-driven rollouts run this many ticks per kernel launch (1 = one tick per launch)")
+    ap.add_argument("--min-seconds", type=float, default=0.06,
+                    help="the K-step plan is repeated until the timed region lasts at least this long")
+    ap.add_argument("--repeats", type=int, default=0, help="force the number of repeats (0 = from --min-seconds)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed kernel")
+    ap.add_argument("--no-1m", action="store_true", help="skip the 1,048,576-env per-kernel table")
+    ap.add_argument("--no-config3", action="store_true", help="skip BASELINE config 3 (world > 1)")
     ap.add_argument("--policy", default="teacher", choices=["teacher", "random"],
                     help="who acts: the teacher (BASELINE config) or uniform random actions (off-policy variant)")
     args = ap.parse_args()

@@ -96,6 +96,19 @@ typedef struct psk_craft_episodes {
 
 /* library / build info: "psketch_b200 <version> sm_100a" */
 const char *psk_version(void);
+/* Run-time tuning knobs, for tests and same-box A/B runs: every kernel variant the dispatcher can
+ * pick by batch size can also be forced.  value -1 = automatic (the default); each knob starts from
+ * the environment variable PSK_<KEY IN UPPER CASE>.  Keys:
+ *   rollout_variant  CTA shape of craft_rollout_kernel: 0 = 64 env threads + 2 feature warps,
+ *                    2 = 32 + 2, 3 = 16 + 2, 4 = 16 + 1
+ *   rollout_tma      0 = 128-bit vector stores, 1 = TMA bulk stores (cp.async.bulk)
+ *   rollout_split    1 = decoupled teacher / feature kernels on two streams (psk_craft_rollout)
+ *   tick_variant     CTA shape of craft_tick_kernel: 0 = 64+2, 1 = 128+4, 2 = 32+1, 3 = 64+4, 4 = 32+2
+ *   tick_tma, tick_persist, feat_persist, tick_pdl, step_variant (0 = tables staged in shared memory)
+ * Unknown keys return PSK_ERR_BADARG.  Results never depend on a knob (tests/test_craft_gpu.py). */
+int psk_set_tuning(const char *key, int32_t value);
+int psk_get_tuning(const char *key, int32_t *value);
+
 /* number of bytes of one feature row, or -1 when the configuration is unsupported */
 int psk_craft_n_features(const psk_craft_tables *t);
 int psk_craft_supported(const psk_craft_tables *t);
@@ -111,6 +124,11 @@ int psk_craft_step(const psk_craft_tables *t, psk_craft_state s, const uint8_t *
  * 2 = shared-memory tile + TMA bulk stores (cp.async.bulk). */
 int psk_craft_features(const psk_craft_tables *t, psk_craft_state s, float *out, int impl,
                        void *stream);
+
+/* The same feature rows as bytes, u8[n][n_features]: every feature is an exact integer <= 255 (0/1
+ * indicators and the u8 inventory counts), so `(float)out[i][j]` IS the reference's value.  A
+ * quarter of the f32 frame, for consumers on the far side of PCIe. */
+int psk_craft_features_u8(const psk_craft_tables *t, psk_craft_state s, uint8_t *out, void *stream);
 
 /* CraftState.satisfies (worlds/craft.py:285-294): out[i] = 1 True, 0 False, 2 None.
  * task (may be NULL) overrides the task id stored in the agent record. */
@@ -211,6 +229,28 @@ int psk_craft_host_tick(psk_craft_host_ctx *ctx, uint8_t *host_grid, uint8_t *ho
                         const uint8_t *host_action_in, float *host_features,
                         uint8_t *host_expert, uint8_t *host_done, uint8_t *host_success,
                         int64_t n, unsigned long long *host_stats, int32_t *host_err_flags);
+
+/* Resident mode of the host-buffer path.  A rollout's caller (trainers/imitation.py:42-77) only
+ * consumes features, teacher actions and the done / success flags, and only produces actions: the
+ * environments themselves can stay in HBM between ticks.  psk_craft_host_reset puts every env at its
+ * episode start (world.init_state for the batch, trainers/imitation.py:26); put/get_state move
+ * whole states when the caller wants them (state.pos / state.inventory for describe(),
+ * teachers/primitive_language.py:60-66).  psk_craft_host_tick_resident = psk_craft_host_tick
+ * without the state copies: H2D host_action_in u8[n] (NULL = follow the teacher), D2H the feature
+ * frame in `feature_format` (host_features f32[n][nf] or u8[n][nf], NULL/NONE = no features), the
+ * teacher actions and flags. */
+#define PSK_FEATURES_NONE 0
+#define PSK_FEATURES_F32 1
+#define PSK_FEATURES_U8 2
+int psk_craft_host_reset(psk_craft_host_ctx *ctx, int64_t n);
+int psk_craft_host_put_state(psk_craft_host_ctx *ctx, const uint8_t *host_grid,
+                             const uint8_t *host_agent, int64_t n);
+int psk_craft_host_get_state(psk_craft_host_ctx *ctx, uint8_t *host_grid, uint8_t *host_agent,
+                             int64_t n);
+int psk_craft_host_tick_resident(psk_craft_host_ctx *ctx, const uint8_t *host_action_in,
+                                 void *host_features, int32_t feature_format,
+                                 uint8_t *host_expert, uint8_t *host_done, uint8_t *host_success,
+                                 int64_t n, unsigned long long *host_stats, int32_t *host_err_flags);
 
 #ifdef __cplusplus
 }

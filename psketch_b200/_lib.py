@@ -22,8 +22,11 @@ CRAFT_EXPORTS = (
     "psk_craft_reset", "psk_craft_tick", "psk_host_alloc", "psk_host_free",
     "psk_craft_host_create", "psk_craft_host_destroy", "psk_craft_host_set_episodes",
     "psk_craft_host_tick", "psk_craft_sample_scenarios", "psk_craft_sample_positions",
-    "psk_random_actions", "psk_craft_rollout",
+    "psk_random_actions", "psk_craft_rollout", "psk_set_tuning", "psk_get_tuning",
+    "psk_craft_features_u8", "psk_craft_host_reset", "psk_craft_host_put_state",
+    "psk_craft_host_get_state", "psk_craft_host_tick_resident",
 )
+FEATURES_NONE, FEATURES_F32, FEATURES_U8 = 0, 1, 2
 
 
 class CraftTablesC(ctypes.Structure):
@@ -96,6 +99,13 @@ def load():
     lib.psk_craft_sample_scenarios.argtypes = [tp, vp, vp, vp, i32, i32, u64, u64, i64, i32, vp, vp]
     lib.psk_craft_sample_positions.argtypes = [tp, vp, vp, i32, vp, u64, u64, i64, i32, vp, vp]
     lib.psk_random_actions.argtypes = [vp, i64, i32, u64, u64, vp, vp]
+    lib.psk_craft_features_u8.argtypes = [tp, CraftStateC, vp, vp]
+    lib.psk_craft_host_reset.argtypes = [vp, i64]
+    lib.psk_craft_host_put_state.argtypes = [vp, vp, vp, i64]
+    lib.psk_craft_host_get_state.argtypes = [vp, vp, vp, i64]
+    lib.psk_craft_host_tick_resident.argtypes = [vp, vp, vp, i32, vp, vp, vp, i64, vp, vp]
+    lib.psk_set_tuning.argtypes = [ctypes.c_char_p, i32]
+    lib.psk_get_tuning.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32)]
     for name in CRAFT_EXPORTS[1:]:
         if name not in ("psk_host_alloc", "psk_host_free", "psk_craft_host_destroy"):
             getattr(lib, name).restype = ctypes.c_int
@@ -123,6 +133,29 @@ def load_light():
             getattr(lib, name).restype = ctypes.c_int
         _light_bound = True
     return lib
+
+
+def set_tuning(**knobs):
+    """psk_set_tuning for every keyword (value None or -1 = automatic); returns the old values."""
+    lib = load()
+    old = {}
+    for key, value in knobs.items():
+        cur = ctypes.c_int32()
+        check(lib.psk_get_tuning(key.encode(), ctypes.byref(cur)), "psk_get_tuning(%s)" % key)
+        old[key] = cur.value
+        check(lib.psk_set_tuning(key.encode(), -1 if value is None else int(value)),
+              "psk_set_tuning(%s)" % key)
+    return old
+
+
+def check_max_timesteps(max_timesteps):
+    """The episode timer is one byte of the agent record (include/psk_craft.h: PSK_AG_TIMER); the
+    reference's is an unbounded Python int (trainers/imitation.py:30)."""
+    t = int(max_timesteps)
+    if not 0 < t <= 255:
+        raise ValueError("max_timesteps must be in 1..255 (u8 timer in the agent record), got %r"
+                         % (max_timesteps,))
+    return t
 
 
 def check(rc, what):

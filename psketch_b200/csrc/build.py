@@ -14,8 +14,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
-    "-shared", "-cudart", "shared",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared"]
+OBJ_DIR = os.path.join(HERE, "build")          # git-ignored; objects are rebuilt per source file
 
 
 def nvcc_path():
@@ -36,15 +37,42 @@ def needs_build():
     return False
 
 
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    mt = os.path.getmtime(target)
+    return any(os.path.exists(d) and os.path.getmtime(d) > mt for d in deps)
+
+
 def build(force=False, verbose=False, out=None, extra=()):
-    """``out`` / ``extra``: experiment builds (another file name, extra -D flags) for A/B runs."""
+    """Compiles every source to its own object (in parallel, only the stale ones) and links the
+    shared library.  ``out`` / ``extra``: experiment builds (another file name, extra -D flags) for
+    A/B runs — those always recompile everything into their own object directory."""
     if not force and not needs_build() and out is None:
         return LIB
-    srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
-    cmd = ([nvcc_path()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) +
-           ["-o", out or LIB] + srcs)
-    subprocess.check_call(cmd, cwd=HERE)
-    return out or LIB
+    from concurrent.futures import ThreadPoolExecutor
+    target = out or LIB
+    obj_dir = OBJ_DIR if out is None else OBJ_DIR + "_" + os.path.basename(out).replace(".", "_")
+    os.makedirs(obj_dir, exist_ok=True)
+    common = [os.path.join(HERE, h) for h in HEADERS] + [os.path.join(HERE, "build.py")]
+    jobs = []
+    for src in SOURCES:
+        sp = os.path.join(HERE, src)
+        if not os.path.exists(sp):
+            continue
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        if force or out is not None or _stale(obj, [sp] + common):
+            cmd = ([nvcc_path()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) +
+                   ["-c", "-o", obj, sp])
+            jobs.append(cmd)
+    with ThreadPoolExecutor(max_workers=max(1, len(jobs))) as pool:
+        for rc in pool.map(lambda c: subprocess.call(c, cwd=HERE), jobs):
+            if rc:
+                raise subprocess.CalledProcessError(rc, "nvcc -c")
+    objs = [os.path.join(obj_dir, s.replace(".cu", ".o")) for s in SOURCES
+            if os.path.exists(os.path.join(HERE, s))]
+    subprocess.check_call([nvcc_path()] + LINK_FLAGS + ["-o", target] + objs, cwd=HERE)
+    return target
 
 
 if __name__ == "__main__":

@@ -33,9 +33,26 @@ struct __align__(16) SharedTables {
         return reinterpret_cast<const uint32_t *>(t().task_nodes)[(task & 31) * PSK_MAX_TASK_NODES + i];
     }
     __device__ __forceinline__ int task_len(int task) const { return t().task_len[task & 31]; }
+    __device__ __forceinline__ int n_recipes() const { return t().n_recipes; }
+    __device__ __forceinline__ int bridge_kind() const { return t().bridge_kind; }
+    __device__ __forceinline__ int axe_kind() const { return t().axe_kind; }
 };
 
 static_assert(sizeof(psk_craft_tables) % 16 == 0, "tables are staged with 128-bit loads");
+
+// The same accessors straight from the device copy (read-only path, L1-resident after the first
+// touch).  For kernels that use a few dozen bytes of the tables per thread and are too short to pay
+// for staging 2.3 KB + a CTA barrier (craft_step_kernel: 160 bytes of kind classes and recipes).
+struct GlobalTables {
+    const psk_craft_tables *p;
+    __device__ __forceinline__ int kind_class(int k) const { return __ldg(p->kind_class + (k & 31)); }
+    __device__ __forceinline__ uint2 recipe(int r) const {
+        return __ldg(reinterpret_cast<const uint2 *>(p->recipes) + r);
+    }
+    __device__ __forceinline__ int n_recipes() const { return __ldg(&p->n_recipes); }
+    __device__ __forceinline__ int bridge_kind() const { return __ldg(&p->bridge_kind); }
+    __device__ __forceinline__ int axe_kind() const { return __ldg(&p->axe_kind); }
+};
 
 // T points at the device copy of the tables (see device_tables() in psk_craft.cu): one coalesced
 // 128-bit load per thread.  (Indexing the struct as a kernel parameter instead costs one

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include "psk_common.cuh"
@@ -26,8 +27,8 @@ namespace psk {
 // Applies `act` to the agent record `a` and the env's grid row.  Cells are read through `rd`
 // (global memory, or a shared-memory copy of the row) and cleared through `row` (global).
 // flags collects PSK_FLAG_* bits.
-template <int W, int H>
-__device__ __forceinline__ void step_env(const SharedTables &st, Agent &a, uint8_t *row,
+template <int W, int H, class TAB>
+__device__ __forceinline__ void step_env(const TAB &st, Agent &a, uint8_t *row,
                                          const uint8_t *rd, int act, uint32_t &flags) {
     int x = a.x(), y = a.y(), dir = a.dir();
     if (act < 4) {  // craft.py:341-352 + 418-421: turn always, move iff the target cell is free
@@ -43,7 +44,6 @@ __device__ __forceinline__ void step_env(const SharedTables &st, Agent &a, uint8
         if (fx >= 0 && fy >= 0 && fx < W && fy < H) {  // neighbors(), craft.py:426-437
             const int thing = rd[fx * H + fy];
             const int cls = st.kind_class(thing);
-            const psk_craft_tables &T = st.t();
             if (cls == KC_GRAB) {  // craft.py:383-386
                 if (thing < PSK_MAX_INV) {
                     if (a.inv(thing) == 255) flags |= PSK_FLAG_INV_OVERFLOW;
@@ -51,7 +51,7 @@ __device__ __forceinline__ void step_env(const SharedTables &st, Agent &a, uint8
                 }
                 row[fx * H + fy] = 0;
             } else if (cls == KC_WORKSHOP) {  // craft.py:388-401: all recipes, in file order
-                for (int r = 0; r < T.n_recipes; r++) {
+                for (int r = 0, nr = st.n_recipes(); r < nr; r++) {
                     const uint2 rc = st.recipe(r);
                     const int out = rc.x & 0xFF, ws = (rc.x >> 8) & 0xFF, n_in = (rc.x >> 16) & 0xFF;
                     if (ws != thing) continue;
@@ -65,12 +65,14 @@ __device__ __forceinline__ void step_env(const SharedTables &st, Agent &a, uint8
                     if (n_in > 1) a.inv_add(in1, -c1);
                 }
             } else if (cls == KC_WATER) {  // craft.py:403-406
-                if (T.bridge_kind && a.inv(T.bridge_kind) > 0) {
+                const int bridge = st.bridge_kind();
+                if (bridge && a.inv(bridge) > 0) {
                     row[fx * H + fy] = 0;
-                    a.inv_add(T.bridge_kind, -1);
+                    a.inv_add(bridge, -1);
                 }
             } else if (cls == KC_STONE) {  // craft.py:408-410 (the axe is kept)
-                if (T.axe_kind && a.inv(T.axe_kind) > 0) row[fx * H + fy] = 0;
+                const int axe = st.axe_kind();
+                if (axe && a.inv(axe) > 0) row[fx * H + fy] = 0;
             }
         }
     } else if (act != PSK_ACT_STOP) {
@@ -78,26 +80,37 @@ __device__ __forceinline__ void step_env(const SharedTables &st, Agent &a, uint8
     }
 }
 
-template <int W, int H>
-__global__ void __launch_bounds__(256)
+// STAGED = true: tables staged in shared memory by the CTA (256-thread CTAs, the round-1 kernel);
+// false: kind classes / recipes read through the read-only path from the device copy, no shared
+// memory and no CTA barrier, 64-thread CTAs so that 65,536 envs spread over all SMs (the kernel
+// is launch-latency bound at that size: 13 MB of traffic).
+template <int W, int H, bool STAGED>
+__global__ void __launch_bounds__(STAGED ? 256 : 64)
 craft_step_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                   uint8_t *__restrict__ agent, const uint8_t *__restrict__ action,
                   const uint8_t *__restrict__ active, float *__restrict__ reward,
                   int32_t *err_flags, int64_t n, int cell_stride) {
-    __shared__ SharedTables st;
-    stage_tables(st, T);
     uint32_t flags = 0;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        if (reward) reward[e] = 0.0f;  // craft.py:338,424
-        if (active && !active[e]) continue;
-        Agent a = load_agent(agent, e);
-        const Agent before = a;
-        step_env<W, H>(st, a, grid + e * cell_stride, grid + e * cell_stride, action[e], flags);
-        bool changed = false;
+    auto body = [&](const auto &tab) {
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+             e += (int64_t)gridDim.x * blockDim.x) {
+            if (reward) reward[e] = 0.0f;  // craft.py:338,424
+            if (active && !active[e]) continue;
+            Agent a = load_agent(agent, e);
+            const Agent before = a;
+            step_env<W, H>(tab, a, grid + e * cell_stride, grid + e * cell_stride, action[e], flags);
+            bool changed = false;
 #pragma unroll
-        for (int i = 0; i < 8; i++) changed |= a.w[i] != before.w[i];
-        if (changed) store_agent(agent, e, a);
+            for (int i = 0; i < 8; i++) changed |= a.w[i] != before.w[i];
+            if (changed) store_agent(agent, e, a);
+        }
+    };
+    if constexpr (STAGED) {
+        __shared__ SharedTables sst;
+        stage_tables(sst, T);
+        body(sst);
+    } else {
+        body(GlobalTables{T});
     }
     if (flags && err_flags) atomicOr(err_flags, (int)flags);
 }
@@ -1173,12 +1186,55 @@ __device__ __forceinline__ void warp_feature_chunk(uint32_t wbuf_s, int it, floa
     }
 }
 
+// Compact observation frame: the same feature rows as bytes (u8[n][nf]; every feature is an exact
+// integer <= 255: 0/1 indicators and inventory counts, which are u8 in the state already).  A
+// quarter of the f32 frame — for consumers on the far side of PCIe (psk_craft_host_tick_resident).
+// The u8 tile is what the vector path builds anyway; here it leaves as it is, 4 features per store.
+template <int W, int H, int WIN, int TPE, int KC>
+__device__ __forceinline__ void warp_feature_chunk_u8(uint32_t wbuf_s, uint8_t *gdst, int ne,
+                                                      const RowChunks<W, H, TPE> &cells,
+                                                      const Agent &a, int K, int nf) {
+    constexpr int EPW = 32 / TPE;
+    if (KC > 0) {
+        K = KC;
+        nf = 2 * WIN * WIN * KC + KC + 5;
+    }
+    const int lane = threadIdx.x & 31;
+    const int le = lane / TPE, j = lane % TPE;
+    const uint32_t trash_s = wbuf_s + feature_tile_bytes(false, EPW, nf, 1) - 16;
+    if (le < ne) scatter_features<W, H, WIN, TPE, 1>(wbuf_s + le * nf, trash_s, cells, a, K, j);
+    __syncwarp();
+    const int n4 = EPW * nf / 4;                 // words of a full chunk (EPW is a multiple of 4)
+    const int bytes = ne * nf;
+    if ((bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(gdst) & 3) == 0) {
+        uint32_t *g4 = reinterpret_cast<uint32_t *>(gdst);
+        for (int i = lane; i < n4; i += 32) {
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(wbuf_s + i * 4));
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(wbuf_s + i * 4), "r"(0) : "memory");
+            if (i < bytes / 4) __stcs(g4 + i, w);
+        }
+    } else {
+        for (int i = lane; i < bytes; i += 32) {
+            uint32_t b;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(wbuf_s + i));
+            gdst[i] = (uint8_t)b;
+        }
+        __syncwarp();
+        for (int i = lane; i < n4; i += 32)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(wbuf_s + i * 4), "r"(0) : "memory");
+    }
+    __syncwarp();
+}
+
 // WPB autonomous warps per CTA; warp w of CTA b takes chunks (b*WPB + w) + k*gridDim.x*WPB.
 // The inputs of the next chunk are fetched before the current one is built (software prefetch).
-template <int W, int H, int WIN, int WPB, int TPE, int KC, bool USE_TMA>
+template <int W, int H, int WIN, int WPB, int TPE, int KC, bool USE_TMA, typename OUT = float>
 __global__ void __launch_bounds__(WPB * 32)
 craft_features_kernel(const uint8_t *__restrict__ grid, const uint8_t *__restrict__ agent,
-                      float *__restrict__ out, int64_t n, int cell_stride, int K, int nf) {
+                      OUT *__restrict__ out, int64_t n, int cell_stride, int K, int nf) {
+    constexpr bool OUT_U8 = sizeof(OUT) == 1;
+    static_assert(!(OUT_U8 && USE_TMA), "the u8 frame uses the vector path");
     constexpr int EPW = 32 / TPE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1202,8 +1258,11 @@ craft_features_kernel(const uint8_t *__restrict__ grid, const uint8_t *__restric
         if (more) fetch(ch + stride, a_next, cells_next);
         const int64_t e0 = ch * EPW;
         const int ne = (int)((n - e0) < EPW ? (n - e0) : EPW);
-        warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA, PSK_ESZ_FEATURES_KERNEL>(wbuf_s, it, out + e0 * nf, ne, cells, a,
-                                                                                 K, nf);
+        if constexpr (OUT_U8)
+            warp_feature_chunk_u8<W, H, WIN, TPE, KC>(wbuf_s, out + e0 * nf, ne, cells, a, K, nf);
+        else
+            warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA, PSK_ESZ_FEATURES_KERNEL>(wbuf_s, it, out + e0 * nf, ne, cells, a,
+                                                                                     K, nf);
         if (more) {
             a = a_next;
             cells = cells_next;
@@ -1450,8 +1509,9 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
 // Register cap: 896 threads per SM at 72 registers, i.e. 7 CTAs of 64 + 2 warps (128 threads) or
 // 9 CTAs of 32 + 2 warps (96 threads); one register more and a CTA less fits per SM (17.5 -> 21 us
 // per tick at 65,536 envs when a change pushed the kernel to 80 registers).
+__host__ __device__ constexpr int rollout_threads(int ne, int nfw) { return (ne + 31) / 32 * 32 + nfw * 32; }
 template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA>
-__global__ void __launch_bounds__(NE + NFW * 32, (NE + NFW * 32) <= 128 ? 896 / (NE + NFW * 32) : 1)
+__global__ void __launch_bounds__(rollout_threads(NE, NFW), rollout_threads(NE, NFW) <= 128 ? 896 / rollout_threads(NE, NFW) : 1)
 craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                      uint8_t *__restrict__ agent, const uint8_t *__restrict__ action_in,
                      const uint8_t *__restrict__ scen_grid, const int32_t *__restrict__ scen_idx,
@@ -1459,7 +1519,8 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
                      int feat_ring, uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
                      uint8_t *__restrict__ success_out, unsigned long long *stats,
                      int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int ticks) {
-    constexpr int NT = NE + NFW * 32;
+    constexpr int NEW = (NE + 31) / 32 * 32;   // env-warp threads (lanes >= NE idle when NE < 32)
+    constexpr int NT = NEW + NFW * 32;
     constexpr int TPE = 8, EPW = 32 / TPE;
     constexpr int SPW = NE / NFW;
     static_assert(SPW % EPW == 0, "feature warps take whole chunks");
@@ -1472,10 +1533,10 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
     asm volatile("griddepcontrol.launch_dependents;");
     stage_tables(st, T);
     const int tid = threadIdx.x;
-    const bool env_warp = tid < NE;
+    const bool env_warp = tid < NEW;
     if (!USE_TMA && !env_warp && features_out)
         feature_buffer_init<8, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
-            smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
+            smem_u32(smem_raw) + (uint32_t)((tid - NEW) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
             nf);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     uint32_t flags = 0;
@@ -1493,8 +1554,8 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
             for (int i = tid; i < ne_sp * 2; i += NT) sag[i] = gag[i];
         }
         __syncthreads();
-        const bool live = env_warp && tid < ne_sp;
-        const int slot = (env_warp && tid < ne_sp) ? tid : 0;
+        const bool live = env_warp && tid < ne_sp;   // ne_sp <= NE
+        const int slot = live ? tid : 0;
         const int64_t e = e_base + slot;
         Agent a;
         const uint8_t *scen_row = nullptr;
@@ -1541,7 +1602,7 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
                     sag[1] = make_uint4(a.w[4], a.w[5], a.w[6], a.w[7]);
                 }
             } else if (features_out) {
-                const int fw = (tid - NE) >> 5, lane = tid & 31;
+                const int fw = (tid - NEW) >> 5, lane = tid & 31;
                 const uint32_t wbuf_s = smem_u32(smem_raw) +
                                         (uint32_t)fw * feature_buffer_bytes(USE_TMA, EPW, nf, PSK_ESZ_FUSED_KERNELS);
                 float *fout = features_out + (int64_t)(t % feat_ring) * n * nf;
@@ -1602,6 +1663,33 @@ static int num_sms() {
         sms[dev] = n > 0 ? n : 148;
     }
     return sms[dev];
+}
+
+// Run-time tuning knobs (psk_set_tuning in include/psk_craft.h): -1 = automatic.  Each knob starts
+// from the environment variable PSK_<NAME> (upper case) the first time any knob is read, and can be
+// changed at any time afterwards, so tests and A/B runs can force every kernel variant.
+enum TuneKey { TUNE_ROLLOUT_VARIANT, TUNE_ROLLOUT_TMA, TUNE_TICK_VARIANT, TUNE_TICK_TMA,
+               TUNE_TICK_PERSIST, TUNE_FEAT_PERSIST, TUNE_TICK_PDL, TUNE_STEP_VARIANT,
+               TUNE_ROLLOUT_SPLIT, TUNE_COUNT };
+static const char *const tune_names[TUNE_COUNT] = {
+    "rollout_variant", "rollout_tma", "tick_variant", "tick_tma", "tick_persist", "feat_persist",
+    "tick_pdl", "step_variant", "rollout_split"};
+static std::atomic<int> tune_val[TUNE_COUNT];
+static std::once_flag tune_once;
+static void tune_init() {
+    for (int i = 0; i < TUNE_COUNT; i++) {
+        char name[64] = "PSK_";
+        size_t j = 4;
+        for (const char *c = tune_names[i]; *c && j + 1 < sizeof(name); c++)
+            name[j++] = (char)(*c >= 'a' && *c <= 'z' ? *c - 32 : *c);
+        name[j] = 0;
+        const char *v = getenv(name);
+        tune_val[i].store(v ? atoi(v) : -1);
+    }
+}
+static inline int tune(TuneKey k) {
+    std::call_once(tune_once, tune_init);
+    return tune_val[k].load(std::memory_order_relaxed);
 }
 
 static inline int grid_for(int64_t n, int block, int ctas_per_sm) {
@@ -1677,8 +1765,12 @@ template <int W, int H, int WIN> struct Config {
     static int step(const psk_craft_tables *t, psk_craft_state s, const uint8_t *action,
                     const uint8_t *active, float *reward, int32_t *err, cudaStream_t st) {
         PSK_DT(dt);
-        craft_step_kernel<W, H><<<grid_for(s.n, 256, 8), 256, 0, st>>>(
-            dt, s.grid, s.agent, action, active, reward, err, s.n, s.cell_stride);
+        if (tune(TUNE_STEP_VARIANT) == 0)
+            craft_step_kernel<W, H, true><<<grid_for(s.n, 256, 8), 256, 0, st>>>(
+                dt, s.grid, s.agent, action, active, reward, err, s.n, s.cell_stride);
+        else
+            craft_step_kernel<W, H, false><<<grid_for(s.n, 64, 32), 64, 0, st>>>(
+                dt, s.grid, s.agent, action, active, reward, err, s.n, s.cell_stride);
         return check(cudaGetLastError());
     }
     static int satisfies(const psk_craft_tables *t, psk_craft_state s, const uint8_t *task,
@@ -1711,22 +1803,22 @@ template <int W, int H, int WIN> struct Config {
                 s.grid, s.agent, kind, goal, len, seq, seq_cap, s.n, s.cell_stride);
         return check(cudaGetLastError());
     }
-    template <bool TMA>
-    static int features_impl(const psk_craft_tables *t, psk_craft_state s, float *out,
+    template <bool TMA, typename OUT = float>
+    static int features_impl(const psk_craft_tables *t, psk_craft_state s, OUT *out,
                              cudaStream_t st) {
         constexpr int WPB = 4, EPW = 32 / TPE;
         const int f = nf(t);
         const size_t smem = (size_t)WPB * feature_buffer_bytes(TMA, EPW, f, PSK_ESZ_FEATURES_KERNEL);
         // the default cookbook has 21 kinds: that case is compiled with K fixed
-        auto kern = t->n_kinds == 21 ? craft_features_kernel<W, H, WIN, WPB, TPE, 21, TMA>
-                                     : craft_features_kernel<W, H, WIN, WPB, TPE, 0, TMA>;
+        auto kern = t->n_kinds == 21 ? craft_features_kernel<W, H, WIN, WPB, TPE, 21, TMA, OUT>
+                                     : craft_features_kernel<W, H, WIN, WPB, TPE, 0, TMA, OUT>;
         // opt in to > 48 KB dynamic smem (both instantiations, once per size)
         static size_t configured_on[PSK_MAX_DEVICES] = {0};   // the attribute is per device
         size_t &configured = configured_on[current_device()];
         if (configured != smem) {
-            if (cudaFuncSetAttribute(craft_features_kernel<W, H, WIN, WPB, TPE, 21, TMA>,
+            if (cudaFuncSetAttribute(craft_features_kernel<W, H, WIN, WPB, TPE, 21, TMA, OUT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-                cudaFuncSetAttribute(craft_features_kernel<W, H, WIN, WPB, TPE, 0, TMA>,
+                cudaFuncSetAttribute(craft_features_kernel<W, H, WIN, WPB, TPE, 0, TMA, OUT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return PSK_ERR_CUDA;
             configured = smem;
@@ -1735,13 +1827,9 @@ template <int W, int H, int WIN> struct Config {
         if (per_sm > 16) per_sm = 16;
         const int64_t ctas = (s.n + (int64_t)WPB * EPW - 1) / ((int64_t)WPB * EPW);
         int64_t g = (int64_t)num_sms() * (per_sm > 0 ? per_sm : 1);
-        static int persist = -1;
-        if (persist < 0) {
-            // One CTA per tile, dispatched in index order, keeps the DRAM write front compact:
-            // 270 us vs 330 us at 1 M envs for a persistent grid-stride grid (profiles/README.md).
-            const char *v = getenv("PSK_FEAT_PERSIST");
-            persist = v ? atoi(v) : 0;
-        }
+        // One CTA per tile, dispatched in index order, keeps the DRAM write front compact:
+        // 270 us vs 330 us at 1 M envs for a persistent grid-stride grid (profiles/README.md).
+        const int persist = tune(TUNE_FEAT_PERSIST) > 0;
         if (g > ctas || !persist) g = ctas > 0 ? ctas : 1;
         kern<<<(int)g, WPB * 32, smem, st>>>(s.grid, s.agent, out, s.n, s.cell_stride, t->n_kinds, f);
         return check(cudaGetLastError());
@@ -1750,6 +1838,9 @@ template <int W, int H, int WIN> struct Config {
                         cudaStream_t st) {
         if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) impl = 1;
         return impl == 2 ? features_impl<true>(t, s, out, st) : features_impl<false>(t, s, out, st);
+    }
+    static int features_u8(const psk_craft_tables *t, psk_craft_state s, uint8_t *out, cudaStream_t st) {
+        return features_impl<false, uint8_t>(t, s, out, st);
     }
     static int advance(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
                        const uint8_t *action, uint8_t *done, uint8_t *success,
@@ -1786,18 +1877,10 @@ template <int W, int H, int WIN> struct Config {
         if (per_sm > by_threads) per_sm = by_threads;
         const int64_t tiles = (s.n + NE - 1) / NE;
         int64_t g = (int64_t)num_sms() * (per_sm > 0 ? per_sm : 1);
-        static int persist = -1;
-        if (persist < 0) {
-            const char *v = getenv("PSK_TICK_PERSIST");   // see features_impl: in-order tiles win
-            persist = v ? atoi(v) : 0;
-        }
+        const int persist = tune(TUNE_TICK_PERSIST) > 0;   // see features_impl: in-order tiles win
         if (g > tiles || !persist) g = tiles > 0 ? tiles : 1;
         PSK_DT(dt);
-        static int pdl = -1;
-        if (pdl < 0) {
-            const char *v = getenv("PSK_TICK_PDL");
-            pdl = v ? atoi(v) : 1;
-        }
+        const int pdl = tune(TUNE_TICK_PDL) != 0;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)g);
         cfg.blockDim = dim3(NE + NFW * 32);
@@ -1838,7 +1921,7 @@ template <int W, int H, int WIN> struct Config {
         PSK_DT(dt);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(tiles > 0 ? tiles : 1));
-        cfg.blockDim = dim3(NE + NFW * 32);
+        cfg.blockDim = dim3(rollout_threads(NE, NFW));
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -1866,19 +1949,19 @@ template <int W, int H, int WIN> struct Config {
             //                   early are replaced instead of leaving their SM idle (16.75 vs
             //                   17.66 us per tick); vector stores up to 196,608 envs, TMA above.
             // PSK_ROLLOUT_VARIANT (0 / 2) and PSK_ROLLOUT_TMA (0 / 1) override for experiments.
-            static int env_tma = -2, env_variant = -2;
-            if (env_tma == -2) {
-                const char *m = getenv("PSK_ROLLOUT_TMA");
-                env_tma = m ? atoi(m) : -1;
-                m = getenv("PSK_ROLLOUT_VARIANT");
-                env_variant = m ? atoi(m) : -1;
-            }
+            const int env_tma = tune(TUNE_ROLLOUT_TMA), env_variant = tune(TUNE_ROLLOUT_VARIANT);
             const int tma = env_tma >= 0 ? env_tma : (s.n > 196608 ? 1 : 0);
             const int variant = env_variant >= 0 ? env_variant : (s.n >= 65536 ? 2 : 0);
 #define PSK_ROLLOUT_ARGS t, s, ep, ticks, action_in, features_out, feat_ring, expert_out, done, success, stats, err, st
             if (variant == 2)
                 return tma ? rollout_variant<32, 2, true>(PSK_ROLLOUT_ARGS)
                            : rollout_variant<32, 2, false>(PSK_ROLLOUT_ARGS);
+            if (variant == 3)   // 16 envs per CTA (half an env warp) + 2 feature warps: 3 waves at 65,536 envs
+                return tma ? rollout_variant<16, 2, true>(PSK_ROLLOUT_ARGS)
+                           : rollout_variant<16, 2, false>(PSK_ROLLOUT_ARGS);
+            if (variant == 4)   // 16 envs + 1 feature warp (64 threads, 14 CTAs per SM)
+                return tma ? rollout_variant<16, 1, true>(PSK_ROLLOUT_ARGS)
+                           : rollout_variant<16, 1, false>(PSK_ROLLOUT_ARGS);
             return tma ? rollout_variant<64, 2, true>(PSK_ROLLOUT_ARGS)
                        : rollout_variant<64, 2, false>(PSK_ROLLOUT_ARGS);
 #undef PSK_ROLLOUT_ARGS
@@ -1895,13 +1978,7 @@ template <int W, int H, int WIN> struct Config {
         // every batch size measured (65,536: 20.4 vs 20.9 us for 64 + 2; 262,144: 71.2 vs 72.9),
         // vector stores up to 262,144 envs, TMA stores above (1 M: 294 vs 318 us).
         // PSK_TICK_VARIANT / PSK_TICK_TMA override.
-        static int env_variant = -2, env_tma = -2;
-        if (env_variant == -2) {
-            const char *v = getenv("PSK_TICK_VARIANT");
-            env_variant = v ? atoi(v) : -1;
-            const char *m = getenv("PSK_TICK_TMA");
-            env_tma = m ? atoi(m) : -1;
-        }
+        const int env_variant = tune(TUNE_TICK_VARIANT), env_tma = tune(TUNE_TICK_TMA);
         const bool big = s.n > 262144;
         const int variant = env_variant >= 0 ? env_variant : 4;
         const int tma = env_tma >= 0 ? env_tma : (big ? 1 : 0);
@@ -1956,7 +2033,28 @@ using namespace psk;
 
 extern "C" {
 
-const char *psk_version(void) { return "psketch_b200 0.1 sm_100a"; }
+const char *psk_version(void) { return "psketch_b200 0.2 sm_100a"; }
+
+int psk_set_tuning(const char *key, int32_t value) {
+    if (!key) return PSK_ERR_BADARG;
+    tune(TUNE_ROLLOUT_VARIANT);   // environment defaults are read before the first override
+    for (int i = 0; i < TUNE_COUNT; i++)
+        if (strcmp(key, tune_names[i]) == 0) {
+            tune_val[i].store(value);
+            return PSK_OK;
+        }
+    return PSK_ERR_BADARG;
+}
+
+int psk_get_tuning(const char *key, int32_t *value) {
+    if (!key || !value) return PSK_ERR_BADARG;
+    for (int i = 0; i < TUNE_COUNT; i++)
+        if (strcmp(key, tune_names[i]) == 0) {
+            *value = tune((TuneKey)i);
+            return PSK_OK;
+        }
+    return PSK_ERR_BADARG;
+}
 
 int psk_craft_supported(const psk_craft_tables *t) {
     if (!t) return 0;
@@ -1981,6 +2079,12 @@ int psk_craft_features(const psk_craft_tables *t, psk_craft_state s, float *out,
     if (!state_ok(t, s) || (!out && s.n)) return PSK_ERR_BADARG;
     if (s.n == 0) return PSK_OK;
     PSK_DISPATCH(t, features(t, s, out, impl, (cudaStream_t)stream));
+}
+
+int psk_craft_features_u8(const psk_craft_tables *t, psk_craft_state s, uint8_t *out, void *stream) {
+    if (!state_ok(t, s) || (!out && s.n)) return PSK_ERR_BADARG;
+    if (s.n == 0) return PSK_OK;
+    PSK_DISPATCH(t, features_u8(t, s, out, (cudaStream_t)stream));
 }
 
 int psk_craft_satisfies(const psk_craft_tables *t, psk_craft_state s, const uint8_t *task,

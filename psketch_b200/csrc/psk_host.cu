@@ -33,6 +33,11 @@ struct psk_craft_host_ctx {
     int64_t n_scen, n_eps;
     unsigned long long *d_stats;
     int32_t *d_err;
+    // resident mode (psk_craft_host_tick_resident): the working state and the per-env byte outputs
+    // of the whole batch stay on the device; allocated on first use
+    uint8_t *r_grid, *r_agent, *r_action, *r_expert, *r_done, *r_success;
+    cudaEvent_t ev_in, ev_chunk[PSK_HOST_STREAMS];
+    bool resident_ready;
 };
 
 #define CK(x)                                   \
@@ -121,6 +126,11 @@ void psk_craft_host_destroy(psk_craft_host_ctx *c) {
     }
     cudaFree(c->d_scen_grid); cudaFree(c->d_init_agent); cudaFree(c->d_scen_idx);
     cudaFree(c->d_stats); cudaFree(c->d_err);
+    cudaFree(c->r_grid); cudaFree(c->r_agent); cudaFree(c->r_action);
+    cudaFree(c->r_expert); cudaFree(c->r_done); cudaFree(c->r_success);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    for (int i = 0; i < PSK_HOST_STREAMS; i++)
+        if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     delete c;
 }
 
@@ -185,6 +195,124 @@ int psk_craft_host_tick(psk_craft_host_ctx *c, uint8_t *host_grid, uint8_t *host
         CK(cudaMemcpy(host_err_flags, c->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost));
         if (*host_err_flags) CK(cudaMemset(c->d_err, 0, sizeof(int32_t)));
     }
+    return PSK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resident mode: what crosses PCIe per tick is only what a rollout's caller consumes — the
+// actions it chose go up, feature rows / teacher actions / done / success come down; the
+// environments stay in HBM (fetch them with psk_craft_host_get_state when .pos / .inventory are
+// needed, e.g. for the language teachers' describe()).
+static int resident_alloc(psk_craft_host_ctx *c) {
+    if (c->resident_ready) return PSK_OK;
+    const size_t n = (size_t)c->max_envs;
+    CK(cudaMalloc(&c->r_grid, n * c->cell_stride));
+    CK(cudaMalloc(&c->r_agent, n * PSK_AGENT_BYTES));
+    CK(cudaMalloc(&c->r_action, n));
+    CK(cudaMalloc(&c->r_expert, n));
+    CK(cudaMalloc(&c->r_done, n));
+    CK(cudaMalloc(&c->r_success, n));
+    CK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+    for (int i = 0; i < PSK_HOST_STREAMS; i++)
+        CK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+    c->resident_ready = true;
+    return PSK_OK;
+}
+
+int psk_craft_host_reset(psk_craft_host_ctx *c, int64_t n) {
+    if (!c || n < 0 || n > c->n_eps) return PSK_ERR_BADARG;
+    DeviceScope scope(c->device);
+    int rc = resident_alloc(c);
+    if (rc) return rc;
+    psk_craft_state state = {c->r_grid, c->r_agent, n, c->cell_stride, 0};
+    psk_craft_episodes ep = {c->d_scen_grid, c->d_scen_idx, c->d_init_agent};
+    rc = psk_craft_reset(state, ep, nullptr, c->streams[0]);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->streams[0]));
+    return PSK_OK;
+}
+
+int psk_craft_host_put_state(psk_craft_host_ctx *c, const uint8_t *host_grid,
+                             const uint8_t *host_agent, int64_t n) {
+    if (!c || !host_grid || !host_agent || n < 0 || n > c->max_envs) return PSK_ERR_BADARG;
+    DeviceScope scope(c->device);
+    const int rc = resident_alloc(c);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->r_grid, host_grid, (size_t)n * c->cell_stride, cudaMemcpyHostToDevice, c->streams[0]));
+    CK(cudaMemcpyAsync(c->r_agent, host_agent, (size_t)n * PSK_AGENT_BYTES, cudaMemcpyHostToDevice, c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[0]));
+    return PSK_OK;
+}
+
+int psk_craft_host_get_state(psk_craft_host_ctx *c, uint8_t *host_grid, uint8_t *host_agent, int64_t n) {
+    if (!c || !c->resident_ready || n < 0 || n > c->max_envs) return PSK_ERR_BADARG;
+    DeviceScope scope(c->device);
+    if (host_grid)
+        CK(cudaMemcpyAsync(host_grid, c->r_grid, (size_t)n * c->cell_stride, cudaMemcpyDeviceToHost, c->streams[0]));
+    if (host_agent)
+        CK(cudaMemcpyAsync(host_agent, c->r_agent, (size_t)n * PSK_AGENT_BYTES, cudaMemcpyDeviceToHost, c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[0]));
+    return PSK_OK;
+}
+
+int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_action_in,
+                                 void *host_features, int32_t feature_format,
+                                 uint8_t *host_expert, uint8_t *host_done, uint8_t *host_success,
+                                 int64_t n, unsigned long long *host_stats, int32_t *host_err_flags) {
+    if (!c || !c->resident_ready || !host_expert || n < 0 || n > c->n_eps) return PSK_ERR_BADARG;
+    if (feature_format != PSK_FEATURES_NONE && feature_format != PSK_FEATURES_F32 &&
+        feature_format != PSK_FEATURES_U8)
+        return PSK_ERR_BADARG;
+    if (!host_features) feature_format = PSK_FEATURES_NONE;
+    DeviceScope scope(c->device);
+    const int cs = c->cell_stride;
+    const size_t fsz = feature_format == PSK_FEATURES_U8 ? 1 : 4;
+    cudaStream_t s0 = c->streams[0];
+    if (host_action_in) {       // one copy for the whole batch, the other streams wait for it
+        CK(cudaMemcpyAsync(c->r_action, host_action_in, (size_t)n, cudaMemcpyHostToDevice, s0));
+        CK(cudaEventRecord(c->ev_in, s0));
+        for (int i = 1; i < PSK_HOST_STREAMS; i++) CK(cudaStreamWaitEvent(c->streams[i], c->ev_in, 0));
+    }
+    int k = 0;
+    for (int64_t off = 0; off < n; off += c->chunk, k++) {
+        const int s = k % PSK_HOST_STREAMS;
+        const int64_t m = (n - off) < c->chunk ? (n - off) : c->chunk;
+        cudaStream_t st = c->streams[s];
+        psk_craft_state state = {c->r_grid + off * cs, c->r_agent + off * PSK_AGENT_BYTES, m, cs, 0};
+        psk_craft_episodes ep = {c->d_scen_grid, c->d_scen_idx + off, c->d_init_agent + off * PSK_AGENT_BYTES};
+        const uint8_t *act = host_action_in ? c->r_action + off : nullptr;
+        int rc;
+        if (feature_format == PSK_FEATURES_U8) {
+            // compact frame: features of the pre-step state as bytes, then teacher + advance
+            rc = psk_craft_features_u8(&c->tables, state, reinterpret_cast<uint8_t *>(c->d_feat[s]), st);
+            if (rc) return rc;
+            rc = psk_craft_tick(&c->tables, state, ep, act, nullptr, c->r_expert + off, c->r_done + off,
+                                c->r_success + off, c->d_stats, c->d_err, 1, st);
+        } else {
+            rc = psk_craft_tick(&c->tables, state, ep, act,
+                                feature_format == PSK_FEATURES_F32 ? c->d_feat[s] : nullptr,
+                                c->r_expert + off, c->r_done + off, c->r_success + off, c->d_stats,
+                                c->d_err, 1, st);
+        }
+        if (rc) return rc;
+        if (feature_format != PSK_FEATURES_NONE)
+            CK(cudaMemcpyAsync(static_cast<uint8_t *>(host_features) + (size_t)off * c->nf * fsz, c->d_feat[s],
+                               (size_t)m * c->nf * fsz, cudaMemcpyDeviceToHost, st));
+    }
+    // the per-env byte outputs of the whole batch: one copy each, after every chunk's kernel
+    for (int i = 1; i < PSK_HOST_STREAMS; i++) {
+        CK(cudaEventRecord(c->ev_chunk[i], c->streams[i]));
+        CK(cudaStreamWaitEvent(s0, c->ev_chunk[i], 0));
+    }
+    CK(cudaMemcpyAsync(host_expert, c->r_expert, (size_t)n, cudaMemcpyDeviceToHost, s0));
+    if (host_done) CK(cudaMemcpyAsync(host_done, c->r_done, (size_t)n, cudaMemcpyDeviceToHost, s0));
+    if (host_success) CK(cudaMemcpyAsync(host_success, c->r_success, (size_t)n, cudaMemcpyDeviceToHost, s0));
+    if (host_stats)
+        CK(cudaMemcpyAsync(host_stats, c->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
+    if (host_err_flags)
+        CK(cudaMemcpyAsync(host_err_flags, c->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
+    for (int i = 0; i < PSK_HOST_STREAMS; i++) CK(cudaStreamSynchronize(c->streams[i]));
+    if (host_err_flags && *host_err_flags) CK(cudaMemset(c->d_err, 0, sizeof(int32_t)));
     return PSK_OK;
 }
 

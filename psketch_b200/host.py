@@ -58,7 +58,7 @@ class HostCraft(object):
         ia[:, _lib.AG_X], ia[:, _lib.AG_Y] = init_pos[:, 0], init_pos[:, 1]
         ia[:, _lib.AG_DIR] = 0 if init_dir is None else np.asarray(init_dir)
         ia[:, _lib.AG_TASK] = np.asarray(task)
-        ia[:, _lib.AG_TIMER] = max_timesteps
+        ia[:, _lib.AG_TIMER] = _lib.check_max_timesteps(max_timesteps)
         ctx = ctypes.c_void_p()
         _lib.check(self.lib.psk_craft_host_create(ctypes.byref(self.ct), n, chunk_envs,
                                                   ctypes.byref(ctx)), "psk_craft_host_create")
@@ -82,8 +82,28 @@ class HostCraft(object):
         self.agent[:] = ia
         self.stats = np.zeros(4, np.uint64)
         self.err = np.zeros(1, np.int32)
+        self.resident = False
+        self._features_u8 = None
+        self.last_h2d = self.last_d2h = 0
+
+    def _raise_flags(self):
+        """What the reference would have raised (worlds/craft.py:415-416, demonstration.py:18)."""
+        flags = int(self.err[0])
+        if not flags:
+            return
+        self.err[0] = 0
+        if flags & _lib.FLAG_BAD_ACTION:
+            raise Exception("Unexpected action")
+        if flags & _lib.FLAG_BAD_LEAF:
+            raise AssertionError("teacher: subtask is neither 'use' nor 'go'")
+        if flags & _lib.FLAG_INV_OVERFLOW:
+            raise OverflowError("inventory count above 255")
+        raise _lib.PskError("kernel error flags 0x%x" % flags)
 
     def tick(self, actions=None, want_features=True):
+        """State round trip per call (psk_craft_host_tick): grid / agent go up, come back advanced."""
+        if self.resident:
+            raise _lib.PskError("state is resident on the device: use tick_resident() or download()")
         if actions is not None:
             self.action[:] = actions
         rc = self.lib.psk_craft_host_tick(
@@ -93,8 +113,55 @@ class HostCraft(object):
             _np_ptr(self.done), _np_ptr(self.success), self.n, _np_ptr(self.stats),
             _np_ptr(self.err))
         _lib.check(rc, "psk_craft_host_tick")
-        if self.err[0] & _lib.FLAG_BAD_ACTION:
-            raise Exception("Unexpected action")
+        self.last_h2d = self.h2d_bytes + (self.n if actions is not None else 0)
+        self.last_d2h = self.d2h_bytes - (0 if want_features else self.n * self.n_features * 4)
+        self._raise_flags()
+        return self.expert
+
+    # ---- resident mode: the environments stay in HBM between ticks
+    def reset_resident(self):
+        """Every env at its episode start, on the device (world.init_state for the batch)."""
+        _lib.check(self.lib.psk_craft_host_reset(self.ctx, self.n), "psk_craft_host_reset")
+        self.resident = True
+
+    def upload(self):
+        """Host state (self.grid / self.agent) -> device; switches to resident mode."""
+        _lib.check(self.lib.psk_craft_host_put_state(self.ctx, _np_ptr(self.grid),
+                                                     _np_ptr(self.agent), self.n),
+                   "psk_craft_host_put_state")
+        self.resident = True
+
+    def download(self, keep_resident=True):
+        """Device state -> self.grid / self.agent (e.g. for state.pos / state.inventory)."""
+        _lib.check(self.lib.psk_craft_host_get_state(self.ctx, _np_ptr(self.grid),
+                                                     _np_ptr(self.agent), self.n),
+                   "psk_craft_host_get_state")
+        self.resident = keep_resident
+
+    @property
+    def features_u8(self):
+        if self._features_u8 is None:
+            self._pins["features_u8"] = PinnedArray(self.lib, (self.n, self.n_features), np.uint8)
+            self._features_u8 = self._pins["features_u8"].array
+        return self._features_u8
+
+    def tick_resident(self, actions=None, features="f32"):
+        """psk_craft_host_tick_resident: only actions go up; features (``"f32"`` -> self.features,
+        ``"u8"`` -> self.features_u8, None), teacher actions and flags come down."""
+        if not self.resident:
+            self.upload()
+        if actions is not None:
+            self.action[:] = actions
+        fmt = {None: _lib.FEATURES_NONE, "f32": _lib.FEATURES_F32, "u8": _lib.FEATURES_U8}[features]
+        buf = self.features if features == "f32" else (self.features_u8 if features == "u8" else None)
+        rc = self.lib.psk_craft_host_tick_resident(
+            self.ctx, _np_ptr(self.action) if actions is not None else None, _np_ptr(buf), fmt,
+            _np_ptr(self.expert), _np_ptr(self.done), _np_ptr(self.success), self.n,
+            _np_ptr(self.stats), _np_ptr(self.err))
+        _lib.check(rc, "psk_craft_host_tick_resident")
+        self.last_h2d = self.n if actions is not None else 0
+        self.last_d2h = self.n * 3 + (0 if buf is None else buf.nbytes) + 36
+        self._raise_flags()
         return self.expert
 
     @property

@@ -44,7 +44,7 @@ class VecCraft(object):
         self.C = self.W * self.H
         self.cell_stride = ((self.C + 63) // 64) * 64
         self.n_features = self.tables.n_features
-        self.max_timesteps = int(max_timesteps)
+        self.max_timesteps = _lib.check_max_timesteps(max_timesteps)
         dev = self.device
         self.grid = torch.zeros((self.n, self.cell_stride), dtype=torch.uint8, device=dev)
         self.agent = torch.zeros((self.n, _lib.AGENT_BYTES), dtype=torch.uint8, device=dev)
@@ -150,6 +150,17 @@ class VecCraft(object):
             rc = self.lib.psk_craft_features(ctypes.byref(self.ct), self._state(), _ptr(out),
                                              int(impl), self._stream())
         _lib.check(rc, "psk_craft_features")
+        return out
+
+    def features_u8(self, out=None):
+        """The feature rows as bytes, u8[N, n_features] (psk_craft_features_u8): every feature is an
+        exact integer <= 255, so ``out.float()`` equals ``features()``."""
+        if out is None:
+            out = torch.empty((self.n, self.n_features), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.psk_craft_features_u8(ctypes.byref(self.ct), self._state(), _ptr(out),
+                                                self._stream())
+        _lib.check(rc, "psk_craft_features_u8")
         return out
 
     def satisfies(self, task=None):

@@ -332,10 +332,120 @@ def test_random_actions_are_uniform_and_reproducible(medium_tables, medium_state
     assert np.abs(hist - 1 / 6).max() < 0.005
 
 
+class _OracleTicks(object):
+    """The rollout loop body of trainers/imitation.py:42-73 (with auto-reset) on the CPU oracle, one
+    tick at a time, with the per-env done / success flags the kernels also report."""
+
+    def __init__(self, oracle, grids, ienv, ipos, itask, max_timesteps=40):
+        self.o, self.T = oracle, max_timesteps
+        n = len(ienv)
+        self.init_grid = np.ascontiguousarray(grids[np.asarray(ienv).astype(np.int64)])
+        self.init_pos = np.asarray(ipos).astype(np.int32)
+        self.task = np.asarray(itask).astype(np.int32)
+        self.grid = self.init_grid.copy()
+        self.inv = np.zeros((n, oracle.K), np.int32)
+        self.pos = self.init_pos.copy()
+        self.dir = np.zeros(n, np.int32)
+        self.timer = np.full(n, max_timesteps, np.int32)
+        self.stats = np.zeros(3, np.int64)
+
+    def tick(self, actions=None, want_features=True):
+        o = self.o
+        expert, _, _ = o.expert(self.grid, self.inv, self.pos, self.dir, self.task)
+        feats = o.features(self.grid, self.inv, self.pos, self.dir) if want_features else None
+        act = expert if actions is None else np.asarray(actions).astype(np.int32)
+        self.timer -= 1
+        done = (act == 5) | (self.timer <= 0)
+        succ = done & (o.satisfies(self.grid, self.inv, self.pos, self.dir, self.task) == 1)
+        g2, i2, p2, d2, _ = o.step(self.grid, self.inv, self.pos, self.dir, np.where(done, 5, act).astype(np.int32))
+        self.grid = np.where(done[:, None], self.init_grid, g2)
+        self.inv = np.where(done[:, None], 0, i2).astype(np.int32)
+        self.pos = np.where(done[:, None], self.init_pos, p2).astype(np.int32)
+        self.dir = np.where(done, 0, d2).astype(np.int32)
+        self.timer = np.where(done, self.T, self.timer).astype(np.int32)
+        self.stats += (int(done.sum()), int(succ.sum()), len(done))
+        return dict(expert=expert.astype(np.uint8), done=done.astype(np.uint8),
+                    success=succ.astype(np.uint8), features=feats)
+
+    def assert_state_equals(self, env):
+        assert np.array_equal(_np(env.cells), self.grid)
+        assert np.array_equal(_np(env.inventory).astype(np.int32), self.inv)
+        assert np.array_equal(_np(env.pos).astype(np.int32), self.pos)
+        assert np.array_equal(_np(env.dir).astype(np.int32), self.dir)
+        assert np.array_equal(_np(env.timer).astype(np.int32), self.timer)
+        st = _np(env.stats)
+        assert (st[0], st[1], st[2]) == tuple(self.stats)
+
+
+_ROLLOUT_REF = {}
+
+
+def _rollout_reference(n, T, splits, oracle):
+    """Oracle outputs of T teacher-driven ticks on the bench workload (train split tiled to n envs),
+    computed once per size and shared by every kernel variant.  Features are kept as u8 (every
+    feature is an exact integer <= 255; the test checks that on the GPU side)."""
+    if n not in _ROLLOUT_REF:
+        idx = np.arange(n) % 17600
+        orc = _OracleTicks(oracle, splits["train_grids"], splits["train_inst_env"][idx],
+                           splits["train_inst_pos"][idx], splits["train_inst_task"][idx])
+        ticks = []
+        for _ in range(T):
+            r = orc.tick()
+            assert r["features"].max() <= 255 and np.array_equal(r["features"], np.floor(r["features"]))
+            r["features"] = r["features"].astype(np.uint8)
+            ticks.append(r)
+        _ROLLOUT_REF.clear()            # one size at a time: a 196,608-env reference holds 0.6 GB
+        _ROLLOUT_REF[n] = (idx, ticks, orc)
+    return _ROLLOUT_REF[n]
+
+
+# (rollout_variant, rollout_tma): 0 = 64 env threads + 2 feature warps, 2 = 32 + 2 (what bench.py
+# times at 65,536 envs: craft_rollout_kernel<8,8,3,32,2,21,0>), 3 = 16 + 2, 4 = 16 + 1
+ROLLOUT_VARIANTS = [(2, 0), (2, 1), (0, 0), (0, 1), (3, 0), (3, 1), (4, 0), (4, 1), (-1, -1)]
+
+
+@pytest.mark.parametrize("n", [65536, 65536 + 37, 196608])
+def test_rollout_kernel_variants_vs_oracle(n, splits, medium_tables, medium_oracle):
+    """Every instantiation of craft_rollout_kernel the dispatcher can select — forced through
+    psk_set_tuning — on BASELINE config 2's workload and size (and a ragged and a 3x size), T = 8
+    ticks per launch into a 9-frame ring exactly as bench.py launches it: expert / done / success /
+    features of EVERY tick, the final state and the counters against the CPU oracle
+    (trainers/imitation.py:42-73, make_data.py:146-152)."""
+    from psketch_b200 import _lib
+    from psketch_b200.vec import VecCraft
+    T, RING = 8, 9
+    idx, ref, orc = _rollout_reference(n, T, splits, medium_oracle)
+    args = (medium_tables, splits["train_grids"], splits["train_inst_env"][idx],
+            splits["train_inst_pos"][idx], splits["train_inst_task"][idx])
+    ring = torch.empty((RING, n, 404), dtype=torch.float32, device="cuda")
+    try:
+        for variant, tma in ROLLOUT_VARIANTS:
+            _lib.set_tuning(rollout_variant=variant, rollout_tma=tma)
+            env = VecCraft.from_instances(*args, max_timesteps=40)
+            ring.fill_(-1.0)
+            out = env.rollout(T, features_out=ring)
+            torch.cuda.synchronize()
+            tag = "variant %d tma %d" % (variant, tma)
+            for t in range(T):
+                r = ref[t]
+                assert np.array_equal(_np(out["expert"][t]), r["expert"]), (tag, t)
+                assert np.array_equal(_np(out["done"][t]), r["done"]), (tag, t)
+                assert np.array_equal(_np(out["success"][t]), r["success"]), (tag, t)
+                f8 = ring[t].to(torch.uint8)
+                assert torch.equal(f8.to(torch.float32), ring[t]), (tag, t)   # exact small integers
+                assert np.array_equal(_np(f8), r["features"]), (tag, t)
+            assert bool((ring[T] == -1.0).all()), tag                         # slot 8 untouched
+            orc.assert_state_equals(env)
+            env.check_errors()
+    finally:
+        _lib.set_tuning(rollout_variant=-1, rollout_tma=-1)
+
+
 @pytest.mark.parametrize("n,with_actions", [(6007, False), (4099, True), (65, False)])
-def test_multi_tick_rollout_equals_single_ticks(n, with_actions, splits, medium_tables):
+def test_multi_tick_rollout_equals_single_ticks(n, with_actions, splits, medium_tables, medium_oracle):
     """psk_craft_rollout (tick loop inside the kernel, state in shared memory) against the same
-    number of psk_craft_tick launches: every per-tick output, the final state and the counters."""
+    number of psk_craft_tick launches AND against the oracle advanced tick by tick: every per-tick
+    output, the final state and the counters."""
     from psketch_b200.vec import VecCraft
     rng = np.random.RandomState(n)
     idx = rng.randint(0, 2200, size=n)
@@ -350,12 +460,19 @@ def test_multi_tick_rollout_equals_single_ticks(n, with_actions, splits, medium_
         acts = torch.from_numpy(rng.choice(6, size=(T, n), p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8)).to(a.device)
     feats = torch.empty((T, n, 404), dtype=torch.float32, device=a.device)
     out = a.rollout(T, actions=acts, features_out=feats)
+    orc = _OracleTicks(medium_oracle, grids, args[2], args[3], args[4], max_timesteps=15)
     for t in range(T):
         o = b.tick(actions=None if acts is None else acts[t], fused=bool(t % 2))
         assert torch.equal(out["expert"][t], o["expert"]), t
         assert torch.equal(out["done"][t], o["done"]), t
         assert torch.equal(out["success"][t], o["success"]), t
         assert torch.equal(feats[t], o["features"]), t
+        ref = orc.tick(None if acts is None else _np(acts[t]))
+        assert np.array_equal(_np(out["expert"][t]), ref["expert"]), t
+        assert np.array_equal(_np(out["done"][t]), ref["done"]), t
+        assert np.array_equal(_np(out["success"][t]), ref["success"]), t
+        assert np.array_equal(_np(feats[t]), ref["features"]), t
+    orc.assert_state_equals(a)
     assert torch.equal(a.grid, b.grid) and torch.equal(a.agent, b.agent)
     assert torch.equal(a.stats, b.stats) and int(a.stats[2]) == T * n and int(a.stats[0]) > 0
     # ring of two feature slots: the last two ticks survive
@@ -518,3 +635,85 @@ def test_million_env_rollout_kernel(splits, medium_tables, medium_oracle):
     assert s[2] == T * n and s[0] == s[1] == int((T // ref_len).sum())
     assert int(out["done"].sum()) == s[0] and int(out["success"].sum()) == s[1]
     env.check_errors()
+
+
+@pytest.mark.parametrize("features", ["f32", "u8", None])
+def test_host_resident_tick_matches_oracle(features, splits, medium_tables, medium_oracle):
+    """psk_craft_host_tick_resident: the environments stay on the device, only actions go up and
+    features (f32 or the compact u8 frame) / teacher actions / flags come down; student-style
+    random actions on even ticks, the teacher's on odd ones."""
+    from psketch_b200.host import HostCraft
+    n = 5003
+    rng = np.random.RandomState(11)
+    idx = rng.randint(0, 2200, size=n)
+    grids = splits["dev_grids"]
+    ienv, ipos, itask = (splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
+                         splits["dev_inst_task"][idx])
+    env = HostCraft(medium_tables, grids, ienv, ipos, itask, max_timesteps=17, chunk_envs=1024)
+    env.reset_resident()
+    orc = _OracleTicks(medium_oracle, grids, ienv, ipos, itask, max_timesteps=17)
+    for t in range(40):
+        a = rng.choice(6, size=n, p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8) if t % 2 == 0 else None
+        env.tick_resident(actions=a, features=features)
+        ref = orc.tick(a)
+        assert np.array_equal(env.expert, ref["expert"]), t
+        assert np.array_equal(env.done, ref["done"]), t
+        assert np.array_equal(env.success, ref["success"]), t
+        if features == "f32":
+            assert np.array_equal(env.features, ref["features"]), t
+        elif features == "u8":
+            assert np.array_equal(env.features_u8.astype(np.float32), ref["features"]), t
+    assert tuple(int(x) for x in env.stats[:3]) == tuple(orc.stats)
+    env.download()
+    assert np.array_equal(env.grid[:, :64], orc.grid)
+    assert np.array_equal(env.agent[:, :21].astype(np.int32), orc.inv)
+    assert np.array_equal(env.agent[:, 24:26].astype(np.int32), orc.pos)
+    assert np.array_equal(env.agent[:, 28].astype(np.int32), orc.timer)
+    # a bad action surfaces as the reference's exception
+    with pytest.raises(Exception, match="Unexpected action"):
+        env.tick_resident(actions=np.full(n, 6, np.uint8), features=None)
+    env.close()
+
+
+@pytest.mark.parametrize("which", ["medium", "large", "custom"])
+def test_features_u8_equals_features(which, medium_tables, medium_states, large_tables, large_states,
+                                     custom_tables, custom_states):
+    tables, S = {"medium": (medium_tables, medium_states), "large": (large_tables, large_states),
+                 "custom": (custom_tables, custom_states)}[which]
+    for n in (len(S["grid"]), 4099, 3, 1):
+        sub = {k: S[k][:n] for k in ("grid", "inv", "pos", "dir")}
+        env = _env_from_states(tables, sub)
+        f8 = env.features_u8()
+        assert f8.dtype == torch.uint8 and tuple(f8.shape) == (n, tables.n_features)
+        assert np.array_equal(_np(f8).astype(np.float32), S["features"][:n].astype(np.float32))
+
+
+def test_step_kernel_variants(medium_tables, medium_states):
+    """craft_step_kernel with the tables staged in shared memory (round-1 shape, step_variant 0) and
+    read through the read-only path (default): same results on every exported state and action."""
+    from psketch_b200 import _lib
+    S = medium_states
+    n = len(S["grid"])
+    try:
+        for variant in (0, -1):
+            _lib.set_tuning(step_variant=variant)
+            env = _env_from_states(medium_tables, S)
+            snap = env.snapshot()
+            for a in range(6):
+                env.restore(snap)
+                env.step(torch.full((n,), a, dtype=torch.uint8))
+                assert np.array_equal(_np(env.cells), S["step_grid"][:, a]), (variant, a)
+                assert np.array_equal(_np(env.inventory), S["step_inv"][:, a]), (variant, a)
+                assert np.array_equal(_np(env.pos), S["step_pos"][:, a]), (variant, a)
+                assert np.array_equal(_np(env.dir), S["step_dir"][:, a]), (variant, a)
+            env.check_errors()
+    finally:
+        _lib.set_tuning(step_variant=-1)
+
+
+def test_max_timesteps_is_validated(medium_tables, medium_states):
+    S = {k: medium_states[k][:4] for k in ("grid", "inv", "pos", "dir")}
+    from psketch_b200.vec import VecCraft
+    for bad in (0, 256, 1000):
+        with pytest.raises(ValueError, match="max_timesteps"):
+            VecCraft.from_states(medium_tables, S["grid"], S["inv"], S["pos"], S["dir"], max_timesteps=bad)
