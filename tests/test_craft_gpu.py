@@ -680,7 +680,7 @@ def test_features_u8_equals_features(which, medium_tables, medium_states, large_
                                      custom_tables, custom_states):
     tables, S = {"medium": (medium_tables, medium_states), "large": (large_tables, large_states),
                  "custom": (custom_tables, custom_states)}[which]
-    for n in (len(S["grid"]), 4099, 3, 1):
+    for n in (len(S["grid"]), 1999, 3, 1):
         sub = {k: S[k][:n] for k in ("grid", "inv", "pos", "dir")}
         env = _env_from_states(tables, sub)
         f8 = env.features_u8()
