@@ -1,0 +1,244 @@
+"""BASELINE config 4 — the reference's OWN trainer, student and model, unchanged, on this repo's
+drop-in world and teacher.  TEST INFRASTRUCTURE, build container only (imports /root/reference).
+
+    python -m oracle.gen_config4 [--iters 30] [--log-every 15]        # ~2-4 minutes
+
+Runs ``trainers.imitation.ImitationTrainer.train`` (trainers/imitation.py:103-180) with
+``students.imitation.ImitationStudent`` + ``models.lstm_seq2seq.LSTMSeq2SeqModel`` on the CPU for a
+few DAgger iterations (configs/experiments/imitation.yaml, seed 123, batch 32, evaluation on the whole
+dev split every ``log_every`` iterations), twice with identical seeds:
+
+  (a) on the reference's world and teacher  (worlds.load / teachers.load of the reference);
+  (b) with ONLY those two factories swapped for psketch_b200.worlds.load / psketch_b200.teachers.load
+       — in this container the façade's device backend is the oracle-backed test
+      double of tests/test_facade_cpu.py (no GPU here); tests/test_config4_gpu.py replays (b) with the
+      CUDA backend on the GPU box.
+
+and asserts that (a) and (b) agree on everything the trainer and the student ever saw or produced:
+the batches, every feature vector (hashed), every sampled / greedy action, every teacher label, the
+loss of every iteration (bit-equal floats), success flags, distances, counters and the evaluation
+trajectories.  The record of (a) is committed as tests/golden/config4_imitation.npz.
+"""
+import argparse
+import hashlib
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def feature_hash(feats_f32):
+    """64 bits of SHA-1 over the float32 feature block the student consumed at one timestep."""
+    return np.frombuffer(hashlib.sha1(np.ascontiguousarray(feats_f32, np.float32).tobytes()).digest()[:8],
+                         np.uint64)[0]
+
+
+def prepare_data(regen_dir, data_dir):
+    """The three split files where data.load expects them (data/dataset.py:17-18).  The train split is
+    missing from the reference checkout and is regenerated with the reference's make_data.py; its
+    Task.__str__ prints 'get wood' where the loader wants 'get[wood]' (SURVEY §0), so the task
+    strings are rewritten — data preparation, the loader itself is untouched."""
+    if not os.path.exists(os.path.join(regen_dir, "craft_medium_train.json")):
+        print("regenerating the dataset with the reference's make_data.py (~30 s)")
+        ref_shim.regenerate_dataset(regen_dir)
+    os.makedirs(data_dir, exist_ok=True)
+    for split in ("train", "dev", "test"):
+        data = json.load(open(os.path.join(regen_dir, "craft_medium_%s.json" % split)))
+        for env in data:
+            for ti in env["task_instances"]:
+                if "[" not in ti["task"]:
+                    ti["task"] = "%s[%s]" % tuple(ti["task"].split(" "))
+        json.dump(data, open(os.path.join(data_dir, "craft_medium_%s.json" % split), "w"))
+
+
+def make_config(data_dir, exp_dir, iters, log_every, seed=123):
+    import torch
+    cfg = ref_shim.make_config("imitation", seed)
+    cfg.data_dir = data_dir
+    cfg.experiment_dir = exp_dir
+    cfg.trainer.max_iters = iters
+    cfg.trainer.log_every = log_every
+    cfg.device = torch.device("cpu")
+    torch.manual_seed(seed)
+    return cfg
+
+
+def run(which, data_dir, iters, log_every, medium_oracle=None):
+    """One training run; returns the record.  ``which``: 'reference' or 'facade'."""
+    import torch
+    ref_shim._install_shims()
+    if ref_shim.REF_ROOT not in sys.path:
+        sys.path.insert(0, ref_shim.REF_ROOT)
+    exp_dir = tempfile.mkdtemp(prefix="psk_config4_")
+    with ref_shim.reference_cwd():
+        import data as ref_data
+        import students as ref_students
+        import teachers as ref_teachers
+        import trainers as ref_trainers
+        import worlds as ref_worlds
+        from students.imitation import ImitationStudent
+        from trainers.imitation import ImitationTrainer
+
+        rec = dict(iters=[], evals=[])
+
+        class RecordingStudent(ImitationStudent):          # the student's code runs unchanged
+            def init(self, tasks, states, is_eval):
+                super().init(tasks, states, is_eval)
+                self.cur = dict(is_eval=is_eval, acts=[], refs=[], fh=[])
+
+            def act(self, states):
+                feats = np.stack([np.asarray(s.features()) for s in states]).astype(np.float32)
+                self.cur["fh"].append(feature_hash(feats))
+                actions = super().act(states)
+                self.cur["acts"].append(list(actions))
+                return actions
+
+            def receive(self, ref_actions):
+                self.cur["refs"].append(list(ref_actions))
+                super().receive(ref_actions)
+
+            def learn(self):
+                loss = super().learn()
+                rec["iters"][-1]["loss"] = loss
+                return loss
+
+        class RecordingTrainer(ImitationTrainer):          # the trainer's code runs unchanged
+            def do_rollout(self, batch, world, student, teacher, is_eval):
+                info = super().do_rollout(batch, world, student, teacher, is_eval)
+                entry = dict(ids=[item["id"] for item in batch], info=info, **student.cur)
+                if is_eval:
+                    rec["evals"][-1].append(entry)
+                else:
+                    rec["iters"].append(entry)
+                return info
+
+            def evaluate(self, dataset, world, student, teacher, save_traj=False):
+                rec["evals"].append([])
+                return super().evaluate(dataset, world, student, teacher, save_traj)
+
+        config = make_config(data_dir, exp_dir, iters, log_every)
+        datasets = ref_data.load(config)                   # also sets config.vocab (data/task.py:63)
+        if which == "reference":
+            world = ref_worlds.load(config)
+            teacher = ref_teachers.load(config)
+        else:
+            import psketch_b200.teachers as my_teachers
+            import psketch_b200.worlds as my_worlds
+            world = my_worlds.load(config)                 # the swap of INTEGRATION.md §1 ...
+            teacher = my_teachers.load(config)             # ... and nothing else
+            if medium_oracle is not None:                  # no GPU in this container
+                from test_facade_cpu import OracleBackend
+                world._backend = OracleBackend(world, medium_oracle)
+        assert config.student.model.input_size == 404 and config.student.model.n_actions == 6
+        student = RecordingStudent(config)
+        trainer = RecordingTrainer(config)
+        torch.manual_seed(config.seed)
+        config.random.seed(config.seed)
+        for d in datasets.values():
+            d.item_idx = 0
+        trainer.train(datasets, world, student, teacher)
+    shutil.rmtree(exp_dir, ignore_errors=True)
+    return rec
+
+
+def assert_same(a, b):
+    assert len(a["iters"]) == len(b["iters"]) and len(a["evals"]) == len(b["evals"])
+    rollouts_a = a["iters"] + [e for ev in a["evals"] for e in ev]
+    rollouts_b = b["iters"] + [e for ev in b["evals"] for e in ev]
+    assert len(rollouts_a) == len(rollouts_b)
+    for k, (x, y) in enumerate(zip(rollouts_a, rollouts_b)):
+        assert x["ids"] == y["ids"], k
+        assert x["acts"] == y["acts"], k
+        assert x["refs"] == y["refs"], k
+        assert [int(h) for h in x["fh"]] == [int(h) for h in y["fh"]], k
+        assert x.get("loss") == y.get("loss"), (k, x.get("loss"), y.get("loss"))   # bit-equal floats
+        ix, iy = x["info"], y["info"]
+        assert ix["action_seqs"] == iy["action_seqs"], k
+        assert [bool(v) for v in ix["success"]] == [bool(v) for v in iy["success"]], k
+        assert ix["distances"] == iy["distances"], k
+        assert ix["num_interactions"] == iy["num_interactions"] and ix["num_steps"] == iy["num_steps"], k
+
+
+def pack(rec, splits):
+    """Flat arrays.  Rollout r has B_r envs and T_r timesteps; 2-D blocks are padded to [R, 40, 32]."""
+    id_to_idx = {}
+    for split in ("train", "dev"):
+        for i, v in enumerate(splits[split + "_inst_id"]):
+            id_to_idx[(split, int(v))] = i
+    rollouts = [("train", e) for e in rec["iters"]] + [("dev", e) for ev in rec["evals"] for e in ev]
+    R, TM, BM = len(rollouts), 40, 32
+    out = dict(
+        n_train_iters=np.int32(len(rec["iters"])),
+        eval_sizes=np.asarray([len(ev) for ev in rec["evals"]], np.int32),
+        batch=np.full((R, BM), -1, np.int32), n_env=np.zeros(R, np.int32), n_t=np.zeros(R, np.int32),
+        is_eval=np.zeros(R, np.uint8),
+        acts=np.full((R, TM, BM), 255, np.uint8), refs=np.full((R, TM, BM), -2, np.int8),
+        feat_hash=np.zeros((R, TM), np.uint64), loss=np.full(R, np.nan, np.float64),
+        success=np.zeros((R, BM), np.uint8), seq_len=np.zeros((R, BM), np.uint8),
+        distances=np.full((R, BM), -1, np.int16), n_dist=np.zeros(R, np.int32),
+        num_interactions=np.zeros(R, np.int64), num_steps=np.zeros(R, np.int64))
+    for r, (split, e) in enumerate(rollouts):
+        B, T = len(e["ids"]), len(e["acts"])
+        out["n_env"][r], out["n_t"][r], out["is_eval"][r] = B, T, int(e["is_eval"])
+        for i, id_ in enumerate(e["ids"]):                 # 'instance_10561' -> row of the split
+            out["batch"][r, i] = id_to_idx[(split, int(id_.split("_")[1]))]
+        out["acts"][r, :T, :B] = np.asarray(e["acts"], np.uint8)
+        if e["refs"]:
+            out["refs"][r, :T, :B] = np.asarray(e["refs"], np.int8)
+        out["feat_hash"][r, :T] = e["fh"]
+        if "loss" in e:
+            out["loss"][r] = e["loss"]
+        info = e["info"]
+        out["success"][r, :B] = [bool(v) for v in info["success"]]
+        out["seq_len"][r, :B] = [len(s) for s in info["action_seqs"]]
+        for i, s in enumerate(info["action_seqs"]):        # what was executed (= acts where not done)
+            assert s == [int(a) for a in np.asarray(e["acts"])[:len(s), i]] or not e["is_eval"]
+        out["n_dist"][r] = len(info["distances"])
+        out["distances"][r, :len(info["distances"])] = info["distances"]
+        out["num_interactions"][r], out["num_steps"][r] = info["num_interactions"], info["num_steps"]
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--log-every", type=int, default=15)
+    args = ap.parse_args()
+    regen_dir = os.environ.get("PSK_REGEN_DIR", "/tmp/psk_data")
+    data_dir = os.path.join(regen_dir, "config4_data")
+    prepare_data(regen_dir, data_dir)
+    splits = np.load(os.path.join(OUT, "craft_medium_splits.npz"))
+    import time
+    t0 = time.time()
+    a = run("reference", data_dir, args.iters, args.log_every)
+    t1 = time.time()
+    print("reference world + teacher: %d train rollouts, %d evaluations, %.1f s; losses %s ..." %
+          (len(a["iters"]), len(a["evals"]), t1 - t0, [round(e["loss"], 4) for e in a["iters"][:4]]))
+    from oracle.craft_oracle import CraftOracle
+    from psketch_b200.tables import CraftTables
+    b = run("facade", data_dir, args.iters, args.log_every, medium_oracle=CraftOracle(CraftTables()))
+    print("psketch_b200 world + teacher (oracle-backed backend): %.1f s" % (time.time() - t1))
+    assert_same(a, b)
+    print("IDENTICAL: batches, features, actions, teacher labels, losses, success, distances, eval trajectories")
+    out = pack(a, splits)
+    path = os.path.join(OUT, "config4_imitation.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes;",
+          "train success %.3f" % np.mean([np.mean([bool(v) for v in e["info"]["success"]]) for e in a["iters"]]),
+          "dev success per evaluation", [float(np.mean([np.mean([bool(v) for v in e["info"]["success"]]) for e in ev])) for ev in a["evals"]])
+
+
+if __name__ == "__main__":
+    main()

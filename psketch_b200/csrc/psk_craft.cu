@@ -80,32 +80,82 @@ __device__ __forceinline__ void step_env(const TAB &st, Agent &a, uint8_t *row,
     }
 }
 
-// STAGED = true: tables staged in shared memory by the CTA (256-thread CTAs, the round-1 kernel);
-// false: kind classes / recipes read through the read-only path from the device copy, no shared
-// memory and no CTA barrier, 64-thread CTAs so that 65,536 envs spread over all SMs (the kernel
-// is launch-latency bound at that size: 13 MB of traffic).
-template <int W, int H, bool STAGED>
-__global__ void __launch_bounds__(STAGED ? 256 : 64)
+// MODE 0: tables staged in shared memory by the CTA, 256-thread CTAs (the round-1 kernel).
+// MODE 1: kind classes / recipes read through the read-only path from the device copy — no table
+//         staging, no CTA barrier — 64-thread CTAs so that 65,536 envs spread over all SMs.
+// MODE 2: MODE 1 + the warp's 32 grid rows (32 x 64 B, contiguous) copied to shared memory with
+//         coalesced 128-bit loads issued TOGETHER with the agent loads, instead of one dependent
+//         byte gather after the agent record has arrived: one DRAM round trip instead of two (the
+//         kernel is latency-bound at 65,536 envs: 13 MB of traffic), and no extra DRAM traffic —
+//         the byte gather already pulled a 32-byte sector of every row.  Rows of 64 bytes only.
+// All modes: programmatic dependent launch — the grid may be scheduled while its predecessor in
+// the stream drains; nothing is read or written before griddepcontrol.wait.
+template <int W, int H, int MODE>
+__global__ void __launch_bounds__(MODE == 0 ? 256 : 64)
 craft_step_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                   uint8_t *__restrict__ agent, const uint8_t *__restrict__ action,
                   const uint8_t *__restrict__ active, float *__restrict__ reward,
                   int32_t *err_flags, int64_t n, int cell_stride) {
+    constexpr int CP = ((W * H + 63) / 64) * 64;
+    static_assert(MODE != 2 || CP == 64, "row preload is built for 64-byte rows");
+    __shared__ __align__(16) uint8_t s_rows[MODE == 2 ? 64 * CP : 16];
+    asm volatile("griddepcontrol.launch_dependents;");
     uint32_t flags = 0;
     auto body = [&](const auto &tab) {
-        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
-             e += (int64_t)gridDim.x * blockDim.x) {
-            if (reward) reward[e] = 0.0f;  // craft.py:338,424
-            if (active && !active[e]) continue;
-            Agent a = load_agent(agent, e);
-            const Agent before = a;
-            step_env<W, H>(tab, a, grid + e * cell_stride, grid + e * cell_stride, action[e], flags);
-            bool changed = false;
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int lane = threadIdx.x & 31;
+        // whole warps iterate so that the cooperative row copy of MODE 2 stays converged
+        for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < n;
+             base += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t e = base + lane;
+            const bool valid = e < n;
+            const uint8_t *rd = grid + e * cell_stride;
+            if (MODE == 2) {
+                uint8_t *wrows = s_rows + (threadIdx.x & ~31) * CP;
+                const uint4 *g = reinterpret_cast<const uint4 *>(grid + base * CP);
+                const int64_t lim = (n - base < 32 ? n - base : 32) * (CP / 16);
+                uint4 v[CP / 16];
 #pragma unroll
-            for (int i = 0; i < 8; i++) changed |= a.w[i] != before.w[i];
-            if (changed) store_agent(agent, e, a);
+                for (int i = 0; i < CP / 16; i++)
+                    if (i * 32 + lane < lim) v[i] = g[i * 32 + lane];
+                Agent a0;
+                int act0 = PSK_ACT_STOP;
+                bool on = valid;
+                if (valid) {                                // in flight together with the rows
+                    a0 = load_agent(agent, e);
+                    act0 = action[e];
+                    if (active) on = active[e] != 0;
+                }
+                __syncwarp();                               // previous iteration's readers are done
+#pragma unroll
+                for (int i = 0; i < CP / 16; i++)
+                    if (i * 32 + lane < lim) reinterpret_cast<uint4 *>(wrows)[i * 32 + lane] = v[i];
+                __syncwarp();
+                rd = wrows + lane * CP;
+                if (!valid) continue;
+                if (reward) reward[e] = 0.0f;  // craft.py:338,424
+                if (!on) continue;
+                Agent a = a0;
+                step_env<W, H>(tab, a, grid + e * cell_stride, rd, act0, flags);
+                bool changed = false;
+#pragma unroll
+                for (int i = 0; i < 8; i++) changed |= a.w[i] != a0.w[i];
+                if (changed) store_agent(agent, e, a);
+            } else {
+                if (!valid) continue;
+                if (reward) reward[e] = 0.0f;  // craft.py:338,424
+                if (active && !active[e]) continue;
+                Agent a = load_agent(agent, e);
+                const Agent before = a;
+                step_env<W, H>(tab, a, grid + e * cell_stride, rd, action[e], flags);
+                bool changed = false;
+#pragma unroll
+                for (int i = 0; i < 8; i++) changed |= a.w[i] != before.w[i];
+                if (changed) store_agent(agent, e, a);
+            }
         }
     };
-    if constexpr (STAGED) {
+    if constexpr (MODE == 0) {
         __shared__ SharedTables sst;
         stage_tables(sst, T);
         body(sst);
@@ -1765,13 +1815,31 @@ template <int W, int H, int WIN> struct Config {
     static int step(const psk_craft_tables *t, psk_craft_state s, const uint8_t *action,
                     const uint8_t *active, float *reward, int32_t *err, cudaStream_t st) {
         PSK_DT(dt);
-        if (tune(TUNE_STEP_VARIANT) == 0)
-            craft_step_kernel<W, H, true><<<grid_for(s.n, 256, 8), 256, 0, st>>>(
-                dt, s.grid, s.agent, action, active, reward, err, s.n, s.cell_stride);
-        else
-            craft_step_kernel<W, H, false><<<grid_for(s.n, 64, 32), 64, 0, st>>>(
-                dt, s.grid, s.agent, action, active, reward, err, s.n, s.cell_stride);
-        return check(cudaGetLastError());
+        // step_variant: 0 staged tables, 1 read-only-path tables, 2 (default for 64-byte rows) + row preload
+        int mode = tune(TUNE_STEP_VARIANT);
+        if (mode < 0 || mode > 2) mode = CP == 64 ? 2 : 1;
+        if (mode == 2 && CP != 64) mode = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(mode == 0 ? 256 : 64);
+        cfg.gridDim = dim3((unsigned)(mode == 0 ? grid_for(s.n, 256, 8) : grid_for(s.n, 64, 32)));
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = tune(TUNE_TICK_PDL) != 0 ? 1 : 0;
+        const int cell_stride = s.cell_stride;
+        const int64_t n = s.n;
+        if (mode == 0)
+            return check(cudaLaunchKernelEx(&cfg, craft_step_kernel<W, H, 0>, dt, s.grid, s.agent, action,
+                                            active, reward, err, n, cell_stride));
+        if constexpr (CP == 64) {
+            if (mode == 2)
+                return check(cudaLaunchKernelEx(&cfg, craft_step_kernel<W, H, 2>, dt, s.grid, s.agent,
+                                                action, active, reward, err, n, cell_stride));
+        }
+        return check(cudaLaunchKernelEx(&cfg, craft_step_kernel<W, H, 1>, dt, s.grid, s.agent, action,
+                                        active, reward, err, n, cell_stride));
     }
     static int satisfies(const psk_craft_tables *t, psk_craft_state s, const uint8_t *task,
                          uint8_t *out, cudaStream_t st) {

@@ -7,11 +7,7 @@
 ``state`` is a psketch_b200.worlds.craft.CraftState; the action for the state's current task is
 normally already cached by the batched flush that produced the state.
 """
-import ctypes
-
-import numpy as np
-
-from .. import _lib
+import numpy as np  # noqa: F401
 
 
 class BaseTeacher(object):
@@ -36,30 +32,8 @@ class BaseTeacher(object):
         """(goal_pos, action_seq) of the closest cell holding ``task.goal_arg``; (last goal cell,
         None) when none is reachable; (None, None) when the kind is absent."""
         world = state.world
-        be = world.backend()
-        torch = be.torch
         kind = world.cookbook.index[task.goal_arg] or 0
-        grid = np.zeros((1, be.cs), np.uint8)
-        grid[0, :be.C] = state.cells
-        agent = np.array(state._agent, np.uint8).reshape(1, _lib.AGENT_BYTES)
-        with torch.cuda.device(be.device):
-            stream = ctypes.c_void_p(torch.cuda.current_stream(be.device).cuda_stream)
-            d_grid = torch.from_numpy(grid).to(be.device)
-            d_agent = torch.from_numpy(agent).to(be.device)
-            d_kind = torch.full((1,), kind, dtype=torch.uint8, device=be.device)
-            d_goal = torch.empty((1, 2), dtype=torch.uint8, device=be.device)
-            d_len = torch.empty(1, dtype=torch.int16, device=be.device)
-            d_seq = torch.empty((1, seq_cap), dtype=torch.uint8, device=be.device)
-            st = _lib.CraftStateC(d_grid.data_ptr(), d_agent.data_ptr(), 1, be.cs, 0)
-            rc = be.lib.psk_craft_find_closest(ctypes.byref(be.ct), st,
-                                               ctypes.c_void_p(d_kind.data_ptr()),
-                                               ctypes.c_void_p(d_goal.data_ptr()),
-                                               ctypes.c_void_p(d_len.data_ptr()),
-                                               ctypes.c_void_p(d_seq.data_ptr()), seq_cap, stream)
-            _lib.check(rc, "psk_craft_find_closest")
-            goal = d_goal.cpu().numpy()[0]
-            length = int(d_len.cpu().numpy()[0])
-            seq = d_seq.cpu().numpy()[0]
+        goal, length, seq = world.backend().find_closest(state.cells, state._agent, kind, seq_cap)
         goal_pos = None if goal[0] == 255 else (int(goal[0]), int(goal[1]))
         if length < 0:
             return goal_pos, None

@@ -42,10 +42,24 @@ def _cfg_get(config, path, default=None):
     return cur
 
 
+def _given_file(path, packaged_default):
+    """A path from the config: the file itself when it exists; None (= the tables embedded in
+    psketch_b200.tables, which ARE the reference's resources/craft files) only when the config names
+    the reference's stock file and the process does not run from a reference checkout; a path the
+    user typed that does not exist raises like the reference's open() (worlds/cookbook.py:9)."""
+    if not path:
+        return None
+    if os.path.exists(path):
+        return path
+    if os.path.normpath(path) == os.path.normpath(packaged_default):
+        return None
+    raise FileNotFoundError(path)
+
+
 class CraftWorld(object):
     def __init__(self, config=None, tables=None, device=None):
         recipes = _cfg_get(config, "recipes")
-        cookbook = Cookbook(recipes if recipes and os.path.exists(recipes) else None)
+        cookbook = Cookbook(_given_file(recipes, "resources/craft/recipes.yaml"))
         world_name = _cfg_get(config, "world.config", "craft_medium")
         world_file = os.path.join("configs/worlds", "%s.yaml" % world_name)
         if os.path.exists(world_file):
@@ -57,7 +71,7 @@ class CraftWorld(object):
         for k, v in world_cfg.items():          # worlds/craft.py:64-67
             setattr(self, k, v)
         hints = _cfg_get(config, "trainer.hints")
-        tm = TaskManager(hints if hints and os.path.exists(hints) else None)
+        tm = TaskManager(_given_file(hints, "resources/craft/hints.hierarchy.yaml"))
         self.tables = tables if tables is not None else CraftTables(cookbook, tm, world_cfg)
         self.cookbook = self.tables.cookbook
         self.task_manager = self.tables.task_manager
@@ -342,6 +356,7 @@ class _Backend(object):
         self.nf = world.tables.n_features
         self.K = world.tables.K
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.h_err = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.T = world.tables.n_tasks - 1                      # task ids 1..T
         self.task_ids = torch.arange(1, self.T + 1, dtype=torch.uint8, device=self.device)
 
@@ -360,6 +375,29 @@ class _Backend(object):
         self.d_feat = torch.zeros(cap * self.nf, dtype=torch.float32, device=self.device)
         self.h_np, self.h_feat_np = self.h_blob.numpy(), self.h_feat.numpy()
         self.cap = cap
+
+    def find_closest(self, cells, agent, kind, seq_cap=96):
+        """BaseTeacher.find_closest_resources (teachers/base.py:27-34) for one state: (goal u8[2],
+        path length or -1, action sequence u8[seq_cap] padded with 255) from psk_craft_find_closest."""
+        import ctypes
+        torch = self.torch
+        grid = np.zeros((1, self.cs), np.uint8)
+        grid[0, :self.C] = cells
+        agent = np.array(agent, np.uint8).reshape(1, _lib.AGENT_BYTES)
+        with torch.cuda.device(self.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            d_grid = torch.from_numpy(grid).to(self.device)
+            d_agent = torch.from_numpy(agent).to(self.device)
+            d_kind = torch.full((1,), int(kind), dtype=torch.uint8, device=self.device)
+            d_goal = torch.empty((1, 2), dtype=torch.uint8, device=self.device)
+            d_len = torch.empty(1, dtype=torch.int16, device=self.device)
+            d_seq = torch.empty((1, seq_cap), dtype=torch.uint8, device=self.device)
+            st = _lib.CraftStateC(d_grid.data_ptr(), d_agent.data_ptr(), 1, self.cs, 0)
+            p = lambda t: ctypes.c_void_p(t.data_ptr())
+            rc = self.lib.psk_craft_find_closest(ctypes.byref(self.ct), st, p(d_kind), p(d_goal),
+                                                 p(d_len), p(d_seq), seq_cap, stream)
+            _lib.check(rc, "psk_craft_find_closest")
+            return d_goal.cpu().numpy()[0], int(d_len.cpu().numpy()[0]), d_seq.cpu().numpy()[0]
 
     def evaluate(self, states, step=True):
         """step=True: ``states`` are pending children (parent + action); computes their state.
@@ -448,7 +486,18 @@ class _Backend(object):
             lo = 0 if step else off_s + 2 * n64
             self.h_blob[lo:end].copy_(self.d_blob[lo:end], non_blocking=True)
             self.h_feat[:n * nf].copy_(self.d_feat[:n * nf], non_blocking=True)
+            self.h_err.copy_(self.err, non_blocking=True)
             cur.synchronize()
+            flags = int(self.h_err.item())
+            if flags:
+                # what the reference does for these conditions: float64 inventories keep counting
+                # (ours are u8), a bad action raises (already rejected in CraftState.step)
+                self.err.zero_()
+                if flags & _lib.FLAG_INV_OVERFLOW:
+                    raise OverflowError("inventory count above 255 (u8 storage; the reference's "
+                                        "float64 inventory has no such limit)")
+                if flags & _lib.FLAG_BAD_ACTION:
+                    raise Exception("Unexpected action")              # worlds/craft.py:415-416
             if all_tasks is not None:
                 all_tasks = all_tasks.cpu().numpy().reshape(2, self.T, len(hintless))
                 for col, i in enumerate(hintless):

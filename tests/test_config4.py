@@ -1,0 +1,109 @@
+"""BASELINE config 4: the record of the reference's own ImitationTrainer.train + ImitationStudent +
+LSTMSeq2SeqModel run (tests/golden/config4_imitation.npz, written by oracle/gen_config4.py from the
+UNMODIFIED reference: 30 DAgger iterations of batch 32 and two evaluations of the whole dev split)
+replayed on this repo's drop-in world and teacher.
+
+gen_config4.py itself runs the reference's trainer/student code twice — on the reference world and on
+the psketch_b200 façade — and asserts bit-identical batches, features, actions, teacher labels and
+losses.  Here the same record drives the façade through the trainer's protocol
+(trainers/imitation.py:18-101, restated in tests/trainer_loop.py) with the student's recorded
+actions, because the reference's student code cannot travel to the GPU box: everything the
+environment and the teacher produced must come out identical — every feature block the student read
+(hashed), every teacher label, success flags, distances, counters."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from trainer_loop import ScriptedStudent, run_protocol
+
+
+def _hash(feats):
+    return np.frombuffer(hashlib.sha1(np.ascontiguousarray(feats, np.float32).tobytes()).digest()[:8],
+                         np.uint64)[0]
+
+
+def _items(world, splits, split, rows):
+    K = world.cookbook.n_kinds
+    out = []
+    for i in rows:
+        ids = splits[split + "_grids"][splits[split + "_inst_env"][i]].reshape(world.WIDTH, world.HEIGHT)
+        onehot = np.zeros((world.WIDTH, world.HEIGHT, K))
+        xs, ys = np.nonzero(ids)
+        onehot[xs, ys, ids[xs, ys]] = 1
+        out.append(dict(grid=onehot, init_pos=tuple(int(v) for v in splits[split + "_inst_pos"][i]),
+                        task=world.task_manager.by_id(int(splits[split + "_inst_task"][i]))))
+    return out
+
+
+def replay(world, teacher, splits, fx, rollouts):
+    n_train = int(fx["n_train_iters"])
+    checked = 0
+    for r in rollouts:
+        B, T, is_eval = int(fx["n_env"][r]), int(fx["n_t"][r]), bool(fx["is_eval"][r])
+        assert is_eval == (r >= n_train)
+        batch = _items(world, splits, "dev" if is_eval else "train", fx["batch"][r, :B])
+        student = ScriptedStudent(fx["acts"][r, :T, :B])
+        got = run_protocol(batch, world, teacher, student, is_eval, 40, 0.0, np.random.RandomState(0))
+        assert student.t == T, r                                   # same number of timesteps
+        for i, seq in enumerate(got["action_seqs"]):
+            L = int(fx["seq_len"][r, i])
+            assert seq == fx["acts"][r, :L, i].tolist(), (r, i)
+        assert [bool(v) for v in got["success"]] == fx["success"][r, :B].astype(bool).tolist(), r
+        assert got["distances"] == fx["distances"][r, :int(fx["n_dist"][r])].tolist(), r
+        assert got["num_interactions"] == int(fx["num_interactions"][r]), r
+        assert got["num_steps"] == int(fx["num_steps"][r]), r
+        assert [int(_hash(f)) for f in student.features] == [int(h) for h in fx["feat_hash"][r, :T]], r
+        if not is_eval:
+            assert np.array_equal(np.asarray(student.received, np.int8), fx["refs"][r, :T, :B]), r
+        checked += 1
+    return checked
+
+
+@pytest.fixture(scope="module")
+def config4():
+    return np.load(os.path.join(GOLDEN, "config4_imitation.npz"))
+
+
+def test_config4_record_is_a_real_training_run(config4):
+    fx = config4
+    n_train = int(fx["n_train_iters"])
+    assert n_train >= 30 and len(fx["eval_sizes"]) == 2 and int(fx["eval_sizes"][0]) == 69   # 2,200 / 32
+    loss = fx["loss"][:n_train]
+    assert np.isfinite(loss).all() and loss[-5:].mean() < loss[:5].mean()     # it learns
+    assert (fx["refs"][:n_train][fx["acts"][:n_train] != 255] >= -1).all()
+
+
+def test_config4_replay_on_the_facade_logic(config4, splits, medium_tables, medium_oracle):
+    """CPU tier: the façade's host logic with the oracle-backed test double as its device backend,
+    on a slice of the record (first / last training iterations, a few evaluation batches)."""
+    from test_facade_cpu import _world
+    from psketch_b200.teachers import DemonstrationTeacher
+    world = _world(medium_tables, medium_oracle)
+    n_train = int(config4["n_train_iters"])
+    picks = [0, 1, n_train - 1, n_train, n_train + 68, n_train + 69]
+    assert replay(world, DemonstrationTeacher(None), splits, config4, picks) == len(picks)
+
+
+@pytest.mark.gpu
+def test_config4_replay_on_the_gpu(config4, splits):
+    """GPU tier: the whole record (30 training rollouts + 2 x 69 evaluation batches, ~3,900 batched
+    launch sequences) through psketch_b200.worlds.CraftWorld / DemonstrationTeacher with the CUDA
+    backend, constructed from the experiment config exactly as worlds.load(config) would."""
+    import yaml
+    from psketch_b200 import teachers, worlds
+    from psketch_b200.worlds.craft import _Struct
+    cfg = _Struct(**yaml.safe_load("""
+recipes: "resources/craft/recipes.yaml"
+world: {name: CraftWorld, config: craft_medium}
+student: {name: ImitationStudent, model: {name: LSTMSeq2SeqModel, hidden_size: 256}}
+teacher: {name: DemonstrationTeacher}
+trainer: {name: ImitationTrainer, hints: "resources/craft/hints.hierarchy.yaml", max_timesteps: 40, batch_size: 32}
+"""))
+    cfg.random = np.random.RandomState(123)
+    world, teacher = worlds.load(cfg), teachers.load(cfg)
+    assert cfg.student.model.input_size == 404 and cfg.student.model.n_actions == 6
+    total = int(config4["n_train_iters"]) + int(config4["eval_sizes"].sum())
+    assert replay(world, teacher, splits, config4, range(total)) == total

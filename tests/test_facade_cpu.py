@@ -23,6 +23,15 @@ class OracleBackend(facade._Backend):
         self.T = world.tables.n_tasks - 1
         self.runs = []
 
+    def find_closest(self, cells, agent, kind, seq_cap=96):
+        agent = np.asarray(agent, np.uint8)
+        goal, length, status, seq = self.o.find_closest(
+            np.asarray(cells, np.uint8)[None], agent[None, [_lib.AG_X, _lib.AG_Y]].astype(np.int32),
+            agent[None, _lib.AG_DIR].astype(np.int32), np.asarray([kind]), seq_cap=seq_cap)
+        g = goal[0].astype(np.int64)
+        g = g.astype(np.uint8) if (g >= 0).all() else np.array([255, 255], np.uint8)
+        return g, int(length[0]), seq[0]
+
     def _run(self, states, step):
         n = len(states)
         self.runs.append((n, step))
@@ -88,22 +97,11 @@ def _world(medium_tables, medium_oracle):
     return world
 
 
-class _Teacher(object):
-    """DemonstrationTeacher's two entry points; the closest-resource query (a device launch in the
-    product) answered by the oracle."""
-
-    def __init__(self, oracle):
-        self.o = oracle
-
-    def __call__(self, task, state):
-        return state.expert_action(task)
-
-    def find_closest_resources(self, task, state):
-        kind = state.world.cookbook.index[task.goal_arg]
-        goal, length, status, seq = self.o.find_closest(
-            np.asarray(state.cells, np.uint8)[None], np.asarray([state.pos], np.int32),
-            np.asarray([state.dir], np.int32), np.asarray([kind]), seq_cap=96)
-        return tuple(int(v) for v in goal[0]), [int(a) for a in seq[0][:int(length[0])]]
+def _Teacher(oracle):
+    """The product teacher: its closest-resource query goes through backend.find_closest, which the
+    test double above answers with the oracle."""
+    from psketch_b200.teachers import DemonstrationTeacher
+    return DemonstrationTeacher(None)
 
 
 def _batch(world, splits, inst):
