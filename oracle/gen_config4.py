@@ -63,9 +63,9 @@ def prepare_data(regen_dir, data_dir):
         json.dump(data, open(os.path.join(data_dir, "craft_medium_%s.json" % split), "w"))
 
 
-def make_config(data_dir, exp_dir, iters, log_every, seed=123):
+def make_config(data_dir, exp_dir, iters, log_every, seed=123, experiment="imitation"):
     import torch
-    cfg = ref_shim.make_config("imitation", seed)
+    cfg = ref_shim.make_config(experiment, seed)
     cfg.data_dir = data_dir
     cfg.experiment_dir = exp_dir
     cfg.trainer.max_iters = iters
@@ -75,7 +75,7 @@ def make_config(data_dir, exp_dir, iters, log_every, seed=123):
     return cfg
 
 
-def run(which, data_dir, iters, log_every, medium_oracle=None):
+def run(which, data_dir, iters, log_every, medium_oracle=None, experiment="imitation"):
     """One training run; returns the record.  ``which``: 'reference' or 'facade'."""
     import torch
     ref_shim._install_shims()
@@ -89,9 +89,42 @@ def run(which, data_dir, iters, log_every, medium_oracle=None):
         import trainers as ref_trainers
         import worlds as ref_worlds
         from students.imitation import ImitationStudent
+        from students.primitive_language import PrimitiveLanguageStudent
         from trainers.imitation import ImitationTrainer
+        from trainers.primitive_language import PrimitiveLanguageTrainer
 
         rec = dict(iters=[], evals=[])
+
+        class RecordingLanguageStudent(PrimitiveLanguageStudent):     # student code runs unchanged
+            def init(self, tasks, instructions, states, is_eval):
+                super().init(tasks, instructions, states, is_eval)
+                self.cur = dict(is_eval=is_eval, acts=[], refs=[], fh=[], phase2_acts=[], phase2_fh=[],
+                                instructions=[list(w) for w in instructions], descriptions=None)
+
+            def _log(self, states, actions):
+                feats = np.stack([np.asarray(s.features()) for s in states]).astype(np.float32)
+                second = self.cur["descriptions"] is not None
+                self.cur["phase2_fh" if second else "fh"].append(feature_hash(feats))
+                self.cur["phase2_acts" if second else "acts"].append(list(actions))
+
+            def act(self, states, t):
+                actions = super().act(states, t)
+                self._log(states, actions)
+                return actions
+
+            def instructed_act(self, states, t):
+                actions = super().instructed_act(states, t)
+                self._log(states, actions)
+                return actions
+
+            def receive(self, descriptions):
+                self.cur["descriptions"] = [list(d) for d in descriptions]
+                super().receive(descriptions)
+
+            def learn(self):
+                loss = super().learn()
+                rec["iters"][-1]["loss"] = loss
+                return loss
 
         class RecordingStudent(ImitationStudent):          # the student's code runs unchanged
             def init(self, tasks, states, is_eval):
@@ -114,7 +147,9 @@ def run(which, data_dir, iters, log_every, medium_oracle=None):
                 rec["iters"][-1]["loss"] = loss
                 return loss
 
-        class RecordingTrainer(ImitationTrainer):          # the trainer's code runs unchanged
+        base_trainer = PrimitiveLanguageTrainer if experiment == "primitive_language" else ImitationTrainer
+
+        class RecordingTrainer(base_trainer):              # the trainer's code runs unchanged
             def do_rollout(self, batch, world, student, teacher, is_eval):
                 info = super().do_rollout(batch, world, student, teacher, is_eval)
                 entry = dict(ids=[item["id"] for item in batch], info=info, **student.cur)
@@ -128,7 +163,7 @@ def run(which, data_dir, iters, log_every, medium_oracle=None):
                 rec["evals"].append([])
                 return super().evaluate(dataset, world, student, teacher, save_traj)
 
-        config = make_config(data_dir, exp_dir, iters, log_every)
+        config = make_config(data_dir, exp_dir, iters, log_every, experiment=experiment)
         datasets = ref_data.load(config)                   # also sets config.vocab (data/task.py:63)
         if which == "reference":
             world = ref_worlds.load(config)
@@ -142,19 +177,25 @@ def run(which, data_dir, iters, log_every, medium_oracle=None):
                 from test_facade_cpu import OracleBackend
                 world._backend = OracleBackend(world, medium_oracle)
         assert config.student.model.input_size == 404 and config.student.model.n_actions == 6
-        student = RecordingStudent(config)
+        student = (RecordingLanguageStudent if experiment == "primitive_language" else RecordingStudent)(config)
         trainer = RecordingTrainer(config)
         torch.manual_seed(config.seed)
         config.random.seed(config.seed)
         for d in datasets.values():
             d.item_idx = 0
-        trainer.train(datasets, world, student, teacher)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):    # the language trainer print()s renders
+            trainer.train(datasets, world, student, teacher)
+        rec["action_map"] = dict(getattr(teacher, "student_action_map", {}))
+        rec["random_state"] = config.random.get_state()[1][:8].tolist()
     shutil.rmtree(exp_dir, ignore_errors=True)
     return rec
 
 
 def assert_same(a, b):
     assert len(a["iters"]) == len(b["iters"]) and len(a["evals"]) == len(b["evals"])
+    assert a["action_map"] == b["action_map"] and a["random_state"] == b["random_state"]
     rollouts_a = a["iters"] + [e for ev in a["evals"] for e in ev]
     rollouts_b = b["iters"] + [e for ev in b["evals"] for e in ev]
     assert len(rollouts_a) == len(rollouts_b)
@@ -164,6 +205,9 @@ def assert_same(a, b):
         assert x["refs"] == y["refs"], k
         assert [int(h) for h in x["fh"]] == [int(h) for h in y["fh"]], k
         assert x.get("loss") == y.get("loss"), (k, x.get("loss"), y.get("loss"))   # bit-equal floats
+        for extra in ("phase2_acts", "instructions", "descriptions"):
+            assert x.get(extra) == y.get(extra), (k, extra)
+        assert [int(h) for h in x.get("phase2_fh", [])] == [int(h) for h in y.get("phase2_fh", [])], k
         ix, iy = x["info"], y["info"]
         assert ix["action_seqs"] == iy["action_seqs"], k
         assert [bool(v) for v in ix["success"]] == [bool(v) for v in iy["success"]], k
@@ -194,7 +238,7 @@ def pack(rec, splits):
         out["n_env"][r], out["n_t"][r], out["is_eval"][r] = B, T, int(e["is_eval"])
         for i, id_ in enumerate(e["ids"]):                 # 'instance_10561' -> row of the split
             out["batch"][r, i] = id_to_idx[(split, int(id_.split("_")[1]))]
-        out["acts"][r, :T, :B] = np.asarray(e["acts"], np.uint8)
+        out["acts"][r, :T, :B] = np.asarray(e["acts"], np.int64).astype(np.uint8)     # -1 (terminated) -> 255
         if e["refs"]:
             out["refs"][r, :T, :B] = np.asarray(e["refs"], np.int8)
         out["feat_hash"][r, :T] = e["fh"]
@@ -203,11 +247,32 @@ def pack(rec, splits):
         info = e["info"]
         out["success"][r, :B] = [bool(v) for v in info["success"]]
         out["seq_len"][r, :B] = [len(s) for s in info["action_seqs"]]
-        for i, s in enumerate(info["action_seqs"]):        # what was executed (= acts where not done)
-            assert s == [int(a) for a in np.asarray(e["acts"])[:len(s), i]] or not e["is_eval"]
         out["n_dist"][r] = len(info["distances"])
         out["distances"][r, :len(info["distances"])] = info["distances"]
         out["num_interactions"][r], out["num_steps"][r] = info["num_interactions"], info["num_steps"]
+    if any("phase2_acts" in e for _, e in rollouts):
+        # primitive_language.yaml: the second (greedy, instructed) decoding pass of training rollouts,
+        # the instruction words handed to the student and the teacher's descriptions (word = action
+        # index of teachers/primitive_language.py:20-32: down 0, up 1, left 2, right 3, use 4, stop 5)
+        words = {"down": 0, "up": 1, "left": 2, "right": 3, "use": 4, "stop": 5}
+        out["phase2_acts"] = np.full((R, TM, BM), 255, np.uint8)
+        out["phase2_n_t"] = np.zeros(R, np.int32)
+        out["phase2_feat_hash"] = np.zeros((R, TM), np.uint64)
+        out["descriptions"] = np.full((R, BM, TM), 255, np.uint8)
+        out["instructions"] = np.full((R, BM, TM), 255, np.uint8)
+        for r, (split, e) in enumerate(rollouts):
+            B = len(e["ids"])
+            T2 = len(e["phase2_acts"])
+            out["phase2_n_t"][r] = T2
+            if T2:
+                out["phase2_acts"][r, :T2, :B] = np.asarray(e["phase2_acts"], np.int64).astype(np.uint8)
+                out["phase2_feat_hash"][r, :T2] = e["phase2_fh"]
+            for i, ws in enumerate(e["instructions"]):
+                out["instructions"][r, i, :len(ws)] = [words[w] for w in ws]
+            for i, ws in enumerate(e["descriptions"] or []):
+                out["descriptions"][r, i, :len(ws)] = [words[w] for w in ws]
+        am = rec["action_map"]
+        out["final_action_map"] = np.asarray([words.get(am.get(a), 255) for a in range(6)], np.uint8)
     return out
 
 
@@ -215,6 +280,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--log-every", type=int, default=15)
+    ap.add_argument("--experiment", default="imitation", choices=["imitation", "primitive_language"])
     args = ap.parse_args()
     regen_dir = os.environ.get("PSK_REGEN_DIR", "/tmp/psk_data")
     data_dir = os.path.join(regen_dir, "config4_data")
@@ -222,18 +288,19 @@ def main():
     splits = np.load(os.path.join(OUT, "craft_medium_splits.npz"))
     import time
     t0 = time.time()
-    a = run("reference", data_dir, args.iters, args.log_every)
+    a = run("reference", data_dir, args.iters, args.log_every, experiment=args.experiment)
     t1 = time.time()
     print("reference world + teacher: %d train rollouts, %d evaluations, %.1f s; losses %s ..." %
           (len(a["iters"]), len(a["evals"]), t1 - t0, [round(e["loss"], 4) for e in a["iters"][:4]]))
     from oracle.craft_oracle import CraftOracle
     from psketch_b200.tables import CraftTables
-    b = run("facade", data_dir, args.iters, args.log_every, medium_oracle=CraftOracle(CraftTables()))
+    b = run("facade", data_dir, args.iters, args.log_every, medium_oracle=CraftOracle(CraftTables()),
+            experiment=args.experiment)
     print("psketch_b200 world + teacher (oracle-backed backend): %.1f s" % (time.time() - t1))
     assert_same(a, b)
     print("IDENTICAL: batches, features, actions, teacher labels, losses, success, distances, eval trajectories")
     out = pack(a, splits)
-    path = os.path.join(OUT, "config4_imitation.npz")
+    path = os.path.join(OUT, "config4_%s.npz" % args.experiment)
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;",
           "train success %.3f" % np.mean([np.mean([bool(v) for v in e["info"]["success"]]) for e in a["iters"]]),

@@ -107,3 +107,111 @@ trainer: {name: ImitationTrainer, hints: "resources/craft/hints.hierarchy.yaml",
     assert cfg.student.model.input_size == 404 and cfg.student.model.n_actions == 6
     total = int(config4["n_train_iters"]) + int(config4["eval_sizes"].sum())
     assert replay(world, teacher, splits, config4, range(total)) == total
+
+
+# ------------------------------------------------------------------------------------------------
+# primitive_language.yaml (trainers/primitive_language.py:16-143 + teachers/primitive_language.py)
+WORDS = ("down", "up", "left", "right", "use", "stop")
+
+
+def _word_ids(seqs):
+    return [[WORDS.index(w) for w in ws] for ws in seqs]
+
+
+def replay_language(world, teacher, splits, fx, rollouts, rng):
+    """``rng`` is the experiment's shared numpy stream (config.random): the dataset shuffles and the
+    teacher's describe() draw from it in the order the reference's run did, so the batches
+    themselves are re-derived here and must match the record."""
+    from trainer_loop import ScriptedLanguageStudent, run_language_protocol
+    n_train = int(fx["n_train_iters"])
+    sizes = [int(v) for v in fx["eval_sizes"]]
+    log_every = n_train // len(sizes)
+    order = {"train": None, "dev": None}
+    cursor = {"train": 0, "dev": 0}
+    checked = 0
+    for r in rollouts:
+        B, T, is_eval = int(fx["n_env"][r]), int(fx["n_t"][r]), bool(fx["is_eval"][r])
+        split = "dev" if is_eval else "train"
+        if cursor[split] == 0:                                     # data/dataset.py:70-72
+            order[split] = list(range(len(splits[split + "_inst_env"])))
+            rng.shuffle(order[split])
+        rows = order[split][cursor[split]:cursor[split] + 32]
+        cursor[split] = cursor[split] + 32 if cursor[split] + 32 < len(order[split]) else 0
+        assert rows == fx["batch"][r, :B].tolist(), r
+        batch = _items(world, splits, split, rows)
+        for item, i in zip(batch, rows):
+            item["ref_actions"] = tuple(int(a) for a in splits[split + "_ref_actions"][i][:splits[split + "_ref_len"][i]])
+        T2 = int(fx["phase2_n_t"][r])
+        student = ScriptedLanguageStudent(fx["acts"][r, :T, :B], fx["phase2_acts"][r, :T2, :B])
+        got = run_language_protocol(batch, world, teacher, student, is_eval, 40)
+        want_instr = [[int(w) for w in row if w != 255] for row in fx["instructions"][r, :B]]
+        assert _word_ids(got["instructions"]) == want_instr, r
+        last = fx["acts"] if is_eval else fx["phase2_acts"]
+        for i, seq in enumerate(got["action_seqs"]):
+            L = int(fx["seq_len"][r, i])
+            assert seq == last[r, :L, i].tolist(), (r, i)
+        if not is_eval:
+            want = [[int(w) for w in row if w != 255] for row in fx["descriptions"][r, :B]]
+            assert _word_ids(got["descriptions"]) == want, r
+            assert student.t == T2 and len(student.features[0]) == T, r
+            assert [int(_hash(f)) for f in student.features[1]] == [int(h) for h in fx["phase2_feat_hash"][r, :T2]], r
+        assert [int(_hash(f)) for f in student.features[0]] == [int(h) for h in fx["feat_hash"][r, :T]], r
+        assert [bool(v) for v in got["success"]] == fx["success"][r, :B].astype(bool).tolist(), r
+        assert got["distances"] == fx["distances"][r, :int(fx["n_dist"][r])].tolist(), r
+        assert got["num_interactions"] == int(fx["num_interactions"][r]), r
+        assert got["num_steps"] == int(fx["num_steps"][r]), r
+        checked += 1
+    learned = [WORDS.index(teacher.student_action_map[a]) if a in teacher.student_action_map else 255
+               for a in range(6)]
+    return checked, learned
+
+
+def _language_order(fx):
+    """Rollout indices of the record in the order the run produced them: log_every training
+    iterations, one evaluation of the dev split, and so on."""
+    n_train, sizes = int(fx["n_train_iters"]), [int(v) for v in fx["eval_sizes"]]
+    per = n_train // len(sizes)
+    out, ev = [], n_train
+    for k, sz in enumerate(sizes):
+        out += list(range(k * per, (k + 1) * per)) + list(range(ev, ev + sz))
+        ev += sz
+    return out
+
+
+@pytest.fixture(scope="module")
+def config4_language():
+    return np.load(os.path.join(GOLDEN, "config4_primitive_language.npz"))
+
+
+def test_config4_language_replay_on_the_facade_logic(config4_language, splits, medium_tables, medium_oracle):
+    """CPU tier: the first training iterations of the primitive_language.yaml record (describe()
+    learns the student's action ids there and draws from the shared random stream)."""
+    from test_facade_cpu import _world
+    from psketch_b200.teachers import PrimitiveLanguageTeacher
+    fx = config4_language
+    world = _world(medium_tables, medium_oracle)
+    rng = np.random.RandomState(123)
+    cfg = type("Cfg", (), {"random": rng})()
+    checked, _ = replay_language(world, PrimitiveLanguageTeacher(cfg), splits, fx, range(6), rng)
+    assert checked == 6
+
+
+@pytest.mark.gpu
+def test_config4_language_replay_on_the_gpu(config4_language, splits):
+    """GPU tier: the whole primitive_language.yaml record (30 training rollouts of two decoding passes
+    each + 2 evaluations of the dev split) on the CUDA-backed world and language teacher."""
+    from psketch_b200 import teachers, worlds
+    from psketch_b200.worlds.craft import _Struct
+    fx = config4_language
+    cfg = _Struct(recipes="resources/craft/recipes.yaml",
+                  world={"name": "CraftWorld", "config": "craft_medium"},
+                  teacher={"name": "PrimitiveLanguageTeacher"},
+                  trainer={"name": "PrimitiveLanguageTrainer", "hints": "resources/craft/hints.hierarchy.yaml",
+                           "max_timesteps": 40, "batch_size": 32})
+    rng = np.random.RandomState(123)
+    cfg.random = rng
+    world, teacher = worlds.load(cfg), teachers.load(cfg)
+    order = _language_order(fx)
+    checked, learned = replay_language(world, teacher, splits, fx, order, rng)
+    assert checked == len(order)
+    assert learned == fx["final_action_map"].tolist()

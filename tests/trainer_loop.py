@@ -88,3 +88,76 @@ def check_against_fixture(fx, make_batch, world, teacher):
         assert np.array_equal(feats, fx[mode + "_features"].astype(np.float64)), mode
         if not is_eval:
             assert np.array_equal(np.asarray(student.received, np.int16), fx["train_ref_actions"])
+
+
+# ------------------------------------------------------------------------------------------------
+# trainers/primitive_language.py:16-143, restated the same way (scripted student): two decoding
+# passes from the SAME initial states in training (the states are persistent: the second pass
+# restarts from init_states[:], :32,82), describe() over the state sequences of the first pass,
+# success / distances from the states the last pass ended in.
+class ScriptedLanguageStudent(object):
+    def __init__(self, pass1, pass2):
+        self.passes = [pass1, pass2]
+        self.which = 0
+        self.t = 0
+        self.features = [[], []]
+        self.descriptions = None
+
+    def next_actions(self, states):
+        self.features[self.which].append(np.stack([np.asarray(s.features()) for s in states]))
+        row = [int(a) if a != 255 else -1 for a in self.passes[self.which][self.t]]
+        self.t += 1
+        return row
+
+    def second_pass(self, descriptions):
+        self.descriptions = descriptions
+        self.which, self.t = 1, 0
+
+
+def run_language_protocol(batch, world, teacher, student, is_eval, max_timesteps):
+    n = len(batch)
+    tasks = [item["task"] for item in batch]
+    starts = [world.init_state(item["grid"], item["init_pos"]) for item in batch]
+    hints = [teacher.instruct(world, item["ref_actions"]) for item in batch]
+    starts[0].render()                                             # :28 (prints; exercises render)
+
+    def decode(record_states):
+        states = starts[:]
+        clock = [max_timesteps] * n
+        finished = [False] * n
+        taken = [[] for _ in range(n)]
+        visited = [[s] for s in states]
+        steps = 0
+        while not all(finished):
+            chosen = student.next_actions(states)
+            for i in range(n):
+                if not finished[i]:
+                    states[i] = states[i].step(chosen[i])[1]
+                    taken[i].append(chosen[i])
+                    if record_states:
+                        visited[i].append(states[i])
+                    steps += 1
+                clock[i] -= 1
+                if chosen[i] == STOP or clock[i] <= 0:
+                    finished[i] = True
+        return states, taken, visited, steps
+
+    states, taken, visited, steps = decode(True)
+    descriptions = None
+    if not is_eval:
+        descriptions = [teacher.describe(world, taken[i], visited[i]) for i in range(n)]
+        student.second_pass(descriptions)
+        states, taken, _, _ = decode(False)
+    solved, gaps = [], []
+    for i in range(n):
+        solved.append(states[i].satisfies(tasks[i]))
+        if tasks[i].goal_name == "get":
+            if solved[i]:
+                gaps.append(0)
+            else:
+                probe = world.init_state(batch[i]["grid"], states[i].pos, states[i].dir)
+                gaps.append(len(teacher.find_closest_resources(tasks[i], probe)[1]))
+    return dict(action_seqs=taken, success=solved, distances=gaps, instructions=hints,
+                descriptions=descriptions,
+                num_interactions=0 if is_eval else sum(len(h) for h in hints),
+                num_steps=0 if is_eval else steps)
