@@ -112,7 +112,7 @@ def train(args):
         rec = dict(iter=it + 1)
         if (it + 1) % args.log_every == 0 or (it + 1) % args.eval_every == 0 or it == args.iters - 1:
             torch.cuda.synchronize()
-            rec.update(loss=float(shown), train_success=float(roll.success.float().mean()),
+            rec.update(loss=float(shown.detach()), train_success=float(roll.success.float().mean()),
                        steps=int(roll.steps), interactions=int(roll.interactions))
         torch.cuda.synchronize() if it < 3 else None
         if it >= 3:                                        # timings after the graph capture / warm-up

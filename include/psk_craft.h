@@ -158,7 +158,16 @@ int psk_craft_reset(psk_craft_state s, psk_craft_episodes ep, const uint8_t *mas
  *     !done -> s = s.step(a)
  * features_out f32[n][n_features] (may be NULL), expert_out u8[n], done_out/success_out u8[n]
  * (may be NULL), stats u64[4] device accumulators {episodes, successes, env_steps, reserved}
- * (may be NULL).  fused != 0 selects the single fused kernel, 0 the three-kernel pipeline. */
+ * (may be NULL).  fused: 0 = three-kernel pipeline, PSK_TICK_FUSED = the single fused kernel,
+ * PSK_TICK_ADVANCE_FIRST = the fused kernel in "step, then observe" order — what a policy in the
+ * loop needs (students/imitation.py:71-84 reads features, THEN the trainer steps):
+ *     action_in ? { timer -= 1; done/success/auto-reset or s = s.step(action_in[i]) } : nothing
+ *     ref = teacher(task, s); f = s.features()          <- of the state AFTER the step
+ * so one launch per timestep serves  a_t = policy(f_t); tick(a_t) -> f_{t+1}, ref_{t+1}, done_t.
+ * In that order done_out / success_out describe the step just applied (0 when action_in is NULL). */
+#define PSK_TICK_PIPELINE 0
+#define PSK_TICK_FUSED 1
+#define PSK_TICK_ADVANCE_FIRST 2
 int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
                    const uint8_t *action_in, float *features_out, uint8_t *expert_out,
                    uint8_t *done_out, uint8_t *success_out, unsigned long long *stats,

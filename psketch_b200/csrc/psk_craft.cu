@@ -1440,7 +1440,7 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
                   const uint8_t *__restrict__ init_agent, float *__restrict__ features_out,
                   uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
                   uint8_t *__restrict__ success_out, unsigned long long *stats,
-                  int32_t *err_flags, int64_t n, int cell_stride, int K, int nf) {
+                  int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int adv_first) {
     constexpr int NT = NE + NFW * 32;
     constexpr int TPE = 8, EPW = 32 / TPE;
     constexpr int SPW = NE / NFW;              // env slots per feature warp
@@ -1478,6 +1478,46 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
             for (int i = tid; i < ne_sp * 2; i += NT) sag[i] = gag[i];
         }
         __syncthreads();
+        if (adv_first) {
+            // "step, then observe" (PSK_TICK_ADVANCE_FIRST): the env threads apply action_in to the
+            // tile in shared memory first — the teacher and the feature warps then see the NEW state
+            if (env_warp && tid < ne_sp) {
+                const int64_t e = e_base + tid;
+                bool done = false, success = false;
+                if (action_in) {
+                    Agent a;
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const uint4 v = reinterpret_cast<const uint4 *>(s_agent)[tid * 2 + i];
+                        a.w[4 * i] = v.x; a.w[4 * i + 1] = v.y; a.w[4 * i + 2] = v.z; a.w[4 * i + 3] = v.w;
+                    }
+                    const Agent before = a;
+                    uint8_t *srow_w = s_rows + tid * CP;
+                    const int act = action_in[e];
+                    done = advance_env<W, H>(st, a, srow_w, srow_w, act,
+                                             scen_grid + (int64_t)scen_idx[e] * CP,
+                                             init_agent + e * PSK_AGENT_BYTES, CP, success, flags);
+                    bool changed = false;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) changed |= a.w[i] != before.w[i];
+                    if (changed) {
+                        store_agent(agent, e, a);
+                        uint4 *sag = reinterpret_cast<uint4 *>(s_agent) + tid * 2;
+                        sag[0] = make_uint4(a.w[0], a.w[1], a.w[2], a.w[3]);
+                        sag[1] = make_uint4(a.w[4], a.w[5], a.w[6], a.w[7]);
+                    }
+                    if (done || act == PSK_ACT_USE) {      // the only transitions that touch cells
+#pragma unroll
+                        for (int i = 0; i < CP / 16; i++)
+                            reinterpret_cast<uint4 *>(grid + e * CP)[i] = reinterpret_cast<const uint4 *>(srow_w)[i];
+                    }
+                }
+                if (done_out) done_out[e] = done;
+                if (success_out) success_out[e] = success;
+                add_stats(stats, done, success, action_in != nullptr);
+            }
+            __syncthreads();
+        }
         if (env_warp) {
             const bool live = tid < ne_sp;
             const int slot = live ? tid : 0;             // dead lanes replay slot 0, unsaved
@@ -1500,8 +1540,9 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
             int dist;
             uint32_t fl = 0;
             int act = expert_env<W, H>(st, a, a.task(), words, facing, dist, fl);
-            if (live) {
-                flags |= fl;
+            if (live) flags |= fl;
+            if (live && adv_first) expert_out[e] = (uint8_t)act;
+            if (live && !adv_first) {
                 const Agent before = a;
                 expert_out[e] = (uint8_t)act;
                 if (action_in) act = action_in[e];
@@ -1515,7 +1556,7 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
                 if (done_out) done_out[e] = done;
                 if (success_out) success_out[e] = success;
             }
-            add_stats(stats, done, success, live);
+            if (!adv_first) add_stats(stats, done, success, live);
         } else if (features_out) {
             const int fw = (tid - NE) >> 5, lane = tid & 31;
             const uint32_t wbuf_s = smem_u32(smem_raw) + (uint32_t)fw * feature_buffer_bytes(USE_TMA, EPW, nf, PSK_ESZ_FUSED_KERNELS);
@@ -1923,7 +1964,7 @@ template <int W, int H, int WIN> struct Config {
     static int tick_variant(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
                             const uint8_t *action_in, float *features_out, uint8_t *expert_out,
                             uint8_t *done, uint8_t *success, unsigned long long *stats,
-                            int32_t *err, cudaStream_t st) {
+                            int32_t *err, cudaStream_t st, int adv_first) {
         constexpr int EPW = 32 / TPE;
         const int f = nf(t);
         const size_t smem = (size_t)NFW * feature_buffer_bytes(TMA, EPW, f, PSK_ESZ_FUSED_KERNELS);
@@ -1962,7 +2003,7 @@ template <int W, int H, int WIN> struct Config {
         const int cell_stride = s.cell_stride, K = t->n_kinds;
         return check(cudaLaunchKernelEx(&cfg, kern, dt, s.grid, s.agent, action_in, ep.scen_grid,
                                         ep.scen_idx, ep.init_agent, features_out, expert_out, done,
-                                        success, stats, err, s.n, cell_stride, K, f));
+                                        success, stats, err, s.n, cell_stride, K, f, adv_first));
     }
     template <int NE, int NFW, bool TMA>
     static int rollout_variant(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
@@ -2038,7 +2079,7 @@ template <int W, int H, int WIN> struct Config {
     static int tick_fused(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
                           const uint8_t *action_in, float *features_out, uint8_t *expert_out,
                           uint8_t *done, uint8_t *success, unsigned long long *stats,
-                          int32_t *err, cudaStream_t st) {
+                          int32_t *err, cudaStream_t st, int adv_first) {
         if constexpr (!BITBOARD) {
             return PSK_ERR_UNSUPPORTED;   // psk_craft_tick falls back to the three-kernel pipeline
         } else {
@@ -2052,16 +2093,20 @@ template <int W, int H, int WIN> struct Config {
         const int tma = env_tma >= 0 ? env_tma : (big ? 1 : 0);
 #define PSK_TV(NE, NFW)                                                                          \
     return tma ? tick_variant<NE, NFW, true>(t, s, ep, action_in, features_out, expert_out, done, \
-                                             success, stats, err, st)                            \
+                                             success, stats, err, st, adv_first)                 \
                : tick_variant<NE, NFW, false>(t, s, ep, action_in, features_out, expert_out, done, \
-                                              success, stats, err, st)
-        if (WIN != 3) PSK_TV(64, 2);
-        switch (variant) {
-            case 1: PSK_TV(128, 4);
-            case 2: PSK_TV(32, 1);
-            case 3: PSK_TV(64, 4);
-            case 4: PSK_TV(32, 2);
-            default: PSK_TV(64, 2);
+                                              success, stats, err, st, adv_first)
+        if constexpr (WIN != 3) {
+            (void)variant;
+            PSK_TV(64, 2);
+        } else {
+            switch (variant) {
+                case 1: PSK_TV(128, 4);
+                case 2: PSK_TV(32, 1);
+                case 3: PSK_TV(64, 4);
+                case 4: PSK_TV(32, 2);
+                default: PSK_TV(64, 2);
+            }
         }
 #undef PSK_TV
         }
@@ -2198,9 +2243,29 @@ int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episo
     if (!expert_out || !ep.scen_grid || !ep.scen_idx || !ep.init_agent) return PSK_ERR_BADARG;
     if (features_out && (reinterpret_cast<uintptr_t>(features_out) & 15)) return PSK_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
+    const int adv_first = fused == PSK_TICK_ADVANCE_FIRST;
     if (fused && t->width * t->height <= 128) {
         PSK_DISPATCH(t, tick_fused(t, s, ep, action_in, features_out, expert_out, done_out,
-                                   success_out, stats, err_flags, st));
+                                   success_out, stats, err_flags, st, adv_first));
+    }
+    if (adv_first) {        // step, then observe — as separate launches (grids above 128 cells)
+        if (action_in) {
+            int rc = PSK_ERR_UNSUPPORTED;
+            do {
+                if (Medium::matches(t)) { rc = Medium::advance(t, s, ep, action_in, done_out, success_out, stats, err_flags, st); break; }
+                if (Large::matches(t)) { rc = Large::advance(t, s, ep, action_in, done_out, success_out, stats, err_flags, st); break; }
+                if (Stress16::matches(t)) { rc = Stress16::advance(t, s, ep, action_in, done_out, success_out, stats, err_flags, st); break; }
+                if (Stress32::matches(t)) { rc = Stress32::advance(t, s, ep, action_in, done_out, success_out, stats, err_flags, st); break; }
+                if (Stress64::matches(t)) { rc = Stress64::advance(t, s, ep, action_in, done_out, success_out, stats, err_flags, st); break; }
+            } while (0);
+            if (rc) return rc;
+        } else {
+            if (done_out && cudaMemsetAsync(done_out, 0, (size_t)s.n, st) != cudaSuccess) return PSK_ERR_CUDA;
+            if (success_out && cudaMemsetAsync(success_out, 0, (size_t)s.n, st) != cudaSuccess) return PSK_ERR_CUDA;
+        }
+        int rc = psk_craft_expert(t, s, nullptr, expert_out, nullptr, err_flags, stream);
+        if (rc) return rc;
+        return features_out ? psk_craft_features(t, s, features_out, 0, stream) : PSK_OK;
     }
     int rc = psk_craft_expert(t, s, nullptr, expert_out, nullptr, err_flags, stream);
     if (rc) return rc;

@@ -4,8 +4,9 @@ The reference's student (students/imitation.py:71-84) turns a Python list of per
 ndarrays into a tensor, copies it to the GPU, decodes one step, and copies the sampled actions back
 to the host — every timestep.  Here the env's ``f32[N, 404]`` feature tensor is already on the
 device, the policy reads it in place, samples on the device, and the sampled ``u8[N]`` actions go
-straight into the env kernels; one whole rollout (features -> decode -> sample -> teacher label ->
-step, 40 timesteps) is ONE CUDA graph replay with no host round trip (``GraphedRollout``).
+straight into the env kernel; one whole rollout (40 timesteps of: fused tick in "step, then
+observe" order -> decode -> sample) is ONE CUDA graph replay with no host round trip
+(``GraphedRollout``).
 
 ``Seq2SeqPolicy`` has the architecture of the reference's ``models/lstm_seq2seq.py:LSTMSeq2SeqModel``
 (task-token encoder LSTM with source-position embeddings, decoder LSTM over [features, time
@@ -136,10 +137,11 @@ def imitation_loss(logits, refs):
 
 class GraphedRollout(object):
     """trainers/imitation.py:18-77 for a whole VecCraft batch with the student in the loop, captured
-    as ONE CUDA graph: per timestep  features kernel -> decode_step -> on-device sampling (Gumbel-max
-    over pre-drawn noise; argmax when greedy) -> teacher kernel (the DAgger label) -> done / timer /
-    success bookkeeping -> step kernel for the envs still running.  Nothing crosses PCIe during a
-    rollout; what the learner needs stays on the device:
+    as ONE CUDA graph: per timestep one psk_craft_tick launch in "step, then observe" order (applies
+    the previous actions with the trainer's timer / done / success rules, returns the features and the
+    teacher's DAgger label of the new states) -> decode_step -> on-device sampling (Gumbel-max over
+    pre-drawn noise; argmax when greedy).  Nothing crosses PCIe during a rollout; what the learner
+    needs stays on the device:
 
         feats f32[T, N, F]   the states the student saw        refs i64[T, N]  teacher labels, -1 = done
         acts  u8[T, N]       what was executed, 255 = done     success bool[N], steps i64[] env-steps taken
@@ -158,7 +160,7 @@ class GraphedRollout(object):
         self.steps = torch.zeros((), dtype=torch.long, device=dev)
         self.interactions = torch.zeros((), dtype=torch.long, device=dev)
         self.zero_time = torch.zeros(n, dtype=torch.long, device=dev)    # students/imitation.py:58,75:
-        self.expert = torch.zeros(n, dtype=torch.uint8, device=dev)      # self.time is never advanced
+        self.out = {}                                                    # self.time is never advanced
         self.mem = None
         self.graph = None
         self.use_graph = use_graph
@@ -170,10 +172,22 @@ class GraphedRollout(object):
         self.success.zero_()
         self.steps.zero_()
         self.interactions.zero_()
-        for t in range(self.T):
-            f = self.feats[t]
-            env.features(out=f)
-            logits, state = pol.decode_step(f, self.zero_time, state, mem)
+        env.timer.fill_(self.T)                 # the kernel's timer is the trainer's (imitation.py:30,63)
+        prev = None
+        for t in range(self.T + 1):
+            # ONE env launch per timestep: apply the previous actions (timer / done / success /
+            # step inside the kernel), then the features and the teacher's label of the new states
+            last = t == self.T
+            out = env.tick(actions=prev, features_out=None if last else self.feats[t],
+                           want_features=not last, out=self.out, advance_first=True)
+            if prev is not None:
+                ended = ~self.done & out["done"].bool()
+                self.success |= ended & out["success"].bool()
+                self.done |= ended
+                self.steps += (~self.done).sum()
+            if last:
+                break
+            logits, state = pol.decode_step(self.feats[t], self.zero_time, state, mem)
             if self.greedy:
                 a = logits.argmax(dim=1)
             else:
@@ -181,16 +195,10 @@ class GraphedRollout(object):
             a8 = a.to(torch.uint8)
             live = ~self.done
             if self.with_teacher:
-                env.expert(out=self.expert)
-                self.refs[t] = torch.where(live, self.expert.long(), torch.full_like(a, -1))
+                self.refs[t] = torch.where(live, out["expert"].long(), torch.full_like(a, -1))
                 self.interactions += live.sum()
             self.acts[t] = torch.where(live, a8, torch.full_like(a8, 255))
-            ends = live & ((a8 == STOP) | (t == self.T - 1))
-            self.success |= ends & (env.satisfies() == 1)
-            self.done |= ends
-            active = ~self.done
-            env.step(a8, active=active.to(torch.uint8))
-            self.steps += active.sum()
+            prev = torch.where(live, a8, torch.full_like(a8, STOP))     # finished envs idle
 
     @torch.no_grad()
     def run(self, mem):

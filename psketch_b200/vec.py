@@ -199,8 +199,12 @@ class VecCraft(object):
         _lib.check(rc, "psk_craft_find_closest")
         return goal, length, seq
 
-    def tick(self, actions=None, features_out=None, want_features=True, fused=True, out=None):
-        """One rollout tick (see psk_craft_tick).  Returns dict(expert, done, success, features)."""
+    def tick(self, actions=None, features_out=None, want_features=True, fused=True, out=None,
+             advance_first=False):
+        """One rollout tick (see psk_craft_tick).  Returns dict(expert, done, success, features).
+        ``advance_first``: "step, then observe" — ``actions`` (None = no step) are applied first and
+        expert / features describe the state AFTER the step (PSK_TICK_ADVANCE_FIRST): the order a
+        policy in the loop needs, one launch per timestep."""
         actions = self._u8(actions)
         if out is None:
             out = {}
@@ -216,7 +220,7 @@ class VecCraft(object):
                                          _ptr(actions), _ptr(features_out), _ptr(out["expert"]),
                                          _ptr(out["done"]), _ptr(out["success"]),
                                          _ptr(self.stats), _ptr(self.err_flags),
-                                         1 if fused else 0, self._stream())
+                                         2 if advance_first else (1 if fused else 0), self._stream())
         _lib.check(rc, "psk_craft_tick")
         return out
 

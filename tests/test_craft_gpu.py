@@ -718,3 +718,59 @@ def test_max_timesteps_is_validated(medium_tables, medium_states):
     for bad in (0, 256, 1000):
         with pytest.raises(ValueError, match="max_timesteps"):
             VecCraft.from_states(medium_tables, S["grid"], S["inv"], S["pos"], S["dir"], max_timesteps=bad)
+
+
+@pytest.mark.parametrize("which", ["medium", "large", "stress16"])
+def test_tick_advance_first_matches_oracle(which, splits, medium_tables, medium_oracle, large_tables,
+                                           large_oracle, large_states):
+    """psk_craft_tick in "step, then observe" order (PSK_TICK_ADVANCE_FIRST): actions of a policy in
+    the loop are applied first, teacher action and features describe the state after the step; the
+    fused kernel (8x8, 10x10) and the launch-sequence fallback (16x16)."""
+    from psketch_b200.vec import VecCraft
+    rng = np.random.RandomState(17)
+    if which == "medium":
+        n = 4099
+        idx = rng.randint(0, 2200, size=n)
+        tables, oracle, grids = medium_tables, medium_oracle, splits["dev_grids"]
+        ienv, ipos, itask = splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx], splits["dev_inst_task"][idx]
+    elif which == "large":
+        n = 1500
+        tables, oracle, grids = large_tables, large_oracle, large_states["grid"][:n]
+        ienv, ipos = np.arange(n), large_states["pos"][:n]
+        itask = rng.choice([13, 14, 15, 19, 20, 21, 22, 23, 24, 25, 26], size=n)
+    else:
+        from oracle.craft_oracle import CraftOracle
+        from psketch_b200.tables import CraftTables
+        tables = CraftTables(world_config=dict(WIDTH=16, HEIGHT=16, WINDOW_WIDTH=3, WINDOW_HEIGHT=3,
+                                               N_WORKSHOPS=3, N_PRIMITIVES=4))
+        oracle = CraftOracle(tables)
+        n = 700
+        g = np.zeros((n, 16, 16), np.uint8)
+        g[:, 0, :] = g[:, 15, :] = g[:, :, 0] = g[:, :, 15] = 1
+        ipos = np.zeros((n, 2), np.int64)
+        for i in range(n):
+            cells = rng.permutation(14 * 14)
+            for j, kind in enumerate([7, 7, 8, 8, 9, 9, 2, 3, 4, 5, 6, 6]):
+                g[i, 1 + cells[j] // 14, 1 + cells[j] % 14] = kind
+            ipos[i] = (1 + cells[20] // 14, 1 + cells[20] % 14)
+        grids, ienv = g.reshape(n, 256), np.arange(n)
+        itask = rng.choice([13, 14, 15, 19, 20, 21, 22, 23, 24, 25, 26], size=n)
+    env = VecCraft.from_instances(tables, grids, ienv, ipos, itask, max_timesteps=19)
+    orc = _OracleTicks(oracle, grids, ienv, ipos, itask, max_timesteps=19)
+    out = env.tick(actions=None, advance_first=True)            # no step: observe the start states
+    ref_e, _, _ = oracle.expert(orc.grid, orc.inv, orc.pos, orc.dir, orc.task)
+    assert np.array_equal(_np(out["expert"]).astype(np.int32), ref_e)
+    assert np.array_equal(_np(out["features"]), oracle.features(orc.grid, orc.inv, orc.pos, orc.dir))
+    assert not _np(out["done"]).any() and not _np(out["success"]).any()
+    for t in range(45):
+        a = rng.choice(6, size=n, p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8)
+        out = env.tick(actions=torch.from_numpy(a), advance_first=True, want_features=bool(t % 3))
+        ref = orc.tick(a, want_features=False)                   # applies a; flags of that step
+        assert np.array_equal(_np(out["done"]), ref["done"]), t
+        assert np.array_equal(_np(out["success"]), ref["success"]), t
+        ref_e, _, _ = oracle.expert(orc.grid, orc.inv, orc.pos, orc.dir, orc.task)
+        assert np.array_equal(_np(out["expert"]).astype(np.int32), ref_e), t
+        if t % 3:
+            assert np.array_equal(_np(out["features"]), oracle.features(orc.grid, orc.inv, orc.pos, orc.dir)), t
+        orc.assert_state_equals(env)
+    env.check_errors()

@@ -70,3 +70,48 @@ def test_instruct_and_describe():
     assert mine == theirs
     assert t.student_action_map == r.student_action_map
     assert cfg.random.randint(1 << 30) == cfg2.random.randint(1 << 30)     # same stream position
+
+
+def _pack(eps, L):
+    """Episodes of _episodes() -> (actions [N, L], agent records [L + 1, N, 32], lengths [N])."""
+    n = len(eps)
+    acts = np.zeros((n, L), np.int64)
+    agent = np.zeros((L + 1, n, 32), np.uint8)
+    lengths = np.zeros(n, np.int64)
+    for i, (a, states) in enumerate(eps):
+        lengths[i] = len(a)
+        acts[i, :len(a)] = a
+        for t in range(L + 1):
+            s = states[min(t, len(states) - 1)]
+            agent[t, i, 24], agent[t, i, 25] = s.pos[0] + 100, s.pos[1] + 100   # only differences matter
+            agent[t, i, :3] = s.inventory
+    return acts, agent, lengths
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_describe_batch_equals_describe(seed):
+    """describe_batch (tensor operations over [N, L], host loop only per new action-map entry)
+    against describe called rollout by rollout: same words, same learned map after every call,
+    same position of the shared random stream — over several consecutive batches, starting from an
+    empty map (so the first calls exercise the learning / guessing / last-id-inference paths)."""
+    import torch
+    from psketch_b200.teachers import PrimitiveLanguageTeacher
+    from psketch_b200.teachers.primitive_language import ACTION_WORDS
+    world = _world()
+    a = PrimitiveLanguageTeacher(types.SimpleNamespace(random=np.random.RandomState(seed)))
+    b = PrimitiveLanguageTeacher(types.SimpleNamespace(random=np.random.RandomState(seed)))
+    rng = np.random.RandomState(100 + seed)
+    perm_rng = np.random.RandomState(seed)               # one student = one private id permutation
+    for call in range(6):
+        eps = _episodes(np.random.RandomState(rng.randint(1 << 30)), n=3 if call < 3 else 40)
+        perm = perm_rng.permutation(6) if call == 0 else perm
+        # re-label with a permutation that stays fixed across calls
+        eps = [([int(perm[x % 6]) for x in acts], states) for acts, states in eps]
+        want = [a.describe(world, acts, states) for acts, states in eps]
+        acts, agent, lengths = _pack(eps, 9)
+        got = b.describe_batch(torch.from_numpy(acts), torch.from_numpy(agent), torch.from_numpy(lengths), n_kinds=3)
+        got = [[ACTION_WORDS[w] for w in row[:n]] for row, n in zip(got.tolist(), lengths)]
+        assert got == want, call
+        assert a.student_action_map == b.student_action_map, call
+    assert a.random.randint(1 << 30) == b.random.randint(1 << 30)
+    assert len(b.student_action_map) == 6
