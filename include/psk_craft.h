@@ -102,7 +102,8 @@ const char *psk_version(void);
  *   rollout_variant  CTA shape of craft_rollout_kernel: 0 = 64 env threads + 2 feature warps,
  *                    2 = 32 + 2, 3 = 16 + 2, 4 = 16 + 1
  *   rollout_tma      0 = 128-bit vector stores, 1 = TMA bulk stores (cp.async.bulk)
- *   rollout_split    1 = decoupled teacher / feature kernels on two streams (psk_craft_rollout)
+ *   tile_chain       0 = consecutive fused launches wait for the whole previous grid
+ *                    (griddepcontrol.wait); default: per-tile ticket counters (psk_common.cuh)
  *   tick_variant     CTA shape of craft_tick_kernel: 0 = 64+2, 1 = 128+4, 2 = 32+1, 3 = 64+4, 4 = 32+2
  *   tick_tma, tick_persist, feat_persist, tick_pdl, step_variant (0 = tables staged in shared memory)
  * Unknown keys return PSK_ERR_BADARG.  Results never depend on a knob (tests/test_craft_gpu.py). */

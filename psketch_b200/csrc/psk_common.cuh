@@ -174,6 +174,37 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tile chaining: fine-grained ordering between consecutive launches of the fused kernels.
+// Envs never interact, so tile b of launch k+1 depends only on the launch-k CTA that owned the same
+// envs — not on the whole grid.  With programmatic dependent launch the next grid becomes resident
+// while the current one drains; instead of griddepcontrol.wait (= the WHOLE previous grid complete
+// and flushed) its CTAs wait for their own predecessors through a pair of counters per group of
+// PSK_CHAIN_GROUP envs:  chain[2g] tickets handed out, chain[2g+1] ticket holders finished.
+// A CTA takes one ticket per group it owns (its position in that group's launch order), waits until
+// every earlier holder has finished (ld.acquire: also drops stale L1 lines), and on exit publishes
+// its state writes with fence + st.release.  The ticket is taken BEFORE launch_dependents, so a
+// dependent CTA can never overtake its predecessor's ticket; the earliest holder of a group never
+// waits on an unfinished CTA, so the chain always drains.  Counters only ever increase (u32 wrap
+// is harmless under ==), which is what makes the scheme work under CUDA-graph replay.
+#define PSK_CHAIN_GROUP 16
+#define PSK_CHAIN_GROUPS (1 << 20)
+__device__ __forceinline__ uint32_t chain_enter(uint32_t *chain, int64_t g) {
+    return atomicAdd(chain + 2 * g, 1u);
+}
+__device__ __forceinline__ void chain_wait(const uint32_t *chain, int64_t g, uint32_t ticket) {
+    uint32_t v;
+    while (true) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(chain + 2 * g + 1) : "memory");
+        if (v == ticket) break;
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ void chain_leave(uint32_t *chain, int64_t g, uint32_t ticket) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(chain + 2 * g + 1), "r"(ticket + 1) : "memory");
+}
+
 // Host-side per-device caches (SM count, shared-memory attributes, table copies) are indexed by this.
 #define PSK_MAX_DEVICES 32
 static inline int current_device() {

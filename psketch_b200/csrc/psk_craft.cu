@@ -1440,7 +1440,8 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
                   const uint8_t *__restrict__ init_agent, float *__restrict__ features_out,
                   uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
                   uint8_t *__restrict__ success_out, unsigned long long *stats,
-                  int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int adv_first) {
+                  int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int adv_first,
+                  uint32_t *chain) {
     constexpr int NT = NE + NFW * 32;
     constexpr int TPE = 8, EPW = 32 / TPE;
     constexpr int SPW = NE / NFW;              // env slots per feature warp
@@ -1451,18 +1452,34 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
     __shared__ SharedTables st;
     __shared__ __align__(16) uint8_t s_rows[NE * CP];
     __shared__ __align__(16) uint32_t s_agent[NE * 8];
+    __shared__ uint32_t s_ticket[NE / PSK_CHAIN_GROUP];
+    const int tid = threadIdx.x;
+    const bool env_warp = tid < NE;
+    // tile chaining (psk_common.cuh): one ticket per group of envs this CTA owns, taken before the
+    // next grid may launch; chain == NULL (persistent grids, huge batches) falls back to waiting
+    // for the whole previous grid
+    const int64_t grp0 = (int64_t)blockIdx.x * (NE / PSK_CHAIN_GROUP);
+    const bool chain_thread = chain && tid < NE / PSK_CHAIN_GROUP &&
+                              (grp0 + tid) * PSK_CHAIN_GROUP < n;
+    if (chain) {
+        if (chain_thread) s_ticket[tid] = chain_enter(chain, grp0 + tid);
+        __syncthreads();
+    }
     // Programmatic dependent launch: let the next kernel in the stream (normally the next tick)
     // be scheduled while this one drains, and do everything that does not depend on the previous
     // kernel (tables, buffer init) before waiting for it.  Both are no-ops for a plain launch.
     asm volatile("griddepcontrol.launch_dependents;");
     stage_tables(st, T);
-    const int tid = threadIdx.x;
-    const bool env_warp = tid < NE;
     if (!USE_TMA && !env_warp && features_out)
         feature_buffer_init<8, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
             smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
             nf);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (chain) {
+        if (chain_thread) chain_wait(chain, grp0 + tid, s_ticket[tid]);
+        __syncthreads();
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     uint32_t flags = 0;
     int it = 0;  // this feature warp's chunk counter
     const int64_t n_super = (n + NE - 1) / NE;
@@ -1581,6 +1598,7 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
         }
         __syncthreads();  // s_rows / s_agent are recycled by the next super-tile
     }
+    if (chain_thread) chain_leave(chain, grp0 + tid, s_ticket[tid]);   // after the barrier above
     if (USE_TMA && !env_warp && (tid & 31) == 0) bulk_wait_read<0>();
     if (flags && err_flags) atomicOr(err_flags, (int)flags);
 }
@@ -1609,7 +1627,8 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
                      const uint8_t *__restrict__ init_agent, float *__restrict__ features_out,
                      int feat_ring, uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
                      uint8_t *__restrict__ success_out, unsigned long long *stats,
-                     int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int ticks) {
+                     int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int ticks,
+                     uint32_t *chain) {
     constexpr int NEW = (NE + 31) / 32 * 32;   // env-warp threads (lanes >= NE idle when NE < 32)
     constexpr int NT = NEW + NFW * 32;
     constexpr int TPE = 8, EPW = 32 / TPE;
@@ -1621,15 +1640,28 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
     __shared__ SharedTables st;
     __shared__ __align__(16) uint8_t s_rows[2][NE * CP];
     __shared__ __align__(16) uint32_t s_agent[2][NE * 8];
-    asm volatile("griddepcontrol.launch_dependents;");
-    stage_tables(st, T);
+    __shared__ uint32_t s_ticket[NE / PSK_CHAIN_GROUP];
     const int tid = threadIdx.x;
     const bool env_warp = tid < NEW;
+    const int64_t grp0 = (int64_t)blockIdx.x * (NE / PSK_CHAIN_GROUP);     // tile chaining, see the tick kernel
+    const bool chain_thread = chain && tid < NE / PSK_CHAIN_GROUP &&
+                              (grp0 + tid) * PSK_CHAIN_GROUP < n;
+    if (chain) {
+        if (chain_thread) s_ticket[tid] = chain_enter(chain, grp0 + tid);
+        __syncthreads();
+    }
+    asm volatile("griddepcontrol.launch_dependents;");
+    stage_tables(st, T);
     if (!USE_TMA && !env_warp && features_out)
         feature_buffer_init<8, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
             smem_u32(smem_raw) + (uint32_t)((tid - NEW) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
             nf);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (chain) {
+        if (chain_thread) chain_wait(chain, grp0 + tid, s_ticket[tid]);
+        __syncthreads();
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     uint32_t flags = 0;
     int it = 0;
     const int64_t n_super = (n + NE - 1) / NE;
@@ -1738,6 +1770,7 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
         }
         __syncthreads();
     }
+    if (chain_thread) chain_leave(chain, grp0 + tid, s_ticket[tid]);   // after the barrier above
     if (USE_TMA && !env_warp && (tid & 31) == 0) bulk_wait_read<0>();
     if (flags && err_flags) atomicOr(err_flags, (int)flags);
 }
@@ -1761,10 +1794,10 @@ static int num_sms() {
 // changed at any time afterwards, so tests and A/B runs can force every kernel variant.
 enum TuneKey { TUNE_ROLLOUT_VARIANT, TUNE_ROLLOUT_TMA, TUNE_TICK_VARIANT, TUNE_TICK_TMA,
                TUNE_TICK_PERSIST, TUNE_FEAT_PERSIST, TUNE_TICK_PDL, TUNE_STEP_VARIANT,
-               TUNE_ROLLOUT_SPLIT, TUNE_COUNT };
+               TUNE_TILE_CHAIN, TUNE_COUNT };
 static const char *const tune_names[TUNE_COUNT] = {
     "rollout_variant", "rollout_tma", "tick_variant", "tick_tma", "tick_persist", "feat_persist",
-    "tick_pdl", "step_variant", "rollout_split"};
+    "tick_pdl", "step_variant", "tile_chain"};
 static std::atomic<int> tune_val[TUNE_COUNT];
 static std::once_flag tune_once;
 static void tune_init() {
@@ -1837,6 +1870,26 @@ static const psk_craft_tables *device_tables(const psk_craft_tables *t, cudaStre
     c.last = i;
     return c.slot[i].dev;
 }
+// Tile-chaining counters (psk_common.cuh), one zero-initialised array per device, allocated on the
+// first call (like the table copies: outside a CUDA-graph capture).  NULL = do not chain.
+static uint32_t *chain_counters(int64_t n) {
+    static uint32_t *ctr[PSK_MAX_DEVICES] = {nullptr};
+    static std::mutex mu;
+    if (tune(TUNE_TILE_CHAIN) == 0 || tune(TUNE_TICK_PDL) == 0) return nullptr;
+    if ((n + PSK_CHAIN_GROUP - 1) / PSK_CHAIN_GROUP > PSK_CHAIN_GROUPS) return nullptr;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ctr[dev]) {
+        const size_t bytes = (size_t)2 * PSK_CHAIN_GROUPS * sizeof(uint32_t);
+        if (cudaMalloc(&ctr[dev], bytes) != cudaSuccess) return nullptr;
+        if (cudaMemset(ctr[dev], 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+            cudaFree(ctr[dev]);
+            ctr[dev] = nullptr;
+        }
+    }
+    return ctr[dev];
+}
+
 #define PSK_DT(var)                                   \
     const psk_craft_tables *var = device_tables(t, st); \
     if (!var) return PSK_ERR_CUDA
@@ -2001,9 +2054,10 @@ template <int W, int H, int WIN> struct Config {
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
         const int cell_stride = s.cell_stride, K = t->n_kinds;
+        uint32_t *chain = (g == tiles && pdl) ? chain_counters(s.n) : nullptr;   // one tile per CTA only
         return check(cudaLaunchKernelEx(&cfg, kern, dt, s.grid, s.agent, action_in, ep.scen_grid,
                                         ep.scen_idx, ep.init_agent, features_out, expert_out, done,
-                                        success, stats, err, s.n, cell_stride, K, f, adv_first));
+                                        success, stats, err, s.n, cell_stride, K, f, adv_first, chain));
     }
     template <int NE, int NFW, bool TMA>
     static int rollout_variant(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
@@ -2039,10 +2093,11 @@ template <int W, int H, int WIN> struct Config {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         const int cell_stride = s.cell_stride, K = t->n_kinds;
+        uint32_t *chain = chain_counters(s.n);
         return check(cudaLaunchKernelEx(&cfg, kern, dt, s.grid, s.agent, action_in, ep.scen_grid,
                                         ep.scen_idx, ep.init_agent, features_out, feat_ring,
                                         expert_out, done, success, stats, err, s.n, cell_stride, K,
-                                        f, ticks));
+                                        f, ticks, chain));
     }
     static int rollout(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep, int ticks,
                        const uint8_t *action_in, float *features_out, int feat_ring,
