@@ -487,8 +487,9 @@ def run_ours(args):
             "timing": "the K-step plan is replayed `repeats` times back to back with CUDA events in "
                       "between (one untimed replay first); value = envs x K / median per-K time, MAX over "
                       "ranks per repeat; timed_region_ms is the whole window",
-            "l2": "feature outputs rotate through a ring of %d frames (%.0f MB > 126 MB L2), every "
-                  "launch continuing where the previous one stopped" % (ring, ring * feat_bytes / 1e6),
+            "l2": "feature outputs rotate through a ring of %d frames (%.0f MB > 126 MB L2); tick t of a "
+                  "launch writes slot t %% ring, so a line is rewritten only after >= 850 MB of other "
+                  "writes" % (ring, ring * feat_bytes / 1e6),
         },
         "clocks": clocks,
         "gpu_launches": timed_launches // R,
@@ -578,6 +579,7 @@ def per_kernel_table(torch, env, n, nf, dev, peak, n_bufs):
                         ("expert", lambda: env.expert(out=act), BYTES_EXPERT),
                         ("step", lambda: env.step(act), BYTES_STEP),
                         ("tick_fused", f_tick, BYTES_FUSED)):
+        env.restore(snap)               # every kernel is timed from the same states
         dt = time_kernel(fn, torch, inner=len(big) if name != "expert" and name != "step" else 10)
         kern[name] = {"us": dt * 1e6, "GBps": b * n / dt / 1e9, "frac": b * n / dt / 1e9 / peak,
                       "env_per_s": n / dt}
