@@ -543,6 +543,11 @@ def run_ours(args):
         line["kernels_1m"] = k1
         del env1
         torch.cuda.empty_cache()
+    if world == 1 and not args.no_light:
+        try:
+            line["light_world"] = light_record(torch, dev, peak)
+        except Exception as ex:  # noqa: BLE001
+            line["light_world"] = {"error": repr(ex)}
     # ---- CPU baselines on this box's host cores (bounded samples; single-GPU runs only)
     if not args.no_cpu and world == 1:
         line["cpu_baseline"] = dict(cpu_python_port(budget_s=12.0)[0], port_vs_reference=PORT_VS_REFERENCE)
@@ -586,6 +591,43 @@ def per_kernel_table(torch, env, n, nf, dev, peak, n_bufs):
     env.restore(snap)
     del big
     return kern
+
+
+def light_record(torch, dev, peak):
+    """Secondary record: the Light world (worlds/light.py) ported the same way — fused tick (table
+    teacher + 12 features + step / auto-reset, one launch) on the reference's 60 scenarios."""
+    from psketch_b200.worlds.light import LightWorld, VecLight
+    goals = ("LL", "LD", "RD", "UL", "UR", "URU", "DRU", "LLD", "RDD", "LUR")
+    w = LightWorld()
+    scens = [w.sample_scenario_with_goal(g) for rep in range(6) for g in goals]
+    rec = {"scenarios": len(scens), "algorithmic_bytes_per_env_step": 63}
+    for n in (65536, 1 << 20):
+        v = VecLight(scens, np.arange(n) % len(scens), device=dev)
+        t0 = time.perf_counter()
+        v._table = None
+        v.teacher_table()
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - t0) * 1e3
+        out = {}
+        feats = [torch.empty((n, 12), dtype=torch.float32, device=dev) for _ in range(4)]
+        cnt = [0]
+
+        def f():
+            v.tick(features_out=feats[cnt[0] % 4], out=out, max_timesteps=100)
+            cnt[0] += 1
+        for _ in range(30):
+            f()                                    # envs spread over their episodes
+        dt = time_kernel(f, torch, inner=8, reps=30)
+        dt_lookup = time_kernel(lambda: v.expert(), torch, inner=8, reps=20)
+        r = {"tick_us": dt * 1e6, "env_steps_per_s": n / dt, "GBps": 63 * n / dt / 1e9,
+             "frac": 63 * n / dt / 1e9 / peak, "teacher_lookup_us": dt_lookup * 1e6,
+             "teacher_table_build_ms_wall": build_ms}
+        if n == 65536:
+            dt_search = time_kernel(lambda: v.expert(search=True), torch, inner=2, reps=3)
+            r["teacher_search_kernel_us"] = dt_search * 1e6       # round 1: one flood per env
+        rec["n_%d" % n] = r
+        del v, feats
+    return rec
 
 
 def measure_config3(torch, dist, pdist, tables, rank, world, dev, args):
@@ -726,6 +768,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed kernel")
     ap.add_argument("--no-1m", action="store_true", help="skip the 1,048,576-env per-kernel table")
     ap.add_argument("--no-config3", action="store_true", help="skip BASELINE config 3 (world > 1)")
+    ap.add_argument("--no-light", action="store_true", help="skip the Light-world secondary record")
     ap.add_argument("--policy", default="teacher", choices=["teacher", "random"],
                     help="who acts: the teacher (BASELINE config) or uniform random actions (off-policy variant)")
     args = ap.parse_args()

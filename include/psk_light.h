@@ -54,6 +54,32 @@ int psk_light_expert(const psk_light_scenario *scen, const int32_t *scen_idx,
                      const uint8_t *state, uint8_t *action, int16_t *dist, int32_t max_keys,
                      int64_t n, void *stream);
 
+/* The teacher as a table.  Its answer depends only on (scenario, x, y, keys on the map) — at most
+ * 32 x 32 x 2^n_keys states per scenario, shared by all envs of the scenario — so the backward
+ * flood of psk_light_expert runs once per scenario (one CTA each) and every later query is a few
+ * loads.  table u16[n_scen][1 << max_keys][32][32]: fewest actions to the goal room from cell
+ * (x, y) with key subset m on the map, 0xFFFF = unreachable; psk_light_teacher_table_bytes gives its
+ * size.  psk_light_expert_table answers like psk_light_expert (same actions, same dist). */
+int64_t psk_light_teacher_table_bytes(int64_t n_scen, int32_t max_keys);
+int psk_light_teacher_build(const psk_light_scenario *scen, int64_t n_scen, int32_t max_keys,
+                            uint16_t *table, void *stream);
+int psk_light_expert_table(const psk_light_scenario *scen, const int32_t *scen_idx, const uint8_t *state,
+                           const uint16_t *table, int32_t max_keys, uint8_t *action, int16_t *dist,
+                           int64_t n, void *stream);
+
+/* One rollout tick for every env, the Craft tick's contract (psk_craft_tick) on this world:
+ *     ref = teacher(s); f = s.features(); a = action_in ? action_in[i] : ref
+ *     elapsed += 1; done = a not in 0..4 (teacher: 254 already in the goal room, 255 unreachable)
+ *                          or elapsed >= max_timesteps
+ *     done -> success = s.satisfies(goal); s <- LightScenario.init()       !done -> s = s.step(a)
+ * state byte 3 counts the steps of the running episode (0 after psk_light_reset).  features_out
+ * f32[n][12] (may be NULL), expert_out u8[n], done_out / success_out u8[n] (may be NULL), stats
+ * u64[4] {episodes, successes, env_steps, reserved} (may be NULL). */
+int psk_light_tick(const psk_light_scenario *scen, const int32_t *scen_idx, uint8_t *state,
+                   const uint16_t *table, int32_t max_keys, const uint8_t *action_in,
+                   float *features_out, uint8_t *expert_out, uint8_t *done_out, uint8_t *success_out,
+                   unsigned long long *stats, int32_t max_timesteps, int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

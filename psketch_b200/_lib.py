@@ -114,7 +114,7 @@ def load():
 
 
 LIGHT_EXPORTS = ("psk_light_reset", "psk_light_step", "psk_light_features", "psk_light_satisfies",
-                 "psk_light_expert")
+                 "psk_light_expert", "psk_light_teacher_build", "psk_light_expert_table", "psk_light_tick")
 _light_bound = False
 
 
@@ -129,6 +129,12 @@ def load_light():
         lib.psk_light_features.argtypes = [vp, vp, vp, vp, i64, vp]
         lib.psk_light_satisfies.argtypes = [vp, vp, vp, vp, i64, vp]
         lib.psk_light_expert.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int32, i64, vp]
+        i32 = ctypes.c_int32
+        lib.psk_light_teacher_table_bytes.argtypes = [i64, i32]
+        lib.psk_light_teacher_table_bytes.restype = ctypes.c_int64
+        lib.psk_light_teacher_build.argtypes = [vp, i64, i32, vp, vp]
+        lib.psk_light_expert_table.argtypes = [vp, vp, vp, vp, i32, vp, vp, i64, vp]
+        lib.psk_light_tick.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i64, vp]
         for name in LIGHT_EXPORTS:
             getattr(lib, name).restype = ctypes.c_int
         _light_bound = True

@@ -65,7 +65,8 @@ light_step_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__
         if (light_wall(s, nx, ny)) { nx = x; ny = y; }      // light.py:231-232
         // doors are tested against the keys BEFORE this step's pick-up (light.py:233 uses self.keys)
         if (light_locked_door(s, nx, ny, alive)) { nx = x; ny = y; }
-        reinterpret_cast<uint32_t *>(state)[e] = uint32_t(nx) | (uint32_t(ny) << 8) | (n_alive << 16);
+        reinterpret_cast<uint32_t *>(state)[e] = uint32_t(nx) | (uint32_t(ny) << 8) | (n_alive << 16) |
+                                                 (st & 0xFF000000u);   // byte 3: psk_light_tick's step counter
     }
     if (flags && err_flags) atomicOr(err_flags, (int)flags);
 }
@@ -250,6 +251,197 @@ light_expert_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Teacher as a table.  The teacher's answer is a function of (scenario, x, y, keys on the map), a
+// state space of at most 32 x 32 x 2^n_keys per scenario, shared by every env of that scenario — so
+// instead of one search per env and query (light_expert_kernel above: 8.4 ms per 65,536 envs) the
+// backward flood runs ONCE per scenario and records, for every key subset m and cell, the level at
+// which the cell entered R[m]: dist u16[n_scen][2^max_keys][32][32] (0xFFFF = goal room unreachable).
+// One CTA per scenario; warp w sweeps the layers m = w, w + 8, ...; lane x holds row x; all layers
+// advance level by level (Jacobi: a level reads only the previous level's boards, double-buffered in
+// shared memory), one __syncthreads_or per level.  A query is then a handful of loads.
+__global__ void __launch_bounds__(256)
+light_teacher_build_kernel(const psk_light_scenario *__restrict__ scen, uint16_t *__restrict__ table,
+                           int layer_cap) {
+    extern __shared__ uint32_t s_boards[];           // [2][layer_cap][32]
+    const psk_light_scenario &s = scen[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int nk = s.n_keys;
+    const int n_layers = 1 << nk;
+    uint16_t *T = table + (size_t)blockIdx.x * layer_cap * 1024;
+    for (int i = threadIdx.x; i < layer_cap * 1024; i += blockDim.x) T[i] = 0xFFFFu;
+    __syncthreads();
+    if (n_layers > layer_cap) return;               // more keys than announced: everything unreachable
+    const uint32_t wall_row = s.walls[lane];
+    uint32_t goal_row = 0;
+    if (lane / PSK_LIGHT_ROOM == s.goal_rx)
+        goal_row = (0x3Fu << (s.goal_ry * PSK_LIGHT_ROOM)) & ~wall_row;
+    auto lock_row = [&](int m) {                     // locked-door cells of this lane's row in layer m
+        uint32_t r = 0;
+        for (int k = 0; k < nk; k++)
+            if (((m >> k) & 1) && s.keys[k][2] == lane) r |= 1u << s.keys[k][3];
+        return r;
+    };
+    uint32_t *B0 = s_boards, *B1 = s_boards + layer_cap * 32;
+    for (int m = warp; m < n_layers; m += nwarps) {
+        const uint32_t r = goal_row & ~lock_row(m);
+        B0[m * 32 + lane] = r;
+        for (uint32_t b = r; b; b &= b - 1) T[(m * 32 + lane) * 32 + (__ffs(b) - 1)] = 0;
+    }
+    __syncthreads();
+    for (int level = 1; level < 0xFFFF; level++) {
+        const uint32_t *prev = (level & 1) ? B0 : B1;
+        uint32_t *cur = (level & 1) ? B1 : B0;
+        int grew = 0;
+        for (int m = warp; m < n_layers; m += nwarps) {
+            const uint32_t c = prev[m * 32 + lane];
+            const uint32_t pass = ~wall_row & ~lock_row(m);
+            const uint32_t up = __shfl_up_sync(FULL, c, 1), dn = __shfl_down_sync(FULL, c, 1);
+            uint32_t add = (c << 1) | (c >> 1) | (lane > 0 ? up : 0u) | (lane < 31 ? dn : 0u);
+            // USE on a key cell: every key of m lying on that cell is picked up (light.py:224-228)
+            for (int k = 0; k < nk; k++) {
+                if (!((m >> k) & 1) || s.keys[k][0] != lane) continue;
+                int gone = 0;
+                for (int j = 0; j < nk; j++)
+                    if (((m >> j) & 1) && s.keys[j][0] == s.keys[k][0] && s.keys[j][1] == s.keys[k][1])
+                        gone |= 1 << j;
+                const uint32_t bit = 1u << s.keys[k][1];
+                if (prev[(m & ~gone) * 32 + lane] & bit) add |= bit;
+            }
+            const uint32_t nxt = c | (add & pass);
+            cur[m * 32 + lane] = nxt;
+            for (uint32_t b = nxt & ~c; b; b &= b - 1)
+                T[(m * 32 + lane) * 32 + (__ffs(b) - 1)] = (uint16_t)level;
+            grew |= nxt != c;
+        }
+        if (!__syncthreads_or(grew)) break;
+    }
+}
+
+// Teacher query against the table (thread per env).  dist 0 = in the goal room (action 254),
+// 0xFFFF = unreachable (action 255); else the smallest action whose successor is one level closer.
+__device__ __forceinline__ int light_table_action(const psk_light_scenario &s, const uint16_t *T,
+                                                  int x, int y, uint32_t alive, int &dist) {
+    if (x / PSK_LIGHT_ROOM == s.goal_rx && y / PSK_LIGHT_ROOM == s.goal_ry && !light_wall(s, x, y)) {
+        dist = 0;
+        return 254;
+    }
+    const int d = T[(alive * 32 + (x & 31)) * 32 + (y & 31)];
+    if (d == 0xFFFF) {
+        dist = -1;
+        return 255;
+    }
+    dist = d;
+    for (int a = 0; a < 4; a++) {
+        const int nx = x + dx_of(a), ny = y + dy_of(a);
+        if (light_wall(s, nx, ny) || light_locked_door(s, nx, ny, alive)) continue;
+        if (T[(alive * 32 + nx) * 32 + ny] == d - 1) return a;
+    }
+    uint32_t m2 = alive;
+    for (int k = 0; k < s.n_keys; k++)
+        if (((alive >> k) & 1) && s.keys[k][0] == x && s.keys[k][1] == y) m2 &= ~(1u << k);
+    if (m2 != alive && T[(m2 * 32 + x) * 32 + y] == d - 1) return 4;
+    return 255;
+}
+
+__global__ void __launch_bounds__(256)
+light_expert_table_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
+                          const uint8_t *__restrict__ state, const uint16_t *__restrict__ table,
+                          int layer_cap, uint8_t *__restrict__ action, int16_t *__restrict__ dist_out,
+                          int64_t n) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int si = scen_idx[e];
+        const psk_light_scenario &s = scen[si];
+        const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
+        int d;
+        const int a = light_table_action(s, table + (size_t)si * layer_cap * 1024, st & 0xFF, (st >> 8) & 0xFF,
+                                         (st >> 16) & 0xFF, d);
+        action[e] = (uint8_t)a;
+        if (dist_out) dist_out[e] = (int16_t)d;
+    }
+}
+
+// Fused Light tick (thread per env) — the Craft tick's contract on this world:
+//     ref = teacher(s); f = s.features(); a = action_in ? action_in[e] : ref
+//     elapsed += 1; done = a is not one of the 5 actions (the teacher's "already there" 254 /
+//                          "unreachable" 255) or elapsed >= max_timesteps
+//     done -> success = s.satisfies(goal); s <- LightScenario.init()      !done -> s = s.step(a)
+// state byte 3 counts the steps of the running episode.
+__global__ void __launch_bounds__(256)
+light_tick_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
+                  uint8_t *__restrict__ state, const uint16_t *__restrict__ table, int layer_cap,
+                  const uint8_t *__restrict__ action_in, float *__restrict__ features_out,
+                  uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
+                  uint8_t *__restrict__ success_out, unsigned long long *stats, int max_timesteps,
+                  int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+        const int64_t e = base + (threadIdx.x & 31);
+        bool live = e < n, done = false, success = false;
+        if (live) {
+            const int si = scen_idx[e];
+            const psk_light_scenario &s = scen[si];
+            const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
+            const int x = st & 0xFF, y = (st >> 8) & 0xFF;
+            const uint32_t alive = (st >> 16) & 0xFF;
+            int d;
+            const int ref = light_table_action(s, table + (size_t)si * layer_cap * 1024, x, y, alive, d);
+            expert_out[e] = (uint8_t)ref;
+            if (features_out) {                                   // light.py:191-204, see light_features_kernel
+                float locked = 0.f, open = 0.f, key = 0.f;
+                for (int dd = 0; dd < s.n_doors; dd++)
+                    if (s.doors[dd][0] == x && s.doors[dd][1] == y) {
+                        if (light_locked_door(s, x, y, alive)) locked += 1.f; else open += 1.f;
+                    }
+                for (int k = 0; k < s.n_keys; k++)
+                    if (((alive >> k) & 1) && s.keys[k][0] == x && s.keys[k][1] == y &&
+                        x % PSK_LIGHT_ROOM != 0 && y % PSK_LIGHT_ROOM != 0)
+                        key += 1.f;
+                float4 *o = reinterpret_cast<float4 *>(features_out + e * PSK_LIGHT_N_FEATURES);
+                __stcs(o, make_float4(locked, locked, locked, locked));
+                __stcs(o + 1, make_float4(open, open, open, open));
+                __stcs(o + 2, make_float4(key, key, key, key));
+            }
+            const int a = action_in ? action_in[e] : ref;
+            const int elapsed = (int)(st >> 24) + 1;
+            done = a >= PSK_LIGHT_N_ACTIONS || elapsed >= max_timesteps;
+            uint32_t nst;
+            if (done) {
+                success = (x / PSK_LIGHT_ROOM == s.goal_rx) && (y / PSK_LIGHT_ROOM == s.goal_ry);
+                const uint32_t all = s.n_keys >= 8 ? 0xFFu : ((1u << s.n_keys) - 1u);
+                nst = uint32_t(s.init_x) | (uint32_t(s.init_y) << 8) | (all << 16);
+            } else {
+                uint32_t n_alive = alive;
+                int nx = x, ny = y;
+                if (a < 4) {
+                    nx = x + dx_of(a);
+                    ny = y + dy_of(a);
+                    if (light_wall(s, nx, ny) || light_locked_door(s, nx, ny, alive)) { nx = x; ny = y; }
+                } else {
+                    for (int k = 0; k < s.n_keys; k++)
+                        if (((alive >> k) & 1) && s.keys[k][0] == x && s.keys[k][1] == y) n_alive &= ~(1u << k);
+                }
+                nst = uint32_t(nx) | (uint32_t(ny) << 8) | (n_alive << 16) | (uint32_t(elapsed) << 24);
+            }
+            reinterpret_cast<uint32_t *>(state)[e] = nst;
+            if (done_out) done_out[e] = done;
+            if (success_out) success_out[e] = success;
+        }
+        if (stats) {
+            const int nd = __popc(__ballot_sync(0xffffffffu, done));
+            const int ns = __popc(__ballot_sync(0xffffffffu, success));
+            const int nl = __popc(__ballot_sync(0xffffffffu, live));
+            if ((threadIdx.x & 31) == 0) {
+                if (nd) atomicAdd(stats + 0, (unsigned long long)nd);
+                if (ns) atomicAdd(stats + 1, (unsigned long long)ns);
+                if (nl) atomicAdd(stats + 2, (unsigned long long)nl);
+            }
+        }
+    }
+}
+
 static inline int lblocks(int64_t n, int per) {
     int64_t b = (n + per - 1) / per;
     return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
@@ -322,6 +514,57 @@ int psk_light_expert(const psk_light_scenario *scen, const int32_t *scen_idx,
     }
     light_expert_kernel<<<lblocks(n, wpb), wpb * 32, smem, (cudaStream_t)stream>>>(
         scen, scen_idx, state, action, dist, n, layer_cap);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+int64_t psk_light_teacher_table_bytes(int64_t n_scen, int32_t max_keys) {
+    if (n_scen < 0 || max_keys < 0 || max_keys > PSK_LIGHT_MAX_KEYS) return -1;
+    return n_scen * ((int64_t)1 << max_keys) * 1024 * (int64_t)sizeof(uint16_t);
+}
+
+int psk_light_teacher_build(const psk_light_scenario *scen, int64_t n_scen, int32_t max_keys,
+                            uint16_t *table, void *stream) {
+    if (n_scen < 0 || max_keys < 0 || max_keys > PSK_LIGHT_MAX_KEYS || (n_scen && (!scen || !table)))
+        return PSK_ERR_BADARG;
+    if (n_scen == 0) return PSK_OK;
+    const int layer_cap = 1 << max_keys;
+    const size_t smem = (size_t)2 * layer_cap * 32 * sizeof(uint32_t);       // 64 KB at 8 keys
+    static size_t configured_on[PSK_MAX_DEVICES] = {0};
+    size_t &configured = configured_on[current_device()];
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(light_teacher_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess)
+            return PSK_ERR_CUDA;
+        configured = smem;
+    }
+    light_teacher_build_kernel<<<(unsigned)n_scen, 256, smem, (cudaStream_t)stream>>>(scen, table, layer_cap);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+int psk_light_expert_table(const psk_light_scenario *scen, const int32_t *scen_idx, const uint8_t *state,
+                           const uint16_t *table, int32_t max_keys, uint8_t *action, int16_t *dist,
+                           int64_t n, void *stream) {
+    if (!light_args_ok(scen, scen_idx, state, n) || (n && (!action || !table)) || max_keys < 0 ||
+        max_keys > PSK_LIGHT_MAX_KEYS)
+        return PSK_ERR_BADARG;
+    if (n == 0) return PSK_OK;
+    light_expert_table_kernel<<<lblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        scen, scen_idx, state, table, 1 << max_keys, action, dist, n);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+int psk_light_tick(const psk_light_scenario *scen, const int32_t *scen_idx, uint8_t *state,
+                   const uint16_t *table, int32_t max_keys, const uint8_t *action_in,
+                   float *features_out, uint8_t *expert_out, uint8_t *done_out, uint8_t *success_out,
+                   unsigned long long *stats, int32_t max_timesteps, int64_t n, void *stream) {
+    if (!light_args_ok(scen, scen_idx, state, n) || (n && (!expert_out || !table)) || max_keys < 0 ||
+        max_keys > PSK_LIGHT_MAX_KEYS || max_timesteps <= 0 || max_timesteps > 255)
+        return PSK_ERR_BADARG;
+    if (features_out && (reinterpret_cast<uintptr_t>(features_out) & 15)) return PSK_ERR_BADARG;
+    if (n == 0) return PSK_OK;
+    light_tick_kernel<<<lblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        scen, scen_idx, state, table, 1 << max_keys, action_in, features_out, expert_out, done_out,
+        success_out, stats, max_timesteps, n);
     return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
 }
 

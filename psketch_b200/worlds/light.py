@@ -249,15 +249,62 @@ class VecLight(object):
         _lib.check(rc, "psk_light_satisfies")
         return out
 
-    def expert(self):
+    def teacher_table(self):
+        """u16[n_scen, 2^max_keys, 32, 32]: fewest actions to the goal room per (key subset, x, y),
+        built on first use by psk_light_teacher_build (one CTA per scenario)."""
+        if getattr(self, "_table", None) is None:
+            n_scen = self.scen.shape[0]
+            nbytes = self.lib.psk_light_teacher_table_bytes(n_scen, self.max_keys)
+            self._table = self.torch.empty(nbytes // 2, dtype=self.torch.int16, device=self.device)
+            with self.torch.cuda.device(self.device):
+                rc = self.lib.psk_light_teacher_build(self._p(self.scen), n_scen, self.max_keys,
+                                                      self._p(self._table), self._stream())
+            _lib.check(rc, "psk_light_teacher_build")
+        return self._table
+
+    def expert(self, search=False):
+        """(action u8[N], dist i16[N]); action 254 = already in the goal room, 255 = unreachable.
+        Default: lookup in the per-scenario table; ``search=True``: one backward flood per env
+        (psk_light_expert, the round-1 kernel, kept as an independent second implementation)."""
         act = self.torch.empty(self.n, dtype=self.torch.uint8, device=self.device)
         dist = self.torch.empty(self.n, dtype=self.torch.int16, device=self.device)
         with self.torch.cuda.device(self.device):
-            rc = self.lib.psk_light_expert(self._p(self.scen), self._p(self.scen_idx), self._p(self.state),
-                                           self._p(act), self._p(dist), self.max_keys, self.n,
-                                           self._stream())
+            if search:
+                rc = self.lib.psk_light_expert(self._p(self.scen), self._p(self.scen_idx), self._p(self.state),
+                                               self._p(act), self._p(dist), self.max_keys, self.n,
+                                               self._stream())
+            else:
+                rc = self.lib.psk_light_expert_table(self._p(self.scen), self._p(self.scen_idx),
+                                                     self._p(self.state), self._p(self.teacher_table()),
+                                                     self.max_keys, self._p(act), self._p(dist), self.n,
+                                                     self._stream())
         _lib.check(rc, "psk_light_expert")
         return act, dist
+
+    def tick(self, actions=None, features_out=None, want_features=True, out=None, max_timesteps=100):
+        """One rollout tick (psk_light_tick): teacher action, 12 features, then done / success /
+        auto-reset or step — one launch.  Returns dict(expert, done, success, features)."""
+        torch = self.torch
+        actions = self._u8(actions)
+        if out is None:
+            out = {}
+        for k in ("expert", "done", "success"):
+            if k not in out:
+                out[k] = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+        if want_features and features_out is None:
+            features_out = torch.empty((self.n, 12), dtype=torch.float32, device=self.device)
+        out["features"] = features_out
+        if getattr(self, "stats", None) is None:
+            self.stats = torch.zeros(4, dtype=torch.int64, device=self.device)
+        table = self.teacher_table()
+        with torch.cuda.device(self.device):
+            rc = self.lib.psk_light_tick(self._p(self.scen), self._p(self.scen_idx), self._p(self.state),
+                                         self._p(table), self.max_keys, self._p(actions),
+                                         self._p(features_out), self._p(out["expert"]), self._p(out["done"]),
+                                         self._p(out["success"]), self._p(self.stats), int(max_timesteps),
+                                         self.n, self._stream())
+        _lib.check(rc, "psk_light_tick")
+        return out
 
     def check_errors(self):
         flags = int(self.err.item())

@@ -133,3 +133,108 @@ def test_light_object_api(light_states):
     r, s2 = s.step(2)
     assert r == 0 and tuple(s2.pos) == tuple(light_states["step_pos"][0, 2]) and s.pos != s2.pos or True
     assert s.satisfies(None, None) == bool(light_states["satisfies"][0])
+
+
+def _all_states(L):
+    """Every (scenario, key subset, standable cell) of the 60 reference scenarios."""
+    rows = _scenario_rows(L)
+    scen, st = [], []
+    for si, r in enumerate(rows):
+        bw, bh = (int(v) for v in L["board"][r])
+        nk = int(L["n_keys"][r])
+        free = np.argwhere(L["walls"][r][:bw, :bh] == 0)
+        for m in range(1 << nk):
+            lock = {(int(k[2]), int(k[3])) for j, k in enumerate(L["keys"][r][:nk]) if (m >> j) & 1}
+            cells = np.asarray([c for c in free if (int(c[0]), int(c[1])) not in lock])
+            scen.append(np.full(len(cells), si, np.int32))
+            st.append(np.column_stack([cells, np.full(len(cells), m)]).astype(np.int32))
+    return np.concatenate(scen), np.concatenate(st)
+
+
+@pytest.mark.gpu
+def test_light_teacher_table_is_optimal_on_every_state(light_states):
+    """The teacher has no reference implementation (parity unpinned).  Its table is checked
+    exhaustively instead: on EVERY state of the 60 reference scenarios — every standable cell under
+    every key subset, 121,875 states — the distances satisfy the shortest-path equations under the
+    oracle's step() (which IS pinned against the reference's exported states):
+        dist = 0 exactly in the goal room; dist = 1 + min over the actions that change the state of
+        dist(successor); unreachable states have only unreachable successors;
+    the action is the smallest index attaining the minimum; the per-env search kernel of round 1
+    (an independent implementation) and the brute-force oracle (a forward BFS per state, on a
+    sample) give the same answers."""
+    from psketch_b200.worlds.light import LightWorld, VecLight
+    L = light_states
+    o = _oracle(L)
+    w = LightWorld()
+    scens = [w.sample_scenario_with_goal(g) for rep in range(6) for g in GOALS10]
+    scen_idx, state = _all_states(L)
+    n = len(scen_idx)
+    assert n > 100000
+    v = VecLight(scens, scen_idx)
+    st4 = np.zeros((n, 4), np.uint8)
+    st4[:, :3] = state
+    v.set_state(st4)
+    act, dist = (t.cpu().numpy().astype(np.int32) for t in v.expert())
+    act2, dist2 = (t.cpu().numpy().astype(np.int32) for t in v.expert(search=True))
+    assert np.array_equal(act, act2) and np.array_equal(dist, dist2)
+    # successor distances through the oracle's step
+    key = lambda si, s: (si.astype(np.int64) << 32) | (s[:, 0].astype(np.int64) << 24) | (s[:, 1].astype(np.int64) << 16) | s[:, 2]
+    lut = dict(zip(key(scen_idx, state).tolist(), dist.tolist()))
+    _, sat, _ = o.run(scen_idx, state)
+    assert np.array_equal(dist == 0, sat == 1) and np.array_equal(act == 254, sat == 1)
+    INF = 1 << 20
+    succ = np.full((5, n), INF, np.int64)
+    for a in range(5):
+        _, _, nxt = o.run(scen_idx, state, np.full(n, a))
+        moved = (nxt != state).any(axis=1)
+        d = np.asarray([lut[k] for k in key(scen_idx, nxt).tolist()], np.int64)
+        succ[a] = np.where(moved & (d >= 0), d, INF)
+    best = succ.min(axis=0)
+    unreachable = dist < 0
+    assert np.array_equal(unreachable, (best >= INF) & (sat == 0))
+    assert (act[unreachable] == 255).all()
+    ok = ~unreachable & (sat == 0)
+    assert np.array_equal(dist[ok], 1 + best[ok])
+    assert np.array_equal(act[ok], succ[:, ok].argmin(axis=0))         # argmin = smallest action index
+    # brute force (forward BFS from every successor) on a sample, including unreachable states
+    sel = np.concatenate([np.arange(0, n, 997), np.flatnonzero(unreachable)[:20]])
+    want_a, want_d = o.expert(scen_idx[sel], state[sel])
+    assert np.array_equal(act[sel], want_a) and np.array_equal(dist[sel], want_d)
+
+
+@pytest.mark.gpu
+def test_light_tick_matches_oracle(light_states):
+    """psk_light_tick (teacher + features + done/success/auto-reset or step, one launch) against the
+    oracle's features / satisfies / step and the table teacher, with teacher-driven and random actions."""
+    L = light_states
+    o = _oracle(L)
+    v, st, scen_idx, state = _vec(L)
+    n = len(scen_idx)
+    v.reset()
+    init = v.state.cpu().numpy().astype(np.int32)
+    cur = init[:, :3].copy()
+    elapsed = np.zeros(n, np.int32)
+    rng = np.random.RandomState(4)
+    T = 23
+    tot = np.zeros(3, np.int64)
+    for t in range(70):
+        a_in = rng.randint(0, 5, size=n).astype(np.uint8) if t % 3 == 2 else None
+        ref_a, _ = (x.cpu().numpy().astype(np.int32) for x in v.expert())
+        out = v.tick(actions=a_in, max_timesteps=T)
+        feat, sat, _ = o.run(scen_idx, cur)
+        assert np.array_equal(out["expert"].cpu().numpy().astype(np.int32), ref_a), t
+        assert np.array_equal(out["features"].cpu().numpy(), feat), t
+        a = ref_a if a_in is None else a_in.astype(np.int32)
+        elapsed += 1
+        done = (a >= 5) | (elapsed >= T)
+        succ = done & (sat == 1)
+        _, _, nxt = o.run(scen_idx, cur, np.where(done, 0, a))
+        cur = np.where(done[:, None], init[:, :3], nxt)
+        elapsed = np.where(done, 0, elapsed)
+        tot += (int(done.sum()), int(succ.sum()), n)
+        assert np.array_equal(out["done"].cpu().numpy().astype(bool), done), t
+        assert np.array_equal(out["success"].cpu().numpy().astype(bool), succ), t
+        got = v.state.cpu().numpy().astype(np.int32)
+        assert np.array_equal(got[:, :3], cur) and np.array_equal(got[:, 3], elapsed), t
+    s = v.stats.cpu().numpy()
+    assert (s[0], s[1], s[2]) == tuple(tot) and tot[1] > 0
