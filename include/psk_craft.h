@@ -77,6 +77,8 @@ typedef struct psk_craft_tables {
     uint8_t recipes[PSK_MAX_RECIPES][8];                     /* out, workshop, n_in, in0, cnt0, in1, cnt1, yield — firing order */
     uint8_t task_len[PSK_MAX_TASKS];                         /* nodes in the pre-order flattening of each task's hint tree */
     uint8_t task_nodes[PSK_MAX_TASKS][PSK_MAX_TASK_NODES][4]; /* sat class, arg kind, leaf kind, skip_to */
+    uint16_t ws_recipes[PSK_MAX_KINDS];                      /* per kind id: bit r set = recipe r is made at this workshop
+                                                                (derived from recipes[] by the library on every call — callers may leave it zero) */
 } psk_craft_tables;
 
 typedef struct psk_craft_state {
@@ -105,7 +107,8 @@ const char *psk_version(void);
  *   tile_chain       0 = consecutive fused launches wait for the whole previous grid
  *                    (griddepcontrol.wait); default: per-tile ticket counters (psk_common.cuh)
  *   tick_variant     CTA shape of craft_tick_kernel: 0 = 64+2, 1 = 128+4, 2 = 32+1, 3 = 64+4, 4 = 32+2
- *   tick_tma, tick_persist, feat_persist, tick_pdl, step_variant (0 = tables staged in shared memory)
+ *   tick_tma, tick_persist, feat_persist, tick_pdl,
+ *   step_variant     0 = tables staged in shared memory (default), 1 = read-only path, 2 = 1 + row preload
  * Unknown keys return PSK_ERR_BADARG.  Results never depend on a knob (tests/test_craft_gpu.py). */
 int psk_set_tuning(const char *key, int32_t value);
 int psk_get_tuning(const char *key, int32_t *value);

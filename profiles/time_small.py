@@ -38,6 +38,10 @@ def main():
     nbuf = max(3, int(np.ceil(200e6 / (n * 1616))))
     big = [torch.empty((n, 404), dtype=torch.float32, device=env.device) for _ in range(nbuf)]
     res = {"n": n, "step": {}, "tick": {}}
+    # launch floor: what a back-to-back chain of trivial kernels costs per launch inside a CUDA graph
+    one = torch.zeros(32, device=env.device)
+    res["launch_floor_us"] = time_kernel(lambda: one.add_(1.0), torch, inner=20, reps=50) * 1e6
+    print("launch floor (32-element add_ in a graph chain): %.2f us per launch" % res["launch_floor_us"], file=sys.stderr)
     for r in range(args.rounds):
         for v in [int(x) for x in args.step_variants.split(",")]:
             _lib.set_tuning(step_variant=v)

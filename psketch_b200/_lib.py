@@ -42,6 +42,7 @@ class CraftTablesC(ctypes.Structure):
         ("recipes", ctypes.c_uint8 * (16 * 8)),
         ("task_len", ctypes.c_uint8 * 32),
         ("task_nodes", ctypes.c_uint8 * (32 * 16 * 4)),
+        ("ws_recipes", ctypes.c_uint16 * 32),
     ]
 
 
@@ -185,4 +186,7 @@ def make_tables(t):
     ctypes.memmove(c.task_len, np.ascontiguousarray(t.task_len[:32]).ctypes.data, 32)
     ctypes.memmove(c.task_nodes, np.ascontiguousarray(t.task_nodes[:32]).ctypes.data, 32 * 16 * 4)
     assert _tables.MAX_TASKS == 32 and _tables.MAX_TASK_NODES == 16
+    rec = np.asarray(t.recipes)
+    for r in range(int(t.n_recipes)):                 # recipes[r] = out, workshop, n_in, ...
+        c.ws_recipes[int(rec[r][1]) & 31] |= 1 << r
     return c

@@ -33,6 +33,7 @@ struct __align__(16) SharedTables {
         return reinterpret_cast<const uint32_t *>(t().task_nodes)[(task & 31) * PSK_MAX_TASK_NODES + i];
     }
     __device__ __forceinline__ int task_len(int task) const { return t().task_len[task & 31]; }
+    __device__ __forceinline__ uint32_t ws_recipes(int k) const { return t().ws_recipes[k & 31]; }
     __device__ __forceinline__ int n_recipes() const { return t().n_recipes; }
     __device__ __forceinline__ int bridge_kind() const { return t().bridge_kind; }
     __device__ __forceinline__ int axe_kind() const { return t().axe_kind; }
@@ -49,6 +50,7 @@ struct GlobalTables {
     __device__ __forceinline__ uint2 recipe(int r) const {
         return __ldg(reinterpret_cast<const uint2 *>(p->recipes) + r);
     }
+    __device__ __forceinline__ uint32_t ws_recipes(int k) const { return __ldg(p->ws_recipes + (k & 31)); }
     __device__ __forceinline__ int n_recipes() const { return __ldg(&p->n_recipes); }
     __device__ __forceinline__ int bridge_kind() const { return __ldg(&p->bridge_kind); }
     __device__ __forceinline__ int axe_kind() const { return __ldg(&p->axe_kind); }

@@ -51,10 +51,11 @@ __device__ __forceinline__ void step_env(const TAB &st, Agent &a, uint8_t *row,
                 }
                 row[fx * H + fy] = 0;
             } else if (cls == KC_WORKSHOP) {  // craft.py:388-401: all recipes, in file order
-                for (int r = 0, nr = st.n_recipes(); r < nr; r++) {
-                    const uint2 rc = st.recipe(r);
-                    const int out = rc.x & 0xFF, ws = (rc.x >> 8) & 0xFF, n_in = (rc.x >> 16) & 0xFF;
-                    if (ws != thing) continue;
+                // only this workshop's recipes are visited (ws_recipes: bit r = recipe r is made here),
+                // lowest bit first = file order
+                for (uint32_t todo = st.ws_recipes(thing); todo; todo &= todo - 1) {
+                    const uint2 rc = st.recipe(__ffs(todo) - 1);
+                    const int out = rc.x & 0xFF, n_in = (rc.x >> 16) & 0xFF;
                     const int in0 = rc.x >> 24, c0 = rc.y & 0xFF;
                     const int in1 = (rc.y >> 8) & 0xFF, c1 = (rc.y >> 16) & 0xFF, yld = rc.y >> 24;
                     if (n_in > 0 && a.inv(in0) < c0) continue;
@@ -1829,7 +1830,7 @@ static inline int check(cudaError_t e) { return e == cudaSuccess ? PSK_OK : PSK_
 // Filling a slot is a pageable H2D copy: it must not happen inside a CUDA-graph capture, so call any
 // entry point once with new tables before capturing (every caller's warm-up does).  When more than
 // SLOTS distinct tables are alive on a device the oldest slot is recycled after a device-wide sync.
-static const psk_craft_tables *device_tables(const psk_craft_tables *t, cudaStream_t st) {
+static const psk_craft_tables *device_tables(const psk_craft_tables *caller_tables, cudaStream_t st) {
     constexpr int MAX_DEV = PSK_MAX_DEVICES, SLOTS = 8;
     struct Slot {
         psk_craft_tables host;
@@ -1843,6 +1844,12 @@ static const psk_craft_tables *device_tables(const psk_craft_tables *t, cudaStre
     static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) return nullptr;
+    // ws_recipes is derived data: always rebuilt from recipes[] here, whatever the caller put there
+    psk_craft_tables canon = *caller_tables;
+    memset(canon.ws_recipes, 0, sizeof(canon.ws_recipes));
+    for (int r = 0; r < canon.n_recipes && r < PSK_MAX_RECIPES; r++)
+        canon.ws_recipes[canon.recipes[r][1] & (PSK_MAX_KINDS - 1)] |= (uint16_t)(1u << r);
+    const psk_craft_tables *t = &canon;
     std::lock_guard<std::mutex> lock(mu);
     PerDevice &c = cache[dev];
     if (c.used && memcmp(&c.slot[c.last].host, t, sizeof(psk_craft_tables)) == 0) return c.slot[c.last].dev;
@@ -1909,9 +1916,12 @@ template <int W, int H, int WIN> struct Config {
     static int step(const psk_craft_tables *t, psk_craft_state s, const uint8_t *action,
                     const uint8_t *active, float *reward, int32_t *err, cudaStream_t st) {
         PSK_DT(dt);
-        // step_variant: 0 staged tables, 1 read-only-path tables, 2 (default for 64-byte rows) + row preload
+        // step_variant: 0 (default) tables staged in shared memory, 256-thread CTAs; 1 tables through
+        // the read-only path, 64-thread CTAs; 2 = 1 + row preload.  Same box, 65,536 envs, after the
+        // per-workshop recipe mask: 3.07 / ~3.3 / 3.6 us (profiles/README.md) — with the USE path
+        // short, staging once per CTA beats per-thread table loads again.
         int mode = tune(TUNE_STEP_VARIANT);
-        if (mode < 0 || mode > 2) mode = CP == 64 ? 2 : 1;
+        if (mode < 0 || mode > 2) mode = 0;
         if (mode == 2 && CP != 64) mode = 1;
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = dim3(mode == 0 ? 256 : 64);

@@ -46,7 +46,7 @@ def test_library_has_sm100a_sass_with_tma(lib_path):
 
 def test_struct_sizes_match_header():
     from psketch_b200 import _lib
-    assert ctypes.sizeof(_lib.CraftTablesC) == 12 * 4 + 32 + 128 + 32 + 2048
+    assert ctypes.sizeof(_lib.CraftTablesC) == 12 * 4 + 32 + 128 + 32 + 2048 + 64
     assert ctypes.sizeof(_lib.CraftStateC) == 32
     assert ctypes.sizeof(_lib.CraftEpisodesC) == 24
 

@@ -158,3 +158,49 @@ def test_policy_rollouts_match_facade_semantics(splits, medium_tables, medium_or
     _, length, _, _ = o.find_closest(grid0, pos, dirs, kinds)
     want = np.where(is_get, np.where(success, 0, length), -1)
     assert np.array_equal(out["distances"].astype(np.int64), want)
+
+
+def test_describe_batch_on_device_states(splits, medium_tables):
+    """PrimitiveLanguageTeacher.describe_batch on CUDA tensors recorded from VecCraft rollouts (the
+    student uses private action ids) against describe() called rollout by rollout on host state
+    objects — words, the learned action map and the position of the shared random stream; pinned to
+    the reference's teachers/primitive_language.py:35-90 through tests/test_language_teacher.py and
+    the config-4 replay (tests/test_config4.py)."""
+    import types
+    from psketch_b200.teachers import PrimitiveLanguageTeacher
+    from psketch_b200.teachers.primitive_language import ACTION_WORDS
+    from psketch_b200.vec import VecCraft
+    n, L = 700, 12
+    rng = np.random.RandomState(8)
+    idx = rng.randint(0, 2200, size=n)
+    env = VecCraft.from_instances(medium_tables, splits["dev_grids"], splits["dev_inst_env"][idx],
+                                  splits["dev_inst_pos"][idx], splits["dev_inst_task"][idx])
+    perm = rng.permutation(6)                      # real action a is known to the student as perm[a]
+    a = PrimitiveLanguageTeacher(types.SimpleNamespace(random=np.random.RandomState(3)))
+    b = PrimitiveLanguageTeacher(types.SimpleNamespace(random=np.random.RandomState(3)))
+    world = types.SimpleNamespace(action_space=list(range(6)))
+    for call in range(3):
+        env.reset()
+        real = rng.choice(6, size=(L, n), p=[.2, .2, .2, .2, .18, .02]).astype(np.uint8)
+        lengths = rng.randint(1, L + 1, size=n)
+        snaps = [env.agent.clone()]
+        for t in range(L):
+            env.step(torch.from_numpy(real[t]), active=torch.from_numpy((t < lengths).astype(np.uint8)))
+            snaps.append(env.agent.clone())
+        agent_seq = torch.stack(snaps)                                   # [L + 1, N, 32] on the device
+        ids = torch.from_numpy(perm[real.T.astype(np.int64)]).to(env.device)   # [N, L] student ids
+        got = b.describe_batch(ids, agent_seq, torch.from_numpy(lengths).to(env.device), n_kinds=21)
+        assert got.is_cuda
+        got = got.cpu().numpy()
+        host = agent_seq.cpu().numpy()
+        for i in range(n):
+            states = [types.SimpleNamespace(pos=(int(host[t, i, 24]), int(host[t, i, 25])),
+                                            inventory=host[t, i, :21].astype(float))
+                      for t in range(lengths[i] + 1)]
+            want = a.describe(world, [int(v) for v in perm[real[:lengths[i], i]]], states)
+            assert [ACTION_WORDS[w] for w in got[i, :lengths[i]]] == want, (call, i)
+            assert (got[i, lengths[i]:] == -1).all()
+        assert a.student_action_map == b.student_action_map
+    assert a.random.randint(1 << 30) == b.random.randint(1 << 30)
+    assert len(b.student_action_map) == 6
+    env.check_errors()
