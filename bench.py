@@ -545,6 +545,10 @@ def run_ours(args):
         torch.cuda.empty_cache()
     if world == 1 and not args.no_light:
         try:
+            line["student_in_loop"] = student_in_loop_record(torch, tables, dev)
+        except Exception as ex:  # noqa: BLE001
+            line["student_in_loop"] = {"error": repr(ex)}
+        try:
             line["light_world"] = light_record(torch, dev, peak)
         except Exception as ex:  # noqa: BLE001
             line["light_world"] = {"error": repr(ex)}
@@ -628,6 +632,42 @@ def light_record(torch, dev, peak):
         rec["n_%d" % n] = r
         del v, feats
     return rec
+
+
+def student_in_loop_record(torch, tables, dev, n=16384):
+    """BASELINE configs[3]'s rollout with a policy in the loop: psketch_b200.students.GraphedRollout
+    (40 timesteps of fused step-then-observe tick -> LSTM decode -> on-device sampling, one CUDA graph)
+    with a randomly initialised student of the reference's architecture (models/lstm_seq2seq.py)."""
+    from psketch_b200.students import GraphedRollout, Seq2SeqPolicy, task_tokens
+    from psketch_b200.vec import VecCraft
+    wl = load_workload(n)
+    env = VecCraft.from_instances(tables, wl["grids"], wl["env"], wl["pos"], wl["task"], max_timesteps=255, device=dev)
+    torch.manual_seed(0)
+    pol = Seq2SeqPolicy(env.n_features, 6, len(tables.task_manager.vocab) + 1, tables.task_manager.vocab["<PAD>"]).to(dev)
+    roll = GraphedRollout(env, pol, max_timesteps=40, greedy=False)
+    with torch.no_grad():
+        mem = pol.encode(task_tokens(tables, env.task))
+    for _ in range(2):
+        roll.run(mem)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps, steps = 5, 0
+    s.record()
+    for _ in range(reps):
+        roll.run(mem)
+        steps += int(roll.interactions)
+    e.record()
+    torch.cuda.synchronize()
+    dt = s.elapsed_time(e) * 1e-3
+    return {"envs": n, "env_steps_per_s": steps / dt, "env_timesteps_per_s": reps * n * 40 / dt,
+            "rollouts_per_s": reps * n / dt,
+            "ms_per_rollout_of_40_timesteps": dt / reps * 1e3,
+            "how": "GraphedRollout: per timestep one psk_craft_tick (step, then observe) + Seq2SeqPolicy.decode_step "
+                   "(cuDNN LSTM 468->256, attention, predictor) + Gumbel-max sampling on the device; env_steps = "
+                   "teacher-labelled states of running episodes (an untrained student samples STOP after ~6 steps "
+                   "and idles for the rest of the 40), env_timesteps = every env x 40; training runs: "
+                   "profiles/bench_runs/r2_dagger_*.json",
+            "reference": "experiments/dagger_no_mix/run.log: ~1.5e3 interactions/s including learning"}
 
 
 def measure_config3(torch, dist, pdist, tables, rank, world, dev, args):

@@ -250,8 +250,10 @@ static int find_incomplete(const orc_tables *t, const uint8_t *grid, const int32
     int n = t->task_len[task], i = 0;
     while (i < n) {
         const uint8_t *nd = t->task_nodes[task][i];
-        if (orc_satisfies_node(t, grid, inv, x, y, dir, nd[0], nd[1]) == 1) i = nd[3];
-        else if (nd[2] != LEAF_NONE) return i;
+        if (orc_satisfies_node(t, grid, inv, x, y, dir, nd[0], nd[1]) == 1) {
+            if (nd[2] & 0x40) return -2; /* last subtask of an unsatisfied task: base.py:23-24 asserts */
+            i = nd[3];
+        } else if ((nd[2] & 0x0F) != LEAF_NONE) return i;
         else i++;
     }
     return -1;
@@ -265,10 +267,11 @@ int orc_expert(const orc_tables *t, const uint8_t *grid, const int32_t *inv, int
     if (dist_out) *dist_out = -1;
     if (status_out) *status_out = 0;
     int leaf = find_incomplete(t, grid, inv, x, y, dir, task);
+    if (leaf == -2) return 255;
     if (leaf < 0) return A_STOP;
     const uint8_t *nd = t->task_nodes[task][leaf];
-    if (nd[2] == LEAF_USE) return A_USE;
-    if (nd[2] != LEAF_GO) return 255;
+    if ((nd[2] & 0x0F) == LEAF_USE) return A_USE;
+    if ((nd[2] & 0x0F) != LEAF_GO) return 255;
     int gx, gy, len;
     uint8_t seq[1];
     int st = orc_find_closest(t, grid, x, y, dir, nd[1], &gx, &gy, &len, seq, 1);

@@ -194,8 +194,12 @@ __device__ __forceinline__ uint32_t find_incomplete(const SharedTables &st, int 
     while (__any_sync(0xffffffffu, i < n && !leaf)) {
         if (i < n && !leaf) {
             const uint32_t nd = st.node(task, i);
-            if (node_satisfied(nd, a, facing) == 1) i = nd >> 24;
-            else if ((nd >> 16) & 0xFF) leaf = nd | 0x80000000u;  // bit 31 marks "found"
+            if (node_satisfied(nd, a, facing) == 1) {
+                // bit 0x40 of the leaf byte: last subtask of an (unsatisfied) task — the reference's
+                // assert at teachers/base.py:23-24; reported like a bad leaf
+                if (nd & 0x00400000u) leaf = (uint32_t(LEAF_BAD) << 16) | 0x80000000u;
+                i = nd >> 24;
+            } else if ((nd >> 16) & 0x0F) leaf = nd | 0x80000000u;  // bit 31 marks "found"
             else i++;
         }
     }
@@ -385,7 +389,7 @@ __device__ __forceinline__ int expert_env(const SharedTables &st, const Agent &a
                                           const uint32_t *row_words, int facing, int &dist,
                                           uint32_t &flags) {
     const uint32_t leaf = find_incomplete(st, task, a, facing);
-    const int kind = (leaf >> 16) & 0x7F;
+    const int kind = (leaf >> 16) & 0x0F;
     const bool need = leaf && kind == LEAF_GO;
     typename Board<W, H>::BT occ, goal;
     build_boards<W, H>(row_words, need ? (leaf >> 8) & 0xFF : 0, occ, goal);
@@ -760,7 +764,7 @@ craft_expert_rows_kernel(const psk_craft_tables *__restrict__ T, const uint8_t *
         const int tk = task ? task[e] : a.task();
         const int facing = facing_kind<W, H>(a, row);
         const uint32_t leaf = find_incomplete(st, tk, a, facing);
-        const int kind = (leaf >> 16) & 0x7F;
+        const int kind = (leaf >> 16) & 0x0F;
         const bool need = leaf && kind == LEAF_GO;
         RowBoard<W, H> occ, goal;
         build_rows<W, H>(row, lane, need ? (leaf >> 8) & 0xFF : 0, occ, goal);

@@ -251,6 +251,9 @@ class TaskManager(object):
         return len(self.tasks) - 1
 
 
+LAST_CHILD = 0x40      # task_nodes[..][2] bit: a satisfied node here = the reference's AssertionError
+
+
 class CraftTables(object):
     """Everything the kernels need, as small numpy arrays (uploaded once per device by
     ``psk_craft_tables_upload``; layout documented in include/psk_craft.h):
@@ -327,7 +330,7 @@ class CraftTables(object):
         self.n_tasks = n_tasks
         nodes = np.zeros((MAX_TASKS, MAX_TASK_NODES, 4), np.uint8)
         lens = np.zeros(MAX_TASKS, np.uint8)
-        self.may_assert = {}
+        self.may_assert = []            # (task, last subtask) pairs where the reference can assert
         for task in tm.tasks:
             flat = []
             self._flatten(task, flat)
@@ -368,7 +371,16 @@ class CraftTables(object):
         flat.append([sat, arg, leaf, 0])
         if task.subtasks is not None:
             for sub in task.subtasks:
+                child = len(flat)
                 self._flatten(sub, flat)
+            # The reference asserts that the LAST subtask of an unsatisfied task is itself incomplete
+            # (teachers/base.py:23-24).  A child is only ever visited below an unsatisfied parent, so
+            # the walk raises exactly when it finds this node satisfied: mark it.  (Never the case
+            # with the stock hint file: its last subtasks are use[...] / makeat[...], which are never
+            # "satisfied".)
+            if flat[child][0] != SAT_NEVER:
+                flat[child][2] |= LAST_CHILD
+                self.may_assert.append((repr(task), repr(sub)))
         flat[here][3] = len(flat)
 
     # --------------------------------------------------------------------------------

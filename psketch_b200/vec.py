@@ -299,10 +299,11 @@ class VecCraft(object):
         if not flags:
             return
         self.err_flags.zero_()
+        if flags & _lib.FLAG_BAD_LEAF:        # the teacher speaks before the step (imitation.py:53,72)
+            raise AssertionError("teacher: subtask is neither 'use' nor 'go', or every subtask of an "
+                                 "unsatisfied task is satisfied")  # demonstration.py:18, base.py:23-24
         if flags & _lib.FLAG_BAD_ACTION:
             raise Exception("Unexpected action")              # worlds/craft.py:415-416
-        if flags & _lib.FLAG_BAD_LEAF:
-            raise AssertionError("teacher: subtask is neither 'use' nor 'go'")
         if flags & _lib.FLAG_INV_OVERFLOW:
             raise OverflowError("inventory count above 255")
         raise _lib.PskError("kernel error flags 0x%x" % flags)

@@ -774,3 +774,40 @@ def test_tick_advance_first_matches_oracle(which, splits, medium_tables, medium_
             assert np.array_equal(_np(out["features"]), oracle.features(orc.grid, orc.inv, orc.pos, orc.dir)), t
         orc.assert_state_equals(env)
     env.check_errors()
+
+
+def test_last_subtask_assert_is_reported(tmp_path):
+    """teachers/base.py:23-24 (see tests/test_oracle.py, checked there against the reference itself):
+    an unsatisfied task whose last subtask is satisfied makes the reference assert; the kernels
+    return action 255 and raise through check_errors instead of walking on to a sibling."""
+    import yaml
+    from oracle.craft_oracle import CraftOracle
+    from psketch_b200.tables import Cookbook, CraftTables, TaskManager
+    from psketch_b200.vec import VecCraft
+    hints = {"use[none]": [], "go[wood]": [], "get[wood]": ["go[wood]", "use[none]"],
+             "make[plank]": ["get[wood]"]}
+    hp = str(tmp_path / "hints.yaml")
+    yaml.safe_dump(hints, open(hp, "w"), sort_keys=False)
+    tables = CraftTables(Cookbook(), TaskManager(hp), "craft_medium")
+    o = CraftOracle(tables)
+    n = 70
+    rng = np.random.RandomState(0)
+    grid = np.zeros((n, 8, 8), np.uint8)
+    grid[:, 0, :] = grid[:, 7, :] = grid[:, :, 0] = grid[:, :, 7] = 1
+    grid[:, 3, 5] = tables.cookbook.index["wood"]
+    grid = grid.reshape(n, 64)
+    inv = np.zeros((n, tables.K), np.int32)
+    has_wood = rng.rand(n) < 0.5
+    inv[has_wood, tables.cookbook.index["wood"]] = 1
+    pos = np.tile(np.asarray([[3, 3]], np.int32), (n, 1))
+    task = np.full(n, tables.task_manager["make[plank]"].task_id, np.int32)
+    env = VecCraft.from_states(tables, grid, inv, pos, np.zeros(n, np.int32), task=task)
+    act = _np(env.expert()).astype(np.int32)
+    want = o.expert(grid, inv, pos, np.zeros(n, np.int32), task)[0]
+    assert np.array_equal(act, want) and (act[has_wood] == 255).all() and (act[~has_wood] == 1).all()
+    with pytest.raises(AssertionError):
+        env.check_errors()
+    out = env.tick(fused=True)                       # same walk inside the fused kernel
+    assert np.array_equal(_np(out["expert"]).astype(np.int32), want)
+    with pytest.raises(AssertionError):
+        env.check_errors()

@@ -1,6 +1,7 @@
 """Pins the CPU oracle (oracle/craft_oracle.c) against the reference's golden vectors and
 against outputs exported from the unmodified reference (tests/golden/, made by
 oracle/gen_golden.py).  CPU only."""
+import os
 import numpy as np
 import pytest
 
@@ -159,3 +160,49 @@ def test_chain_crafting(medium_oracle, medium_tables):
     assert use_at("workshop0", {"wood": 2, "grass": 1}) == {"wood": 1, "plank": 1, "rope": 1}
     assert use_at("workshop2", {"grass": 1, "wood": 1, "iron": 1, "plank": 1, "stick": 1}) == \
         {"cloth": 1, "bridge": 1, "ladder": 1}
+
+
+def test_unsatisfied_task_whose_last_subtask_is_satisfied_asserts(tmp_path):
+    """teachers/base.py:23-24: `assert incomplete_subtask is not None` fires when every subtask of an
+    unsatisfied task is satisfied.  Cannot happen with the stock hint file (last subtasks are use[...]
+    / makeat[...]); a custom file whose last subtask is a get/make/go node can trigger it.  The table
+    builder marks such nodes, the oracle (and the kernels, tests/test_craft_gpu.py) report the
+    reference's AssertionError (action 255 + PSK_FLAG_BAD_LEAF) instead of walking on."""
+    import yaml
+    from oracle.craft_oracle import CraftOracle
+    from psketch_b200.tables import Cookbook, CraftTables, TaskManager
+    hints = {"use[none]": [], "go[wood]": [], "get[wood]": ["go[wood]", "use[none]"],
+             "make[plank]": ["get[wood]"]}
+    hp = str(tmp_path / "hints.yaml")
+    yaml.safe_dump(hints, open(hp, "w"), sort_keys=False)
+    tables = CraftTables(Cookbook(), TaskManager(hp), "craft_medium")
+    assert tables.may_assert and "plank" in tables.may_assert[0][0]
+    o = CraftOracle(tables)
+    cb = tables.cookbook
+    grid = np.zeros((2, 8, 8), np.uint8)
+    grid[:, 0, :] = grid[:, 7, :] = grid[:, :, 0] = grid[:, :, 7] = 1
+    grid[:, 3, 5] = cb.index["wood"]
+    grid = grid.reshape(2, 64)
+    inv = np.zeros((2, tables.K), np.int32)
+    inv[1, cb.index["wood"]] = 1                      # env 1 already holds wood, has no plank
+    pos = np.asarray([[3, 3], [3, 3]], np.int32)
+    dirs = np.zeros(2, np.int32)
+    task = np.full(2, tables.task_manager["make[plank]"].task_id, np.int32)
+    act, _, _ = o.expert(grid, inv, pos, dirs, task)
+    assert act[0] == 1 and act[1] == 255              # env 0 walks UP towards the wood; env 1: assert
+    ref_root = "/root/reference"
+    if os.path.isdir(os.path.join(ref_root, "teachers")):
+        from oracle import ref_shim
+        R = ref_shim.Reference(hints=hp)
+        with ref_shim.reference_cwd():
+            K = R.world.cookbook.n_kinds
+            onehot = np.zeros((8, 8, K))
+            g = grid[1].reshape(8, 8)
+            xs, ys = np.nonzero(g)
+            onehot[xs, ys, g[xs, ys]] = 1
+            state = R.world.init_state(onehot, (3, 3))
+            t = R.task_manager["make[plank]"]
+            assert R.teacher(t, state) == 1
+            state.inventory[R.world.cookbook.index["wood"]] = 1
+            with pytest.raises(AssertionError):
+                R.teacher(t, state)
