@@ -811,3 +811,41 @@ def test_last_subtask_assert_is_reported(tmp_path):
     assert np.array_equal(_np(out["expert"]).astype(np.int32), want)
     with pytest.raises(AssertionError):
         env.check_errors()
+
+
+def test_concurrent_streams_and_tile_chaining(splits, medium_tables, medium_oracle):
+    """Two batches ticking concurrently on two streams share the per-device tile-chaining counters
+    (psk_common.cuh): tickets of the two streams interleave, results must not change and nothing
+    may deadlock; then the same with chaining switched off."""
+    from psketch_b200 import _lib
+    from psketch_b200.vec import VecCraft
+    rng = np.random.RandomState(21)
+    try:
+        for chain in (-1, 0):
+            _lib.set_tuning(tile_chain=chain)
+            envs, orcs, streams = [], [], [torch.cuda.Stream(), torch.cuda.Stream()]
+            for k, n in enumerate((8191, 3001)):
+                idx = rng.randint(0, 2200, size=n)
+                args = (splits["dev_grids"], splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
+                        splits["dev_inst_task"][idx])
+                envs.append(VecCraft.from_instances(medium_tables, *args, max_timesteps=13))
+                orcs.append(_OracleTicks(medium_oracle, *args, max_timesteps=13))
+            torch.cuda.synchronize()
+            outs = [[], []]
+            for rep in range(6):
+                for k in (0, 1):
+                    with torch.cuda.stream(streams[k]):
+                        for _ in range(3):                     # back-to-back PDL launches per stream
+                            o = envs[k].tick(want_features=False)
+                            outs[k].append(o["expert"].clone())
+                        o = envs[k].rollout(4)
+                        outs[k] += [o["expert"][t].clone() for t in range(4)]
+            torch.cuda.synchronize()
+            for k in (0, 1):
+                for t, got in enumerate(outs[k]):
+                    ref = orcs[k].tick(want_features=False)
+                    assert np.array_equal(_np(got), ref["expert"]), (chain, k, t)
+                orcs[k].assert_state_equals(envs[k])
+                envs[k].check_errors()
+    finally:
+        _lib.set_tuning(tile_chain=-1)
