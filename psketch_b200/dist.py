@@ -26,7 +26,8 @@ def init_from_env(backend=None):
         if backend == "nccl":
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
-            if os.environ.get("PSK_BIND_CPUS", "1") != "0":
+            # opt-in: a measured no-op on single-NUMA-node hosts like this pool's (profiles/README.md)
+            if os.environ.get("PSK_BIND_CPUS", "0") == "1":
                 bind_to_gpu_cpus(local)
         dist.init_process_group(backend, rank=rank, world_size=world, **kw)
     return rank, world, local
