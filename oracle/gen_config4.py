@@ -147,7 +147,48 @@ def run(which, data_dir, iters, log_every, medium_oracle=None, experiment="imita
                 rec["iters"][-1]["loss"] = loss
                 return loss
 
-        base_trainer = PrimitiveLanguageTrainer if experiment == "primitive_language" else ImitationTrainer
+        from students.interactive_primitive_language import InteractivePrimitiveLanguageStudent
+        from trainers.interactive_primitive_language import InteractivePrimitiveLanguageTrainer
+
+        class RecordingInteractiveStudent(InteractivePrimitiveLanguageStudent):   # runs unchanged
+            def init(self, states):
+                super().init(states)
+                self.cur = dict(is_eval=None, acts=[], refs=[], fh=[], instr_steps=[], desc_steps=[])
+
+            def set_tasks(self, tasks, is_eval):
+                self.cur["is_eval"] = is_eval
+                super().set_tasks(tasks, is_eval)
+
+            def _log(self, states, actions):
+                feats = np.stack([np.asarray(s.features()) for s in states]).astype(np.float32)
+                self.cur["fh"].append(feature_hash(feats))
+                self.cur["acts"].append(list(actions))
+
+            def act(self, states):
+                actions = super().act(states)
+                self._log(states, actions)
+                return actions
+
+            def instructed_act(self, states):
+                actions = super().instructed_act(states)
+                self._log(states, actions)
+                return actions
+
+            def set_instructions(self, instructions, is_eval):
+                # called with the teacher's instructions before instructed_act, and again (from
+                # receive) with the descriptions of the same timestep
+                key = "desc_steps" if len(self.cur["instr_steps"]) > len(self.cur["desc_steps"]) else "instr_steps"
+                self.cur[key].append([None if w is None else list(w) for w in instructions])
+                super().set_instructions(instructions, is_eval)
+
+            def learn(self):
+                loss = super().learn()
+                rec["iters"][-1]["loss"] = loss
+                return loss
+
+        base_trainer = {"primitive_language": PrimitiveLanguageTrainer,
+                        "interactive_primitive_language": InteractivePrimitiveLanguageTrainer}.get(
+                            experiment, ImitationTrainer)
 
         class RecordingTrainer(base_trainer):              # the trainer's code runs unchanged
             def do_rollout(self, batch, world, student, teacher, is_eval):
@@ -177,7 +218,8 @@ def run(which, data_dir, iters, log_every, medium_oracle=None, experiment="imita
                 from test_facade_cpu import OracleBackend
                 world._backend = OracleBackend(world, medium_oracle)
         assert config.student.model.input_size == 404 and config.student.model.n_actions == 6
-        student = (RecordingLanguageStudent if experiment == "primitive_language" else RecordingStudent)(config)
+        student = {"primitive_language": RecordingLanguageStudent,
+                   "interactive_primitive_language": RecordingInteractiveStudent}.get(experiment, RecordingStudent)(config)
         trainer = RecordingTrainer(config)
         torch.manual_seed(config.seed)
         config.random.seed(config.seed)
@@ -205,7 +247,7 @@ def assert_same(a, b):
         assert x["refs"] == y["refs"], k
         assert [int(h) for h in x["fh"]] == [int(h) for h in y["fh"]], k
         assert x.get("loss") == y.get("loss"), (k, x.get("loss"), y.get("loss"))   # bit-equal floats
-        for extra in ("phase2_acts", "instructions", "descriptions"):
+        for extra in ("phase2_acts", "instructions", "descriptions", "instr_steps", "desc_steps"):
             assert x.get(extra) == y.get(extra), (k, extra)
         assert [int(h) for h in x.get("phase2_fh", [])] == [int(h) for h in y.get("phase2_fh", [])], k
         ix, iy = x["info"], y["info"]
@@ -250,6 +292,21 @@ def pack(rec, splits):
         out["n_dist"][r] = len(info["distances"])
         out["distances"][r, :len(info["distances"])] = info["distances"]
         out["num_interactions"][r], out["num_steps"][r] = info["num_interactions"], info["num_steps"]
+    if any("instr_steps" in e for _, e in rollouts):
+        # interactive_primitive_language.yaml: per timestep the teacher's one-word instruction for
+        # EVERY env (finished ones too, trainers/interactive_primitive_language.py:49-51) and its
+        # one-word description of what each running env's action did (:61-66); 255 = none
+        words = {"down": 0, "up": 1, "left": 2, "right": 3, "use": 4, "stop": 5}
+        out["instr_steps"] = np.full((R, TM, BM), 255, np.uint8)
+        out["desc_steps"] = np.full((R, TM, BM), 255, np.uint8)
+        for r, (split, e) in enumerate(rollouts):
+            for key in ("instr_steps", "desc_steps"):
+                for t, row in enumerate(e[key]):
+                    for i, w in enumerate(row):
+                        if w is not None:
+                            out[key][r, t, i] = words[w[0]]
+        am = rec["action_map"]
+        out["final_action_map"] = np.asarray([words.get(am.get(a), 255) for a in range(6)], np.uint8)
     if any("phase2_acts" in e for _, e in rollouts):
         # primitive_language.yaml: the second (greedy, instructed) decoding pass of training rollouts,
         # the instruction words handed to the student and the teacher's descriptions (word = action
@@ -280,7 +337,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--log-every", type=int, default=15)
-    ap.add_argument("--experiment", default="imitation", choices=["imitation", "primitive_language"])
+    ap.add_argument("--experiment", default="imitation",
+                    choices=["imitation", "primitive_language", "interactive_primitive_language"])
     args = ap.parse_args()
     regen_dir = os.environ.get("PSK_REGEN_DIR", "/tmp/psk_data")
     data_dir = os.path.join(regen_dir, "config4_data")

@@ -215,3 +215,80 @@ def test_config4_language_replay_on_the_gpu(config4_language, splits):
     checked, learned = replay_language(world, teacher, splits, fx, order, rng)
     assert checked == len(order)
     assert learned == fx["final_action_map"].tolist()
+
+
+# ------------------------------------------------------------------------------------------------
+# interactive_primitive_language.yaml (trainers/interactive_primitive_language.py:16-106 +
+# teachers/interactive_primitive_language.py): the ONLINE teacher is asked every timestep for every
+# env (finished ones too) and describes every executed action from a (previous, new) state pair.
+def replay_interactive(world, teacher, splits, fx, rollouts, rng):
+    from trainer_loop import ScriptedInteractiveStudent, run_interactive_protocol
+    order = {"train": None, "dev": None}
+    cursor = {"train": 0, "dev": 0}
+    checked = 0
+    for r in rollouts:
+        B, T, is_eval = int(fx["n_env"][r]), int(fx["n_t"][r]), bool(fx["is_eval"][r])
+        split = "dev" if is_eval else "train"
+        if cursor[split] == 0:
+            order[split] = list(range(len(splits[split + "_inst_env"])))
+            rng.shuffle(order[split])
+        rows = order[split][cursor[split]:cursor[split] + 32]
+        cursor[split] = cursor[split] + 32 if cursor[split] + 32 < len(order[split]) else 0
+        assert rows == fx["batch"][r, :B].tolist(), r
+        batch = _items(world, splits, split, rows)
+        student = ScriptedInteractiveStudent(fx["acts"][r, :T, :B])
+        got = run_interactive_protocol(batch, world, teacher, student, is_eval, 40)
+        assert student.t == T, r
+        for i, seq in enumerate(got["action_seqs"]):
+            L = int(fx["seq_len"][r, i])
+            assert seq == fx["acts"][r, :L, i].tolist(), (r, i)
+        ids = lambda rows_: [[255 if w is None else WORDS.index(w[0]) for w in row] for row in rows_]
+        if not is_eval:
+            assert ids(student.instructions) == fx["instr_steps"][r, :T, :B].tolist(), r
+        # the student is handed the descriptions only in training; eval still computes them
+        if not is_eval:
+            assert ids(student.descriptions) == fx["desc_steps"][r, :T, :B].tolist(), r
+        assert [int(_hash(f)) for f in student.features] == [int(h) for h in fx["feat_hash"][r, :T]], r
+        assert [bool(v) for v in got["success"]] == fx["success"][r, :B].astype(bool).tolist(), r
+        assert got["distances"] == fx["distances"][r, :int(fx["n_dist"][r])].tolist(), r
+        assert got["num_interactions"] == int(fx["num_interactions"][r]), r
+        assert got["num_steps"] == int(fx["num_steps"][r]), r
+        checked += 1
+    learned = [WORDS.index(teacher.student_action_map[a]) if a in teacher.student_action_map else 255
+               for a in range(6)]
+    return checked, learned
+
+
+@pytest.fixture(scope="module")
+def config4_interactive():
+    return np.load(os.path.join(GOLDEN, "config4_interactive_primitive_language.npz"))
+
+
+def test_config4_interactive_replay_on_the_facade_logic(config4_interactive, splits, medium_tables, medium_oracle):
+    from test_facade_cpu import _world
+    from psketch_b200.teachers import InteractivePrimitiveLanguageTeacher
+    world = _world(medium_tables, medium_oracle)
+    rng = np.random.RandomState(123)
+    cfg = type("Cfg", (), {"random": rng})()
+    checked, _ = replay_interactive(world, InteractivePrimitiveLanguageTeacher(cfg), splits,
+                                    config4_interactive, range(5), rng)
+    assert checked == 5
+
+
+@pytest.mark.gpu
+def test_config4_interactive_replay_on_the_gpu(config4_interactive, splits):
+    from psketch_b200 import teachers, worlds
+    from psketch_b200.worlds.craft import _Struct
+    fx = config4_interactive
+    cfg = _Struct(recipes="resources/craft/recipes.yaml",
+                  world={"name": "CraftWorld", "config": "craft_medium"},
+                  teacher={"name": "InteractivePrimitiveLanguageTeacher"},
+                  trainer={"name": "InteractivePrimitiveLanguageTrainer",
+                           "hints": "resources/craft/hints.hierarchy.yaml", "max_timesteps": 40, "batch_size": 32})
+    rng = np.random.RandomState(123)
+    cfg.random = rng
+    world, teacher = worlds.load(cfg), teachers.load(cfg)
+    order = _language_order(fx)
+    checked, learned = replay_interactive(world, teacher, splits, fx, order, rng)
+    assert checked == len(order)
+    assert learned == fx["final_action_map"].tolist()

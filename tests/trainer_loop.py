@@ -161,3 +161,63 @@ def run_language_protocol(batch, world, teacher, student, is_eval, max_timesteps
                 descriptions=descriptions,
                 num_interactions=0 if is_eval else sum(len(h) for h in hints),
                 num_steps=0 if is_eval else steps)
+
+
+# ------------------------------------------------------------------------------------------------
+# trainers/interactive_primitive_language.py:16-106, restated: per timestep the teacher gives a
+# one-word instruction for EVERY env (also the finished ones: the teacher must tolerate
+# post-terminal states), the student acts, and the teacher describes what each running env's
+# action did from the (previous state, new state) pair.
+class ScriptedInteractiveStudent(object):
+    def __init__(self, script):
+        self.script, self.t = script, 0
+        self.features, self.instructions, self.descriptions = [], [], []
+
+    def next_actions(self, states):
+        self.features.append(np.stack([np.asarray(s.features()) for s in states]))
+        row = [int(a) if a != 255 else -1 for a in self.script[self.t]]
+        self.t += 1
+        return row
+
+
+def run_interactive_protocol(batch, world, teacher, student, is_eval, max_timesteps):
+    n = len(batch)
+    tasks = [item["task"] for item in batch]
+    states = [world.init_state(item["grid"], item["init_pos"]) for item in batch]
+    states[0].render()
+    clock = [max_timesteps] * n
+    finished = [False] * n
+    taken = [[] for _ in range(n)]
+    interactions = steps = 0
+    told = [None] * n
+    said = [None] * n
+    while not all(finished):
+        if not is_eval:
+            for i in range(n):
+                told[i] = teacher(tasks[i], states[i])
+                interactions += 0 if finished[i] else 1
+            student.instructions.append([None if w is None else list(w) for w in told])
+        chosen = student.next_actions(states)
+        before = states[:]
+        for i in range(n):
+            if not finished[i]:
+                states[i] = states[i].step(chosen[i])[1]
+                taken[i].append(chosen[i])
+                steps += 0 if is_eval else 1
+                said[i] = teacher.describe(world, [chosen[i]], [before[i], states[i]])
+        student.descriptions.append([None if w is None else list(w) for w in said])
+        for i in range(n):
+            clock[i] -= 1
+            if chosen[i] == STOP or clock[i] <= 0:
+                finished[i] = True
+    solved, gaps = [], []
+    for i in range(n):
+        solved.append(states[i].satisfies(tasks[i]))
+        if tasks[i].goal_name == "get":
+            if solved[i]:
+                gaps.append(0)
+            else:
+                probe = world.init_state(batch[i]["grid"], states[i].pos, states[i].dir)
+                gaps.append(len(teacher.find_closest_resources(tasks[i], probe)[1]))
+    return dict(action_seqs=taken, success=solved, distances=gaps, num_interactions=interactions,
+                num_steps=steps)
