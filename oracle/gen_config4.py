@@ -186,7 +186,27 @@ def run(which, data_dir, iters, log_every, medium_oracle=None, experiment="imita
                 rec["iters"][-1]["loss"] = loss
                 return loss
 
+        from students.active_primitive_language import ActivePrimitiveLanguageStudent
+        from trainers.active_primitive_language import ActivePrimitiveLanguageTrainer
+
+        class RecordingActiveStudent(ActivePrimitiveLanguageStudent):           # runs unchanged
+            # active_primitive_language.yaml: A/B only (no replay fixture) — rollout infos, losses,
+            # the learned action map and the random-stream position must agree
+            def init(self, states):
+                super().init(states)
+                self.cur = dict(is_eval=None, acts=[], refs=[], fh=[])
+
+            def set_tasks(self, tasks, is_eval):
+                self.cur["is_eval"] = is_eval
+                super().set_tasks(tasks, is_eval)
+
+            def learn(self):
+                loss = super().learn()
+                rec["iters"][-1]["loss"] = loss
+                return loss
+
         base_trainer = {"primitive_language": PrimitiveLanguageTrainer,
+                        "active_primitive_language": ActivePrimitiveLanguageTrainer,
                         "interactive_primitive_language": InteractivePrimitiveLanguageTrainer}.get(
                             experiment, ImitationTrainer)
 
@@ -219,7 +239,8 @@ def run(which, data_dir, iters, log_every, medium_oracle=None, experiment="imita
                 world._backend = OracleBackend(world, medium_oracle)
         assert config.student.model.input_size == 404 and config.student.model.n_actions == 6
         student = {"primitive_language": RecordingLanguageStudent,
-                   "interactive_primitive_language": RecordingInteractiveStudent}.get(experiment, RecordingStudent)(config)
+                   "interactive_primitive_language": RecordingInteractiveStudent,
+                   "active_primitive_language": RecordingActiveStudent}.get(experiment, RecordingStudent)(config)
         trainer = RecordingTrainer(config)
         torch.manual_seed(config.seed)
         config.random.seed(config.seed)
@@ -338,7 +359,9 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--log-every", type=int, default=15)
     ap.add_argument("--experiment", default="imitation",
-                    choices=["imitation", "primitive_language", "interactive_primitive_language"])
+                    choices=["imitation", "primitive_language", "interactive_primitive_language",
+                             "active_primitive_language"])
+    ap.add_argument("--no-golden", action="store_true", help="A/B comparison only, write no fixture")
     args = ap.parse_args()
     regen_dir = os.environ.get("PSK_REGEN_DIR", "/tmp/psk_data")
     data_dir = os.path.join(regen_dir, "config4_data")
@@ -357,6 +380,9 @@ def main():
     print("psketch_b200 world + teacher (oracle-backed backend): %.1f s" % (time.time() - t1))
     assert_same(a, b)
     print("IDENTICAL: batches, features, actions, teacher labels, losses, success, distances, eval trajectories")
+    if args.no_golden or args.experiment == "active_primitive_language":
+        print("A/B only: no fixture written; final losses", [round(e["loss"], 4) for e in a["iters"][-3:]])
+        return
     out = pack(a, splits)
     path = os.path.join(OUT, "config4_%s.npz" % args.experiment)
     np.savez_compressed(path, **out)
