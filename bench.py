@@ -537,6 +537,8 @@ def run_ours(args):
         w1 = load_workload(n1)
         env1 = VecCraft.from_instances(tables, w1["grids"], w1["env"], w1["pos"], w1["task"],
                                        max_timesteps=40, device=dev)
+        for _ in range(13):             # states spread over their episodes, as in the 65,536-env table
+            env1.tick(want_features=False)
         k1 = per_kernel_table(torch, env1, n1, nf, dev, peak, 3)
         k1["tick"] = k1.pop("tick_fused")
         k1["n_envs"] = n1
