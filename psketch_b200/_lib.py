@@ -68,10 +68,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("PSK_LIB") or LIB_PATH        # PSK_LIB: experiment builds for same-box A/B runs
+    if not os.path.exists(path):
         raise PskError("%s not found — run `python -c 'import __graft_entry__ as g; g.build()'` "
-                       "(there is no CPU fallback)" % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+                       "(there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
     lib.psk_version.restype = ctypes.c_char_p
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
     tp = ctypes.POINTER(CraftTablesC)
