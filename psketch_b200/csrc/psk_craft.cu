@@ -1446,7 +1446,7 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
                   uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
                   uint8_t *__restrict__ success_out, unsigned long long *stats,
                   int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int adv_first,
-                  uint32_t *chain) {
+                  uint32_t *chain, int64_t chain_g0) {
     constexpr int NT = NE + NFW * 32;
     constexpr int TPE = 8, EPW = 32 / TPE;
     constexpr int SPW = NE / NFW;              // env slots per feature warp
@@ -1464,10 +1464,13 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
     // next grid may launch; chain == NULL (persistent grids, huge batches) falls back to waiting
     // for the whole previous grid
     const int64_t grp0 = (int64_t)blockIdx.x * (NE / PSK_CHAIN_GROUP);
+    // groups are identified by the ADDRESS of their agent records (chain_g0 = group of env 0), so
+    // that launches on different slices of one batch agree on which counters guard which envs
+    auto grp = [&](int j) { return (chain_g0 + grp0 + j) & (PSK_CHAIN_GROUPS - 1); };
     const bool chain_thread = chain && tid < NE / PSK_CHAIN_GROUP &&
                               (grp0 + tid) * PSK_CHAIN_GROUP < n;
     if (chain) {
-        if (chain_thread) s_ticket[tid] = chain_enter(chain, grp0 + tid);
+        if (chain_thread) s_ticket[tid] = chain_enter(chain, grp(tid));
         __syncthreads();
     }
     // Programmatic dependent launch: let the next kernel in the stream (normally the next tick)
@@ -1480,7 +1483,7 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
             smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
             nf);
     if (chain) {
-        if (chain_thread) chain_wait(chain, grp0 + tid, s_ticket[tid]);
+        if (chain_thread) chain_wait(chain, grp(tid), s_ticket[tid]);
         __syncthreads();
     } else {
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1603,7 +1606,7 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
         }
         __syncthreads();  // s_rows / s_agent are recycled by the next super-tile
     }
-    if (chain_thread) chain_leave(chain, grp0 + tid, s_ticket[tid]);   // after the barrier above
+    if (chain_thread) chain_leave(chain, grp(tid), s_ticket[tid]);   // after the barrier above
     if (USE_TMA && !env_warp && (tid & 31) == 0) bulk_wait_read<0>();
     if (flags && err_flags) atomicOr(err_flags, (int)flags);
 }
@@ -1633,7 +1636,7 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
                      int feat_ring, uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
                      uint8_t *__restrict__ success_out, unsigned long long *stats,
                      int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int ticks,
-                     uint32_t *chain) {
+                     uint32_t *chain, int64_t chain_g0) {
     constexpr int NEW = (NE + 31) / 32 * 32;   // env-warp threads (lanes >= NE idle when NE < 32)
     constexpr int NT = NEW + NFW * 32;
     constexpr int TPE = 8, EPW = 32 / TPE;
@@ -1649,10 +1652,11 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
     const int tid = threadIdx.x;
     const bool env_warp = tid < NEW;
     const int64_t grp0 = (int64_t)blockIdx.x * (NE / PSK_CHAIN_GROUP);     // tile chaining, see the tick kernel
+    auto grp = [&](int j) { return (chain_g0 + grp0 + j) & (PSK_CHAIN_GROUPS - 1); };
     const bool chain_thread = chain && tid < NE / PSK_CHAIN_GROUP &&
                               (grp0 + tid) * PSK_CHAIN_GROUP < n;
     if (chain) {
-        if (chain_thread) s_ticket[tid] = chain_enter(chain, grp0 + tid);
+        if (chain_thread) s_ticket[tid] = chain_enter(chain, grp(tid));
         __syncthreads();
     }
     asm volatile("griddepcontrol.launch_dependents;");
@@ -1662,7 +1666,7 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
             smem_u32(smem_raw) + (uint32_t)((tid - NEW) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
             nf);
     if (chain) {
-        if (chain_thread) chain_wait(chain, grp0 + tid, s_ticket[tid]);
+        if (chain_thread) chain_wait(chain, grp(tid), s_ticket[tid]);
         __syncthreads();
     } else {
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1775,7 +1779,7 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
         }
         __syncthreads();
     }
-    if (chain_thread) chain_leave(chain, grp0 + tid, s_ticket[tid]);   // after the barrier above
+    if (chain_thread) chain_leave(chain, grp(tid), s_ticket[tid]);   // after the barrier above
     if (USE_TMA && !env_warp && (tid & 31) == 0) bulk_wait_read<0>();
     if (flags && err_flags) atomicOr(err_flags, (int)flags);
 }
@@ -1883,11 +1887,17 @@ static const psk_craft_tables *device_tables(const psk_craft_tables *caller_tabl
 }
 // Tile-chaining counters (psk_common.cuh), one zero-initialised array per device, allocated on the
 // first call (like the table copies: outside a CUDA-graph capture).  NULL = do not chain.
-static uint32_t *chain_counters(int64_t n) {
+static uint32_t *chain_counters(const psk_craft_state &s, int64_t *g0) {
     static uint32_t *ctr[PSK_MAX_DEVICES] = {nullptr};
     static std::mutex mu;
+    const int64_t n = s.n;
     if (tune(TUNE_TILE_CHAIN) == 0 || tune(TUNE_TICK_PDL) == 0) return nullptr;
     if ((n + PSK_CHAIN_GROUP - 1) / PSK_CHAIN_GROUP > PSK_CHAIN_GROUPS) return nullptr;
+    // groups are keyed by the address of their agent records: only batches (or slices) that start
+    // on a group boundary chain; anything else waits for the whole previous grid
+    constexpr uintptr_t GROUP_BYTES = (uintptr_t)PSK_CHAIN_GROUP * PSK_AGENT_BYTES;
+    if (reinterpret_cast<uintptr_t>(s.agent) % GROUP_BYTES) return nullptr;
+    *g0 = (int64_t)(reinterpret_cast<uintptr_t>(s.agent) / GROUP_BYTES);
     const int dev = current_device();
     std::lock_guard<std::mutex> lock(mu);
     if (!ctr[dev]) {
@@ -2068,10 +2078,12 @@ template <int W, int H, int WIN> struct Config {
         cfg.attrs = attr;
         cfg.numAttrs = pdl ? 1 : 0;
         const int cell_stride = s.cell_stride, K = t->n_kinds;
-        uint32_t *chain = (g == tiles && pdl) ? chain_counters(s.n) : nullptr;   // one tile per CTA only
+        int64_t chain_g0 = 0;
+        uint32_t *chain = (g == tiles && pdl) ? chain_counters(s, &chain_g0) : nullptr;   // one tile per CTA only
         return check(cudaLaunchKernelEx(&cfg, kern, dt, s.grid, s.agent, action_in, ep.scen_grid,
                                         ep.scen_idx, ep.init_agent, features_out, expert_out, done,
-                                        success, stats, err, s.n, cell_stride, K, f, adv_first, chain));
+                                        success, stats, err, s.n, cell_stride, K, f, adv_first, chain,
+                                        chain_g0));
     }
     template <int NE, int NFW, bool TMA>
     static int rollout_variant(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
@@ -2107,11 +2119,12 @@ template <int W, int H, int WIN> struct Config {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         const int cell_stride = s.cell_stride, K = t->n_kinds;
-        uint32_t *chain = chain_counters(s.n);
+        int64_t chain_g0 = 0;
+        uint32_t *chain = chain_counters(s, &chain_g0);
         return check(cudaLaunchKernelEx(&cfg, kern, dt, s.grid, s.agent, action_in, ep.scen_grid,
                                         ep.scen_idx, ep.init_agent, features_out, feat_ring,
                                         expert_out, done, success, stats, err, s.n, cell_stride, K,
-                                        f, ticks, chain));
+                                        f, ticks, chain, chain_g0));
     }
     static int rollout(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep, int ticks,
                        const uint8_t *action_in, float *features_out, int feat_ring,
