@@ -1469,6 +1469,14 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
     auto grp = [&](int j) { return (chain_g0 + grp0 + j) & (PSK_CHAIN_GROUPS - 1); };
     const bool chain_thread = chain && tid < NE / PSK_CHAIN_GROUP &&
                               (grp0 + tid) * PSK_CHAIN_GROUP < n;
+    // The table loads are ISSUED first and committed to shared memory after the ticket round trip:
+    // the two global latencies of a CTA's start-up overlap instead of adding up (a single-tick CTA
+    // lives ~10 us, ~3 us of which used to be start-up latency: ticket, tables, state).
+    constexpr int TW = (int)(sizeof(psk_craft_tables) / 16);
+    uint4 tv[(TW + NT - 1) / NT];
+#pragma unroll
+    for (int k = 0; k < (TW + NT - 1) / NT; k++)
+        if (tid + k * NT < TW) tv[k] = __ldg(reinterpret_cast<const uint4 *>(T) + tid + k * NT);
     if (chain) {
         if (chain_thread) s_ticket[tid] = chain_enter(chain, grp(tid));
         __syncthreads();
@@ -1477,17 +1485,20 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
     // be scheduled while this one drains, and do everything that does not depend on the previous
     // kernel (tables, buffer init) before waiting for it.  Both are no-ops for a plain launch.
     asm volatile("griddepcontrol.launch_dependents;");
-    stage_tables(st, T);
     if (!USE_TMA && !env_warp && features_out)
         feature_buffer_init<8, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
             smem_u32(smem_raw) + (uint32_t)((tid - NE) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
             nf);
+#pragma unroll
+    for (int k = 0; k < (TW + NT - 1) / NT; k++)
+        if (tid + k * NT < TW) reinterpret_cast<uint4 *>(st.words)[tid + k * NT] = tv[k];
     if (chain) {
         if (chain_thread) chain_wait(chain, grp(tid), s_ticket[tid]);
-        __syncthreads();
+        __syncthreads();            // nobody touches the state before the chain threads' acquire
     } else {
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
+    // (without chaining the tables become visible with the barrier that follows the state load)
     uint32_t flags = 0;
     int it = 0;  // this feature warp's chunk counter
     const int64_t n_super = (n + NE - 1) / NE;
@@ -2079,7 +2090,10 @@ template <int W, int H, int WIN> struct Config {
         cfg.numAttrs = pdl ? 1 : 0;
         const int cell_stride = s.cell_stride, K = t->n_kinds;
         int64_t chain_g0 = 0;
-        uint32_t *chain = (g == tiles && pdl) ? chain_counters(s, &chain_g0) : nullptr;   // one tile per CTA only
+        // one tile per CTA only; not with TMA stores: a single-tick CTA would pay the release fence of
+        // chain_leave while its bulk stores are in flight (1 M envs, same box: 342 us chained vs 304 not;
+        // vector stores at 262,144 envs: 72.4 chained vs 78.5 not — profiles/README.md)
+        uint32_t *chain = (g == tiles && pdl && !TMA) ? chain_counters(s, &chain_g0) : nullptr;
         return check(cudaLaunchKernelEx(&cfg, kern, dt, s.grid, s.agent, action_in, ep.scen_grid,
                                         ep.scen_idx, ep.init_agent, features_out, expert_out, done,
                                         success, stats, err, s.n, cell_stride, K, f, adv_first, chain,
