@@ -185,7 +185,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 // PSK_CHAIN_GROUP envs:  chain[2g] tickets handed out, chain[2g+1] ticket holders finished.
 // A CTA takes one ticket per group it owns (its position in that group's launch order), waits until
 // every earlier holder has finished (ld.acquire: also drops stale L1 lines), and on exit publishes
-// its state writes with fence + st.release.  The ticket is taken BEFORE launch_dependents, so a
+// its state writes with st.release (after the CTA barrier).  The ticket is taken BEFORE launch_dependents, so a
 // dependent CTA can never overtake its predecessor's ticket; the earliest holder of a group never
 // waits on an unfinished CTA, so the chain always drains.  Counters only ever increase (u32 wrap
 // is harmless under ==), which is what makes the scheme work under CUDA-graph replay.
@@ -203,7 +203,9 @@ __device__ __forceinline__ void chain_wait(const uint32_t *chain, int64_t g, uin
     }
 }
 __device__ __forceinline__ void chain_leave(uint32_t *chain, int64_t g, uint32_t ticket) {
-    __threadfence();
+    // st.release.gpu IS fence + store (SASS: MEMBAR.ALL.GPU; ST): with the CTA barrier before it, it
+    // publishes every thread's state writes.  (A __threadfence() in front adds a second, sequentially
+    // consistent MEMBAR.SC.GPU for nothing.)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(chain + 2 * g + 1), "r"(ticket + 1) : "memory");
 }
 
