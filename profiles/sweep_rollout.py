@@ -27,7 +27,6 @@ def main():
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--ticks", type=int, default=8)
     ap.add_argument("--variants", default="0:0,0:1,2:0,2:1,3:0,3:1,4:0,4:1")
-    ap.add_argument("--extra", default="", help="extra knobs, e.g. rollout_split=1")
     args = ap.parse_args()
     tables = CraftTables()
     T = args.ticks
