@@ -341,8 +341,11 @@ def run_ours(args):
     def n_launches(plan):
         return len(plan) * (1 if T > 1 else per_tick_launches)
 
+    ticks_done = [0]
+
     def run_steps(k):
         """Exactly k ticks."""
+        ticks_done[0] += k
         if args.no_graph:
             done = 0
             while T > 1 and k - done >= T:
@@ -389,6 +392,8 @@ def run_ours(args):
     if args.repeats > 0:
         R = args.repeats
     env.stats.zero_()
+    ticks_before = ticks_done[0]
+    phase0 = (40 - env.timer.to(torch.int64)).cpu().numpy()      # ticks into the running episode, per env
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
@@ -409,6 +414,17 @@ def run_ours(args):
                            dtype=torch.float64, device=dev)
     total = torch.tensor([marks[0].elapsed_time(marks[R]) * 1e-3], dtype=torch.float64, device=dev)
     stats = env.stats.clone()
+    # Size-independent invariant over the WHOLE timed region (every launch, chained or not): teacher-
+    # driven episodes of instance i last exactly ref_len[i] ticks and always succeed, so the number of
+    # episodes that end inside the region is known in closed form; one env whose state was corrupted
+    # anywhere would break the count.
+    episodes_ok = None
+    if rand_act is None:
+        ref_len = np.roll(wl["raw"]["train_ref_len"][np.arange(n) % wl["n_instances"]], -shift).astype(np.int64)
+        expected = int(((phase0 + (ticks_done[0] - ticks_before)) // ref_len).sum())
+        local = stats.cpu().numpy()
+        episodes_ok = bool(int(local[0]) == expected and int(local[1]) == expected)
+        assert episodes_ok, "episodes %d / successes %d, expected %d" % (local[0], local[1], expected)
     if distributed:
         dist.all_reduce(per_rep, op=dist.ReduceOp.MAX)      # MAX over ranks, repeat by repeat
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
@@ -495,6 +511,7 @@ def run_ours(args):
         "gpu_launches": timed_launches // R,
         "gpu_launches_timed_region": timed_launches,
         "parity_checked": parity is not None, "parity": parity,
+        "episodes_match_closed_form": episodes_ok,
         "stats_allreduce_us": stats_allreduce_us if distributed else None,
         "e2e": e2e["headline"], "e2e_variants": e2e["variants"],
         "episodes": int(st[0]), "successes": int(st[1]),
