@@ -271,7 +271,9 @@ def run_ours(args):
     # Teacher-driven rollouts need nothing from outside the kernel, so T ticks run per launch
     # (psk_craft_rollout: state stays in shared memory between ticks).  T = 1, the random policy
     # and --unfused use one psk_craft_tick launch per step.
-    T = max(1, args.ticks_per_launch) if (fused and rand_act is None) else 1
+    T = max(1, args.ticks_per_launch) if fused else 1
+    rand_block = (torch.empty((T, n), dtype=torch.uint8, device=dev)
+                  if (rand_act is not None and T > 1) else None)
     # Ring of output frames: larger than L2 (126 MB), and at least T + 1 frames so that no frame is
     # written twice within one launch — a CTA that came back to the same lines a few ticks later
     # would find them still dirty in L2, the writes would merge there and never reach HBM, and the
@@ -293,7 +295,11 @@ def run_ours(args):
         # tick t of a launch writes ring slot t % ring: nothing is written twice within a launch,
         # and between two launches' writes to the same line >= 850 MB pass through the 126 MB L2
         ticks = ticks or T
-        env.rollout(ticks, features_out=feat_ring, out=routs.setdefault(ticks, {}), want_flags=True)
+        acts = None
+        if rand_block is not None:      # off-policy: one Philox launch fills the action block of the rollout
+            acts = rand_block[:ticks]
+            env.random_actions(0, seed=123, out=acts, device_clock=True, ticks=ticks)
+        env.rollout(ticks, actions=acts, features_out=feat_ring, out=routs.setdefault(ticks, {}), want_flags=True)
 
     for i in range(ring):           # allocate output tensors outside the graph
         tick(i)
@@ -339,7 +345,7 @@ def run_ours(args):
             graphs[r] = capture(plan_for(r))
 
     def n_launches(plan):
-        return len(plan) * (1 if T > 1 else per_tick_launches)
+        return len(plan) * ((2 if rand_block is not None else 1) if T > 1 else per_tick_launches)
 
     ticks_done = [0]
 
@@ -351,11 +357,11 @@ def run_ours(args):
             while T > 1 and k - done >= T:
                 launch_rollout()
                 done += T
-                launches[0] += 1
+                launches[0] += 2 if rand_block is not None else 1
             while done < k:
                 if T > 1:
                     launch_rollout(k - done)
-                    launches[0] += 1
+                    launches[0] += 2 if rand_block is not None else 1
                     done = k
                 else:
                     tick(done)

@@ -206,6 +206,10 @@ int psk_craft_sample_scenarios(const psk_craft_tables *t, uint8_t *scen_grid, ui
  * replay. */
 int psk_random_actions(uint8_t *out, int64_t n, int32_t n_actions, uint64_t seed, uint64_t t,
                        const unsigned long long *t_dev, void *stream);
+/* The same for `ticks` consecutive clocks at once: out u8[ticks][n], row k = the actions of clock
+ * t + k — the action_in block of a psk_craft_rollout launch (off-policy rollouts, `ticks` per launch). */
+int psk_random_actions_block(uint8_t *out, int64_t n, int32_t ticks, int32_t n_actions, uint64_t seed,
+                             uint64_t t, const unsigned long long *t_dev, void *stream);
 
 /* Dataset instance positions (make_data.py:203-208): per group, `per_group` distinct uniformly
  * random free cells of scenario group_scen[g]; out_pos u8[n_groups][per_group][2]. */

@@ -24,7 +24,7 @@ CRAFT_EXPORTS = (
     "psk_craft_host_tick", "psk_craft_sample_scenarios", "psk_craft_sample_positions",
     "psk_random_actions", "psk_craft_rollout", "psk_set_tuning", "psk_get_tuning",
     "psk_craft_features_u8", "psk_craft_host_reset", "psk_craft_host_put_state",
-    "psk_craft_host_get_state", "psk_craft_host_tick_resident",
+    "psk_craft_host_get_state", "psk_craft_host_tick_resident", "psk_random_actions_block",
 )
 FEATURES_NONE, FEATURES_F32, FEATURES_U8 = 0, 1, 2
 
@@ -101,6 +101,7 @@ def load():
     lib.psk_craft_sample_scenarios.argtypes = [tp, vp, vp, vp, i32, i32, u64, u64, i64, i32, vp, vp]
     lib.psk_craft_sample_positions.argtypes = [tp, vp, vp, i32, vp, u64, u64, i64, i32, vp, vp]
     lib.psk_random_actions.argtypes = [vp, i64, i32, u64, u64, vp, vp]
+    lib.psk_random_actions_block.argtypes = [vp, i64, i32, i32, u64, u64, vp, vp]
     lib.psk_craft_features_u8.argtypes = [tp, CraftStateC, vp, vp]
     lib.psk_craft_host_reset.argtypes = [vp, i64]
     lib.psk_craft_host_put_state.argtypes = [vp, vp, vp, i64]

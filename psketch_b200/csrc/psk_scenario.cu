@@ -174,14 +174,19 @@ craft_sample_positions_kernel(const uint8_t *__restrict__ scen_grid,
 
 // Off-policy action source: action[e] ~ U{0..n_actions-1} from
 // Philox(key = seed, counter = (env, t)): reproducible whatever the launch geometry.
+// out u8[ticks][n]: row k holds the actions of clock t + k (ticks = 1: the plain per-tick form; a
+// block of rows feeds psk_craft_rollout's action_in, so the off-policy variant also runs `ticks`
+// ticks per launch).
 __global__ void __launch_bounds__(256)
-random_actions_kernel(uint8_t *__restrict__ out, int64_t n, int n_actions, uint64_t seed, uint64_t t,
-                      const unsigned long long *__restrict__ t_dev) {
+random_actions_kernel(uint8_t *__restrict__ out, int64_t n, int ticks, int n_actions, uint64_t seed,
+                      uint64_t t, const unsigned long long *__restrict__ t_dev) {
     if (t_dev) t += *t_dev;   // device-side clock (e.g. the env-step counter): advances under graph replay
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        Philox rng(seed, (uint64_t)e, t);
-        out[e] = (uint8_t)rng.below(n_actions);
+    const int64_t total = n * ticks;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = i / n, e = i - k * n;
+        Philox rng(seed, (uint64_t)e, t + (uint64_t)k);
+        out[i] = (uint8_t)rng.below(n_actions);
     }
 }
 
@@ -222,7 +227,17 @@ int psk_random_actions(uint8_t *out, int64_t n, int32_t n_actions, uint64_t seed
     if (n == 0) return PSK_OK;
     int64_t b = (n + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;
-    random_actions_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(out, n, n_actions, seed, t, t_dev);
+    random_actions_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(out, n, 1, n_actions, seed, t, t_dev);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+int psk_random_actions_block(uint8_t *out, int64_t n, int32_t ticks, int32_t n_actions, uint64_t seed,
+                             uint64_t t, const unsigned long long *t_dev, void *stream) {
+    if (n < 0 || ticks < 0 || n_actions <= 0 || n_actions > 255 || (n && ticks && !out)) return PSK_ERR_BADARG;
+    if (n == 0 || ticks == 0) return PSK_OK;
+    int64_t b = (n * ticks + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    random_actions_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(out, n, ticks, n_actions, seed, t, t_dev);
     return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
 }
 

@@ -248,17 +248,20 @@ class VecCraft(object):
         _lib.check(rc, "psk_craft_rollout")
         return out
 
-    def random_actions(self, t=0, seed=123, out=None, device_clock=False):
-        """u8[N] uniform actions from Philox(seed, counter=(env, t)) — off-policy rollouts.
+    def random_actions(self, t=0, seed=123, out=None, device_clock=False, ticks=None):
+        """u8[N] uniform actions from Philox(seed, counter=(env, t)) — off-policy rollouts; with
+        ``ticks`` u8[ticks, N], row k from clock t + k (the ``actions`` block of ``rollout``).
         device_clock=True adds the env-step counter (stats[2]) to t on the device, so a captured
         CUDA graph draws fresh actions on every replay."""
+        shape = (self.n,) if ticks is None else (int(ticks), self.n)
         if out is None:
-            out = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+            out = torch.empty(shape, dtype=torch.uint8, device=self.device)
         clock = ctypes.c_void_p(self.stats.data_ptr() + 16) if device_clock else None
         with torch.cuda.device(self.device):
-            rc = self.lib.psk_random_actions(_ptr(out), self.n, 6, ctypes.c_uint64(seed),
-                                             ctypes.c_uint64(t), clock, self._stream())
-        _lib.check(rc, "psk_random_actions")
+            rc = self.lib.psk_random_actions_block(_ptr(out), self.n, 1 if ticks is None else int(ticks), 6,
+                                                   ctypes.c_uint64(seed), ctypes.c_uint64(t), clock,
+                                                   self._stream())
+        _lib.check(rc, "psk_random_actions_block")
         return out
 
     # ------------------------------------------------------------------ views / checks

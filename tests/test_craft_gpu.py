@@ -898,3 +898,28 @@ def test_back_to_back_ticks_on_overlapping_slices(splits, medium_tables, medium_
     assert np.array_equal(_np(env.pos).astype(np.int32), orc.pos)
     assert np.array_equal(_np(env.timer).astype(np.int32), orc.timer)
     env.check_errors()
+
+
+def test_random_action_block_feeds_the_rollout_kernel(splits, medium_tables, medium_oracle):
+    """Off-policy variant with several ticks per launch: psk_random_actions_block fills the action
+    block of psk_craft_rollout; rows equal the per-tick generator, and the rollout equals the oracle
+    driven by the same actions."""
+    from psketch_b200.vec import VecCraft
+    n, T = 5003, 7
+    idx = np.arange(n) % 2200
+    args = (splits["dev_grids"], splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
+            splits["dev_inst_task"][idx])
+    env = VecCraft.from_instances(medium_tables, *args, max_timesteps=9)
+    block = env.random_actions(t=100, seed=123, ticks=T)
+    for k in range(T):
+        assert torch.equal(block[k], env.random_actions(t=100 + k, seed=123))
+    orc = _OracleTicks(medium_oracle, *args, max_timesteps=9)
+    for rep in range(4):
+        block = env.random_actions(t=1000 * rep, seed=7, ticks=T)
+        out = env.rollout(T, actions=block)
+        for k in range(T):
+            ref = orc.tick(_np(block[k]), want_features=False)
+            assert np.array_equal(_np(out["expert"][k]), ref["expert"]), (rep, k)
+            assert np.array_equal(_np(out["done"][k]), ref["done"]), (rep, k)
+    orc.assert_state_equals(env)
+    env.check_errors()
