@@ -1050,12 +1050,16 @@ __device__ __forceinline__ void fence_async_smem() {
 // KC > 0 fixes the number of kinds at compile time (KC == K) so that the loops unroll.
 // Each tile is EPW*nf elements (rounded up to 16 bytes) + one 16-byte trash slot for the
 // scatter's no-op stores.
-// Element size of the tile on the vector-store path, measured on one box (profiles/README.md):
-// the stand-alone features kernel is 4 % faster with the u8 tile (it is bound by the L1/LSU data
-// pipe), the fused kernels are 3 % slower with it (their feature warps share the issue slots
-// with the teacher, and widening costs 8 more instructions per 16 bytes), so they keep f32.
+// Element size of the tile on the vector-store path (profiles/README.md).  Round 1: the stand-alone
+// features kernel was 4 % faster with the u8 tile, the fused kernels 3 % slower (their feature warps
+// share the issue slots with the teacher, widening costs 8 more instructions per 16 bytes).  Round 2,
+// with tile chaining and the shorter USE path the balance flipped: u8 tile 15.36 vs 15.40 us per tick
+// in the rollout kernel, 17.65 vs 18.35 us in the single-tick kernel (same box, interleaved) — u8
+// everywhere now; -DPSK_ESZ_FUSED_KERNELS=4 rebuilds the f32 tile for A/B runs.
 #define PSK_ESZ_FEATURES_KERNEL 1
-#define PSK_ESZ_FUSED_KERNELS 4
+#ifndef PSK_ESZ_FUSED_KERNELS          // experiment builds: -DPSK_ESZ_FUSED_KERNELS=4 + PSK_LIB
+#define PSK_ESZ_FUSED_KERNELS 1
+#endif
 __host__ __device__ constexpr int feature_tile_bytes(bool tma, int epw, int nf, int vec_esz) {
     return ((epw * nf * (tma ? 4 : vec_esz) + 15) / 16) * 16 + 16;
 }
