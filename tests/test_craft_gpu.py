@@ -923,3 +923,35 @@ def test_random_action_block_feeds_the_rollout_kernel(splits, medium_tables, med
             assert np.array_equal(_np(out["done"][k]), ref["done"]), (rep, k)
     orc.assert_state_equals(env)
     env.check_errors()
+
+
+def test_host_state_upload_download_round_trip(splits, medium_tables, medium_oracle):
+    """psk_craft_host_put_state / _get_state: a caller moves between the state-round-trip mode and
+    the resident mode without losing anything."""
+    from psketch_b200.host import HostCraft
+    n = 3001
+    idx = np.arange(n) % 2200
+    args = (splits["dev_grids"], splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
+            splits["dev_inst_task"][idx])
+    env = HostCraft(medium_tables, *args, max_timesteps=15, chunk_envs=512)
+    orc = _OracleTicks(medium_oracle, *args, max_timesteps=15)
+    for t in range(4):                       # states travel with every call
+        env.tick()
+        ref = orc.tick()
+        assert np.array_equal(env.expert, ref["expert"]) and np.array_equal(env.features, ref["features"])
+    env.upload()                             # host state -> device, resident from here on
+    with pytest.raises(Exception, match="resident"):
+        env.tick()
+    for t in range(5):
+        env.tick_resident(features="u8")
+        ref = orc.tick()
+        assert np.array_equal(env.expert, ref["expert"])
+        assert np.array_equal(env.features_u8.astype(np.float32), ref["features"])
+    env.download(keep_resident=False)        # back to host-side states
+    assert np.array_equal(env.grid[:, :64], orc.grid)
+    for t in range(3):
+        env.tick()
+        ref = orc.tick()
+        assert np.array_equal(env.expert, ref["expert"]) and np.array_equal(env.done, ref["done"])
+    assert np.array_equal(env.agent[:, 24:26].astype(np.int32), orc.pos)
+    env.close()
