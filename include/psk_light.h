@@ -57,9 +57,10 @@ int psk_light_expert(const psk_light_scenario *scen, const int32_t *scen_idx,
 /* The teacher as a table.  Its answer depends only on (scenario, x, y, keys on the map) — at most
  * 32 x 32 x 2^n_keys states per scenario, shared by all envs of the scenario — so the backward
  * flood of psk_light_expert runs once per scenario (one CTA each) and every later query is a few
- * loads.  table u16[n_scen][1 << max_keys][32][32]: fewest actions to the goal room from cell
- * (x, y) with key subset m on the map, 0xFFFF = unreachable; psk_light_teacher_table_bytes gives its
- * size.  psk_light_expert_table answers like psk_light_expert (same actions, same dist). */
+ * loads.  Per scenario the table holds u16[1 << max_keys][32][32] — fewest actions to the goal room
+ * from cell (x, y) with key subset m on the map, 0xFFFF = unreachable — followed by three u8[32][32]
+ * per-cell maps (keys locking the door here, keys lying here, doors here) that replace the door / key
+ * loops of step and features in the fused tick; psk_light_teacher_table_bytes gives the total size.  psk_light_expert_table answers like psk_light_expert (same actions, same dist). */
 int64_t psk_light_teacher_table_bytes(int64_t n_scen, int32_t max_keys);
 int psk_light_teacher_build(const psk_light_scenario *scen, int64_t n_scen, int32_t max_keys,
                             uint16_t *table, void *stream);

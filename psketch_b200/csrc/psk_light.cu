@@ -260,6 +260,27 @@ light_expert_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *
 // One CTA per scenario; warp w sweeps the layers m = w, w + 8, ...; lane x holds row x; all layers
 // advance level by level (Jacobi: a level reads only the previous level's boards, double-buffered in
 // shared memory), one __syncthreads_or per level.  A query is then a handful of loads.
+// Per-scenario block of the teacher table: dist u16[layer_cap][32][32], then three per-cell byte maps
+// that turn the door / key loops of step, features and the teacher query into single loads:
+//   cell_lock[x*32+y]   bitmask of the keys that lock the door at this cell (0: no door here)
+//   cell_keys[x*32+y]   bitmask of the keys lying on this cell
+//   cell_doors[x*32+y]  number of doors at this cell
+#define PSK_LIGHT_AUX_BYTES (3 * 1024)
+__host__ __device__ constexpr size_t light_block_u16(int layer_cap) {
+    return (size_t)layer_cap * 1024 + PSK_LIGHT_AUX_BYTES / 2;
+}
+struct LightAux {
+    const uint8_t *lock, *keys, *doors;
+    __device__ __forceinline__ LightAux(const uint16_t *block, int layer_cap) {
+        lock = reinterpret_cast<const uint8_t *>(block + (size_t)layer_cap * 1024);
+        keys = lock + 1024;
+        doors = keys + 1024;
+    }
+    __device__ __forceinline__ bool locked(int x, int y, uint32_t alive) const {     // light.py:233
+        return (lock[(x & 31) * 32 + (y & 31)] & alive) != 0;
+    }
+};
+
 __global__ void __launch_bounds__(256)
 light_teacher_build_kernel(const psk_light_scenario *__restrict__ scen, uint16_t *__restrict__ table,
                            int layer_cap) {
@@ -269,8 +290,24 @@ light_teacher_build_kernel(const psk_light_scenario *__restrict__ scen, uint16_t
     constexpr unsigned FULL = 0xffffffffu;
     const int nk = s.n_keys;
     const int n_layers = 1 << nk;
-    uint16_t *T = table + (size_t)blockIdx.x * layer_cap * 1024;
+    uint16_t *T = table + (size_t)blockIdx.x * light_block_u16(layer_cap);
     for (int i = threadIdx.x; i < layer_cap * 1024; i += blockDim.x) T[i] = 0xFFFFu;
+    {   // per-cell maps
+        uint8_t *aux = reinterpret_cast<uint8_t *>(T + (size_t)layer_cap * 1024);
+        for (int c = threadIdx.x; c < 1024; c += blockDim.x) {
+            const int x = c >> 5, y = c & 31;
+            int nd = 0;
+            uint32_t lk = 0, ky = 0;
+            for (int d = 0; d < s.n_doors; d++) nd += (s.doors[d][0] == x && s.doors[d][1] == y);
+            for (int k = 0; k < s.n_keys; k++) {
+                if (nd && s.keys[k][2] == x && s.keys[k][3] == y) lk |= 1u << k;
+                if (s.keys[k][0] == x && s.keys[k][1] == y) ky |= 1u << k;
+            }
+            aux[c] = (uint8_t)lk;
+            aux[1024 + c] = (uint8_t)ky;
+            aux[2048 + c] = (uint8_t)nd;
+        }
+    }
     __syncthreads();
     if (n_layers > layer_cap) return;               // more keys than announced: everything unreachable
     const uint32_t wall_row = s.walls[lane];
@@ -322,7 +359,8 @@ light_teacher_build_kernel(const psk_light_scenario *__restrict__ scen, uint16_t
 // Teacher query against the table (thread per env).  dist 0 = in the goal room (action 254),
 // 0xFFFF = unreachable (action 255); else the smallest action whose successor is one level closer.
 __device__ __forceinline__ int light_table_action(const psk_light_scenario &s, const uint16_t *T,
-                                                  int x, int y, uint32_t alive, int &dist) {
+                                                  const LightAux &aux, int x, int y, uint32_t alive,
+                                                  int &dist) {
     if (x / PSK_LIGHT_ROOM == s.goal_rx && y / PSK_LIGHT_ROOM == s.goal_ry && !light_wall(s, x, y)) {
         dist = 0;
         return 254;
@@ -333,14 +371,19 @@ __device__ __forceinline__ int light_table_action(const psk_light_scenario &s, c
         return 255;
     }
     dist = d;
+    // the four neighbours' distances are independent loads: issue them together
+    int nd[4];
+    bool ok[4];
+#pragma unroll
     for (int a = 0; a < 4; a++) {
         const int nx = x + dx_of(a), ny = y + dy_of(a);
-        if (light_wall(s, nx, ny) || light_locked_door(s, nx, ny, alive)) continue;
-        if (T[(alive * 32 + nx) * 32 + ny] == d - 1) return a;
+        ok[a] = !light_wall(s, nx, ny) && !aux.locked(nx, ny, alive);
+        nd[a] = ok[a] ? T[(alive * 32 + (nx & 31)) * 32 + (ny & 31)] : 0xFFFF;
     }
-    uint32_t m2 = alive;
-    for (int k = 0; k < s.n_keys; k++)
-        if (((alive >> k) & 1) && s.keys[k][0] == x && s.keys[k][1] == y) m2 &= ~(1u << k);
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+        if (ok[a] && nd[a] == d - 1) return a;
+    const uint32_t m2 = alive & ~(uint32_t)aux.keys[(x & 31) * 32 + (y & 31)];
     if (m2 != alive && T[(m2 * 32 + x) * 32 + y] == d - 1) return 4;
     return 255;
 }
@@ -356,8 +399,9 @@ light_expert_table_kernel(const psk_light_scenario *__restrict__ scen, const int
         const psk_light_scenario &s = scen[si];
         const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
         int d;
-        const int a = light_table_action(s, table + (size_t)si * layer_cap * 1024, st & 0xFF, (st >> 8) & 0xFF,
-                                         (st >> 16) & 0xFF, d);
+        const uint16_t *T = table + (size_t)si * light_block_u16(layer_cap);
+        const LightAux aux(T, layer_cap);
+        const int a = light_table_action(s, T, aux, st & 0xFF, (st >> 8) & 0xFF, (st >> 16) & 0xFF, d);
         action[e] = (uint8_t)a;
         if (dist_out) dist_out[e] = (int16_t)d;
     }
@@ -387,18 +431,18 @@ light_tick_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__
             const int x = st & 0xFF, y = (st >> 8) & 0xFF;
             const uint32_t alive = (st >> 16) & 0xFF;
             int d;
-            const int ref = light_table_action(s, table + (size_t)si * layer_cap * 1024, x, y, alive, d);
+            const uint16_t *T = table + (size_t)si * light_block_u16(layer_cap);
+            const LightAux aux(T, layer_cap);
+            const int ref = light_table_action(s, T, aux, x, y, alive, d);
             expert_out[e] = (uint8_t)ref;
+            const int cell = (x & 31) * 32 + (y & 31);
             if (features_out) {                                   // light.py:191-204, see light_features_kernel
-                float locked = 0.f, open = 0.f, key = 0.f;
-                for (int dd = 0; dd < s.n_doors; dd++)
-                    if (s.doors[dd][0] == x && s.doors[dd][1] == y) {
-                        if (light_locked_door(s, x, y, alive)) locked += 1.f; else open += 1.f;
-                    }
-                for (int k = 0; k < s.n_keys; k++)
-                    if (((alive >> k) & 1) && s.keys[k][0] == x && s.keys[k][1] == y &&
-                        x % PSK_LIGHT_ROOM != 0 && y % PSK_LIGHT_ROOM != 0)
-                        key += 1.f;
+                const float doors_here = (float)aux.doors[cell];
+                const bool lk = aux.locked(x, y, alive);
+                const float locked = lk ? doors_here : 0.f, open = lk ? 0.f : doors_here;
+                float key = 0.f;
+                if (x % PSK_LIGHT_ROOM != 0 && y % PSK_LIGHT_ROOM != 0)
+                    key = (float)__popc((uint32_t)aux.keys[cell] & alive);
                 float4 *o = reinterpret_cast<float4 *>(features_out + e * PSK_LIGHT_N_FEATURES);
                 __stcs(o, make_float4(locked, locked, locked, locked));
                 __stcs(o + 1, make_float4(open, open, open, open));
@@ -418,10 +462,9 @@ light_tick_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__
                 if (a < 4) {
                     nx = x + dx_of(a);
                     ny = y + dy_of(a);
-                    if (light_wall(s, nx, ny) || light_locked_door(s, nx, ny, alive)) { nx = x; ny = y; }
+                    if (light_wall(s, nx, ny) || aux.locked(nx, ny, alive)) { nx = x; ny = y; }
                 } else {
-                    for (int k = 0; k < s.n_keys; k++)
-                        if (((alive >> k) & 1) && s.keys[k][0] == x && s.keys[k][1] == y) n_alive &= ~(1u << k);
+                    n_alive = alive & ~(uint32_t)aux.keys[cell];
                 }
                 nst = uint32_t(nx) | (uint32_t(ny) << 8) | (n_alive << 16) | (uint32_t(elapsed) << 24);
             }
@@ -519,7 +562,7 @@ int psk_light_expert(const psk_light_scenario *scen, const int32_t *scen_idx,
 
 int64_t psk_light_teacher_table_bytes(int64_t n_scen, int32_t max_keys) {
     if (n_scen < 0 || max_keys < 0 || max_keys > PSK_LIGHT_MAX_KEYS) return -1;
-    return n_scen * ((int64_t)1 << max_keys) * 1024 * (int64_t)sizeof(uint16_t);
+    return n_scen * (int64_t)light_block_u16(1 << max_keys) * (int64_t)sizeof(uint16_t);
 }
 
 int psk_light_teacher_build(const psk_light_scenario *scen, int64_t n_scen, int32_t max_keys,
