@@ -2151,16 +2151,14 @@ template <int W, int H, int WIN> struct Config {
         if constexpr (!BITBOARD || WIN != 3) {
             return PSK_ERR_UNSUPPORTED;
         } else {
-            // CTA shape and store path by batch size (bench.py sweeps, profiles/README.md):
-            //   < 65,536 envs   64 env threads + 2 feature warps, one wave of CTAs, vector stores;
-            //   65,536 and up   32 env threads + 2 feature warps (96 threads, 9 CTAs per SM): at
-            //                   65,536 envs that is 2,048 CTAs on 1,332 slots, so CTAs that finish
-            //                   early are replaced instead of leaving their SM idle (16.75 vs
-            //                   17.66 us per tick); vector stores up to 196,608 envs, TMA above.
-            // PSK_ROLLOUT_VARIANT (0 / 2) and PSK_ROLLOUT_TMA (0 / 1) override for experiments.
+            // CTA shape and store path (sweeps in profiles/README.md): 32 env threads + 2 feature warps
+            // (96 threads, 9 CTAs per SM) at every batch size — in round 1 a single wave of 64 + 2 CTAs
+            // won below 65,536 envs, with tile chaining the smaller CTAs win there too (32,768 envs:
+            // 8.10 vs 8.65 us per tick; 4,096: 3.89 vs 4.87); vector stores up to 196,608 envs, TMA above.
+            // rollout_variant (0 = 64 + 2, 2 = 32 + 2, 3 = 16 + 2, 4 = 16 + 1) and rollout_tma override.
             const int env_tma = tune(TUNE_ROLLOUT_TMA), env_variant = tune(TUNE_ROLLOUT_VARIANT);
             const int tma = env_tma >= 0 ? env_tma : (s.n > 196608 ? 1 : 0);
-            const int variant = env_variant >= 0 ? env_variant : (s.n >= 65536 ? 2 : 0);
+            const int variant = env_variant >= 0 ? env_variant : 2;
 #define PSK_ROLLOUT_ARGS t, s, ep, ticks, action_in, features_out, feat_ring, expert_out, done, success, stats, err, st
             if (variant == 2)
                 return tma ? rollout_variant<32, 2, true>(PSK_ROLLOUT_ARGS)
