@@ -43,8 +43,10 @@ def policy_rollouts(env, policy, max_timesteps=40, is_eval=True, mix=None, poll_
     Returns dict(action_seqs, ref_seqs, success, distances, num_steps, num_interactions) with the
     reference's meanings; distances: for failed get-tasks the teacher's path length from the final
     pose on the ORIGINAL grid (imitation.py:83-91), 0 for successful ones, -1 for other tasks."""
+    from . import _lib
     n = env.n
     dev = env.device
+    max_timesteps = _lib.check_max_timesteps(max_timesteps)
     env.reset()
     env.timer.fill_(max_timesteps)            # the kernel's timer is the trainer's (imitation.py:30,63)
     done = torch.zeros(n, dtype=torch.bool, device=dev)

@@ -148,7 +148,8 @@ class GraphedRollout(object):
     """
 
     def __init__(self, env, policy, max_timesteps=40, greedy=False, with_teacher=True, use_graph=True):
-        self.env, self.policy, self.T = env, policy, int(max_timesteps)
+        from . import _lib
+        self.env, self.policy, self.T = env, policy, _lib.check_max_timesteps(max_timesteps)
         self.greedy, self.with_teacher = greedy, with_teacher
         n, dev = env.n, env.device
         self.feats = torch.zeros((self.T, n, env.n_features), dtype=torch.float32, device=dev)
