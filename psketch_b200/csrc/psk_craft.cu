@@ -1643,7 +1643,8 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
 // per tick at 65,536 envs when a change pushed the kernel to 80 registers).
 __host__ __device__ constexpr int rollout_threads(int ne, int nfw) { return (ne + 31) / 32 * 32 + nfw * 32; }
 template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA>
-__global__ void __launch_bounds__(rollout_threads(NE, NFW), rollout_threads(NE, NFW) <= 128 ? 896 / rollout_threads(NE, NFW) : 1)
+__global__ void __launch_bounds__(rollout_threads(NE, NFW),
+                                  (W * H <= 64 && rollout_threads(NE, NFW) <= 128) ? 896 / rollout_threads(NE, NFW) : 1)
 craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                      uint8_t *__restrict__ agent, const uint8_t *__restrict__ action_in,
                      const uint8_t *__restrict__ scen_grid, const int32_t *__restrict__ scen_idx,
@@ -2148,7 +2149,13 @@ template <int W, int H, int WIN> struct Config {
                        const uint8_t *action_in, float *features_out, int feat_ring,
                        uint8_t *expert_out, uint8_t *done, uint8_t *success,
                        unsigned long long *stats, int32_t *err, cudaStream_t st) {
-        if constexpr (!BITBOARD || WIN != 3) {
+        if constexpr (!BITBOARD) {
+            return PSK_ERR_UNSUPPORTED;
+        } else if constexpr (WIN != 3) {
+            // craft_large (10 x 10, window 5, 128-bit boards, 1,076 features): the multi-tick kernel was
+            // built and measured — 185 registers, 3 CTAs per SM, 73.6 us per tick at 65,536 envs against
+            // 56.0 us for chained single ticks (profiles/README.md) — so psk_craft_rollout loops over
+            // craft_tick_kernel launches for this geometry
             return PSK_ERR_UNSUPPORTED;
         } else {
             // CTA shape and store path (sweeps in profiles/README.md): 32 env threads + 2 feature warps
@@ -2389,6 +2396,7 @@ int psk_craft_rollout(const psk_craft_tables *t, psk_craft_state s, psk_craft_ep
     if (Medium::matches(t))
         rc = Medium::rollout(t, s, ep, ticks, action_in, features_out, feat_ring, expert_out, done_out,
                              success_out, stats, err_flags, st);
+
     if (rc != PSK_ERR_UNSUPPORTED) return rc;
     // other geometries: one fused / pipelined tick per iteration, same outputs
     const int nfeat = psk_craft_n_features(t);

@@ -955,3 +955,33 @@ def test_host_state_upload_download_round_trip(splits, medium_tables, medium_ora
         assert np.array_equal(env.expert, ref["expert"]) and np.array_equal(env.done, ref["done"])
     assert np.array_equal(env.agent[:, 24:26].astype(np.int32), orc.pos)
     env.close()
+
+
+@pytest.mark.parametrize("tma", [0, 1])
+def test_rollout_kernel_craft_large_vs_oracle(tma, large_tables, large_oracle, large_states):
+    """craft_large (configs/worlds/craft_large.yaml: 10x10, window 5, 1,076 features, 128-bit boards)
+    through psk_craft_rollout (for this geometry: chained craft_tick_kernel launches), both store paths:
+    every tick's teacher action / done / success / features and the final state against the oracle."""
+    from psketch_b200 import _lib
+    from psketch_b200.vec import VecCraft
+    n, T = 1500, 11
+    rng = np.random.RandomState(4)
+    task = rng.choice([13, 14, 15, 19, 20, 21, 22, 23, 24, 25, 26], size=n).astype(np.int32)
+    grid, pos = large_states["grid"][:n], large_states["pos"][:n].astype(np.int32)
+    try:
+        _lib.set_tuning(tick_tma=tma)
+        env = VecCraft.from_instances(large_tables, grid, np.arange(n), pos, task, max_timesteps=19)
+        orc = _OracleTicks(large_oracle, grid, np.arange(n), pos, task, max_timesteps=19)
+        ring = torch.empty((T, n, large_tables.n_features), dtype=torch.float32, device=env.device)
+        for rep in range(3):
+            out = env.rollout(T, features_out=ring)
+            for t in range(T):
+                ref = orc.tick()
+                assert np.array_equal(_np(out["expert"][t]), ref["expert"]), (rep, t)
+                assert np.array_equal(_np(out["done"][t]), ref["done"]), (rep, t)
+                assert np.array_equal(_np(out["success"][t]), ref["success"]), (rep, t)
+                assert np.array_equal(_np(ring[t]), ref["features"]), (rep, t)
+        orc.assert_state_equals(env)
+        env.check_errors()
+    finally:
+        _lib.set_tuning(tick_tma=-1)
