@@ -574,6 +574,10 @@ def run_ours(args):
         except Exception as ex:  # noqa: BLE001
             line["student_in_loop"] = {"error": repr(ex)}
         try:
+            line["stress_grids"] = stress_record(torch, dev)
+        except Exception as ex:  # noqa: BLE001
+            line["stress_grids"] = {"error": repr(ex)}
+        try:
             line["light_world"] = light_record(torch, dev, peak)
         except Exception as ex:  # noqa: BLE001
             line["light_world"] = {"error": repr(ex)}
@@ -693,6 +697,34 @@ def student_in_loop_record(torch, tables, dev, n=16384):
                    "and idles for the rest of the 40), env_timesteps = every env x 40; training runs: "
                    "profiles/bench_runs/r2_dagger_*.json",
             "reference": "experiments/dagger_no_mix/run.log: ~1.5e3 interactions/s including learning"}
+
+
+def stress_record(torch, dev, n=65536):
+    """Secondary record (BASELINE configs[4]): the enlarged-grid BFS stress test — the row-per-lane
+    warp-cooperative teacher (one warp per env), features and step on 16x16 / 32x32 / 64x64 grids
+    with 20 % obstacles (tests/test_stress_gpu.py checks these kernels against the oracle)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_stress_gpu import _random_states, _tables
+    from psketch_b200.vec import VecCraft
+    rec = {"envs": n}
+    for size in (16, 32, 64):
+        tables = _tables(size)
+        m = min(n, 4096 if size < 64 else 512)
+        grid, inv, pos, dirs, task = _random_states(tables, m, seed=size, wall_frac=0.2)
+        rep = (n + m - 1) // m
+        tile = lambda a: np.concatenate([a] * rep)[:n]
+        env = VecCraft.from_states(tables, tile(grid), tile(inv), tile(pos), tile(dirs), task=tile(task), device=dev)
+        act = env.expert()
+        feats = env.features()
+        snap = env.snapshot()
+        dt_e = time_kernel(lambda: env.expert(out=act), torch, inner=5, reps=6)
+        dt_f = time_kernel(lambda: env.features(out=feats), torch, inner=5, reps=6)
+        dt_s = time_kernel(lambda: env.step(act), torch, inner=5, reps=6)
+        env.restore(snap)
+        rec["%dx%d" % (size, size)] = {"expert_us": dt_e * 1e6, "expert_env_per_s": n / dt_e,
+                                        "features_us": dt_f * 1e6, "step_us": dt_s * 1e6}
+        del env, feats
+    return rec
 
 
 def measure_config3(torch, dist, pdist, tables, rank, world, dev, args):
