@@ -105,7 +105,7 @@ def cpu_python_port(budget_s=20.0, procs=None, rounds=1, warm=0):
     procs = procs or os.cpu_count() or 1
     sp = load_workload(1, "dev")["raw"]
     # ~4.8k env-steps/s/core and ~10 env-steps per instance
-    n_inst = int(min(2200 * 8, max(procs * 20, budget_s * 450 * procs)))
+    n_inst = int(min(2200 * 32, max(procs * 20, budget_s * 450 * procs)))     # ~5 k env-steps/s/core, ~10 per instance
     idx = np.arange(n_inst) % 2200
     runner = port.ParallelRunner("craft_medium", sp["dev_grids"], procs)
     out = []
