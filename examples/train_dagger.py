@@ -53,8 +53,10 @@ class Batches(object):
         self.d_task = torch.from_numpy(split["inst_task"].astype(np.uint8)).to(device)
 
     def next(self):
-        if self.order is None or self.cursor + self.batch > self.n:
-            self.order, self.cursor = self.rng.permutation(self.n), 0
+        if self.order is None or self.cursor + self.batch > len(self.order):
+            passes = max(1, -(-self.batch // self.n))          # batches larger than the split: several passes
+            self.order = np.concatenate([self.rng.permutation(self.n) for _ in range(passes)])
+            self.cursor = 0
         rows = torch.from_numpy(self.order[self.cursor:self.cursor + self.batch]).to(self.env.device)
         self.cursor += self.batch
         env = self.env
@@ -81,6 +83,9 @@ def evaluate(policy, tables, split, device, cache={}):
 
 def train(args):
     device = torch.device("cuda:0")
+    if getattr(args, "tf32", False):        # opt-in: TF32 tensor cores for the student's GEMMs (the
+        torch.backends.cuda.matmul.allow_tf32 = True   # reference's student is plain fp32)
+        torch.backends.cudnn.allow_tf32 = True
     torch.manual_seed(args.seed)
     tables = CraftTables()
     train_split, dev_split = load_split("train"), load_split("dev")
@@ -152,6 +157,7 @@ def main():
     ap.add_argument("--log-every", type=int, default=50)
     ap.add_argument("--eval-every", type=int, default=250)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--tf32", action="store_true", help="TF32 tensor cores for the student's matmuls")
     ap.add_argument("--save", default=None, help="write a reference-format checkpoint (students/imitation.py:100-104)")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
