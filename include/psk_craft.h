@@ -2,7 +2,7 @@
  * psk_craft.h — C ABI of the B200-native batched Craft environment + BFS teacher.
  *
  * The reference (khanhptnk/psketch) has no FFI: its boundary for this path is the duck-typed
- * Python object API of worlds/craft.py and teachers/*.py.  Every entry point below replaces
+ * Python object API of worlds/craft.py and the teachers/ package.  Every entry point below replaces
  * one reference method, applied to a whole batch of environments whose state lives in HBM as
  * structure-of-arrays tensors; psketch_b200/worlds/craft.py and psketch_b200/teachers/ are the
  * Python-side mirror that binds them (ctypes) and INTEGRATION.md shows the binding a reference

@@ -111,3 +111,40 @@ def test_rollout_kernel_register_budget(lib_path):
         assert regs, "rollout kernel %s not found in the library" % shape
         # registers are allocated per warp in units of 8 per thread
         assert ctas * threads * ((max(regs) + 7) // 8 * 8) <= 65536, (shape, regs)
+
+
+def _build_c_host(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_rollout")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-O2", "-I", os.path.join(root, "include"),
+                           "-I", os.path.join(cuda, "include"), os.path.join(root, "examples", "host_rollout.c"),
+                           "-L", os.path.join(root, "psketch_b200"), "-lpsk_b200",
+                           "-L", os.path.join(cuda, "lib64"), "-lcudart",
+                           "-Wl,-rpath," + os.path.join(root, "psketch_b200"), "-o", exe])
+    return exe
+
+
+def test_headers_are_plain_c_and_a_c_host_links(tmp_path):
+    """The boundary is a C ABI: both headers compile as strict C99 (-Wall -Werror), and a host written
+    in plain C (examples/host_rollout.c: no Python, no torch) builds and links against the library."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "inc.c"
+    src.write_text('#include "psk_craft.h"\n#include "psk_light.h"\nint main(void) { return PSK_OK; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only",
+                           "-I", os.path.join(root, "include"), str(src)])
+    assert os.path.exists(_build_c_host(tmp_path))
+
+
+@pytest.mark.gpu
+def test_c_host_runs_rollouts(tmp_path):
+    """The plain-C host on the GPU: teacher-driven rollouts of get[wood] on its hand-built scenario.
+    The teacher's plan is RIGHT, RIGHT, USE, STOP (4 ticks per episode), so 24 ticks of 4,096 envs
+    are 24,576 episodes, all successful."""
+    import subprocess
+    out = subprocess.check_output([_build_c_host(tmp_path), "4096", "24"], text=True)
+    assert "sm_100a" in out
+    assert "episodes=24576 successes=24576 env_steps=98304 err=0" in out, out
+    assert out.strip().endswith("teacher: 3 3 4 5 3 3 4 5"), out
