@@ -789,9 +789,10 @@ def measure_config3(torch, dist, pdist, tables, rank, world, dev, args):
 
 def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
     """The same tick through the reference-facing C ABI with HOST buffers, copies inside the timed
-    region, MAX over ranks.  Three forms, all checked against the step counter:
-      resident_f32 (headline)  psk_craft_host_tick_resident: environments stay in HBM; per step the
-                               f32[n,404] frame + teacher actions + done/success come down
+    region, MAX over ranks.  Four forms, all checked against the step counter:
+      host_in_loop_f32 (headline)  psk_craft_host_tick_resident, step-then-observe: the host's actions
+                               go up every step, the f32[n,404] frame + teacher actions + flags come down
+      resident_f32             the same without an action upload (teacher-driven inside the kernel)
       roundtrip_f32            psk_craft_host_tick: additionally the states go up and come back
       resident_u8              the compact u8[n,404] frame instead of f32 (opt-in format)
     plus pcie_ceiling: a plain pinned D2H copy of the f32 frame's bytes, all ranks concurrently."""
@@ -829,6 +830,21 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
         assert int(env.stats[2]) - before == (steps + 3) * n
         variants[name] = {"value": n * steps * world / wall, "unit": UNIT,
                           "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
+    # host in the loop: the host's policy (here: follow the teacher action it was handed) picks the
+    # actions, they go UP with every call, the step is applied, the new observation comes DOWN
+    env.reset_resident()
+    env.tick_resident(features="f32", advance_first=True)          # first observation, no step yet
+    acts = env.expert.copy()
+
+    def host_loop_step():
+        env.tick_resident(actions=acts, features="f32", advance_first=True)
+        acts[:] = env.expert                                        # the host "policy": np copy of n bytes
+
+    before = int(env.stats[2])
+    wall = timed(host_loop_step, steps)
+    assert int(env.stats[2]) - before == (steps + 3) * n
+    variants["host_in_loop_f32"] = {"value": n * steps * world / wall, "unit": UNIT,
+                                    "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
     # PCIe ceiling for the f32 frame: the same bytes, pinned, nothing else
     frame = torch.empty((n, env.n_features), dtype=torch.float32, device=dev)
     host = torch.empty((n, env.n_features), dtype=torch.float32, pin_memory=True)
@@ -836,12 +852,14 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
     gbs = frame.numel() * 4 * steps / wall / 1e9
     ceiling = {"d2h_GBps_per_gpu": gbs, "env_steps_per_s": n * steps * world / wall,
                "how": "pinned cudaMemcpy D2H of one f32[%d,%d] frame per step, all %d ranks at once" % (n, env.n_features, world)}
-    head = dict(variants["resident_f32"])
+    head = dict(variants["host_in_loop_f32"])
     head.update({"steps": steps, "pcie_ceiling": ceiling,
                  "frac_of_pcie_ceiling": head["value"] / ceiling["env_steps_per_s"],
-                 "how": "psk_craft_host_tick_resident (C ABI, pinned host numpy buffers): per step fused tick in "
-                        "%d-env chunks over 3 streams, D2H f32 features + teacher actions + done/success; the "
-                        "environments stay in HBM" % args.e2e_chunk})
+                 "how": "psk_craft_host_tick_resident (C ABI, pinned host numpy buffers), host in the loop: per step "
+                        "H2D the actions the host chose (u8[n]), fused step-then-observe tick in %d-env chunks over "
+                        "3 streams, D2H f32 features + teacher actions + done/success of the new states; the "
+                        "environments stay in HBM (e2e_variants: without the action upload, with the state round "
+                        "trip of round 1, with the u8 frame)" % args.e2e_chunk})
     env.close()
     return {"headline": head, "variants": variants}
 

@@ -255,7 +255,9 @@ int psk_craft_host_tick(psk_craft_host_ctx *ctx, uint8_t *host_grid, uint8_t *ho
  * teachers/primitive_language.py:60-66).  psk_craft_host_tick_resident = psk_craft_host_tick
  * without the state copies: H2D host_action_in u8[n] (NULL = follow the teacher), D2H the feature
  * frame in `feature_format` (host_features f32[n][nf] or u8[n][nf], NULL/NONE = no features), the
- * teacher actions and flags. */
+ * teacher actions and flags.  advance_first != 0: "step, then observe" (PSK_TICK_ADVANCE_FIRST) — the
+ * host-in-the-loop form: the actions the host chose from the previous call's features go up, the
+ * step is applied, and the features / teacher actions of the NEW states come down. */
 #define PSK_FEATURES_NONE 0
 #define PSK_FEATURES_F32 1
 #define PSK_FEATURES_U8 2
@@ -265,7 +267,7 @@ int psk_craft_host_put_state(psk_craft_host_ctx *ctx, const uint8_t *host_grid,
 int psk_craft_host_get_state(psk_craft_host_ctx *ctx, uint8_t *host_grid, uint8_t *host_agent,
                              int64_t n);
 int psk_craft_host_tick_resident(psk_craft_host_ctx *ctx, const uint8_t *host_action_in,
-                                 void *host_features, int32_t feature_format,
+                                 void *host_features, int32_t feature_format, int32_t advance_first,
                                  uint8_t *host_expert, uint8_t *host_done, uint8_t *host_success,
                                  int64_t n, unsigned long long *host_stats, int32_t *host_err_flags);
 

@@ -106,7 +106,7 @@ def load():
     lib.psk_craft_host_reset.argtypes = [vp, i64]
     lib.psk_craft_host_put_state.argtypes = [vp, vp, vp, i64]
     lib.psk_craft_host_get_state.argtypes = [vp, vp, vp, i64]
-    lib.psk_craft_host_tick_resident.argtypes = [vp, vp, vp, i32, vp, vp, vp, i64, vp, vp]
+    lib.psk_craft_host_tick_resident.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i64, vp, vp]
     lib.psk_set_tuning.argtypes = [ctypes.c_char_p, i32]
     lib.psk_get_tuning.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32)]
     for name in CRAFT_EXPORTS[1:]:

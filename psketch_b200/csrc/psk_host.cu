@@ -256,7 +256,7 @@ int psk_craft_host_get_state(psk_craft_host_ctx *c, uint8_t *host_grid, uint8_t 
 }
 
 int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_action_in,
-                                 void *host_features, int32_t feature_format,
+                                 void *host_features, int32_t feature_format, int32_t advance_first,
                                  uint8_t *host_expert, uint8_t *host_done, uint8_t *host_success,
                                  int64_t n, unsigned long long *host_stats, int32_t *host_err_flags) {
     if (!c || !c->resident_ready || !host_expert || n < 0 || n > c->n_eps) return PSK_ERR_BADARG;
@@ -282,17 +282,23 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
         psk_craft_episodes ep = {c->d_scen_grid, c->d_scen_idx + off, c->d_init_agent + off * PSK_AGENT_BYTES};
         const uint8_t *act = host_action_in ? c->r_action + off : nullptr;
         int rc;
+        const int mode = advance_first ? PSK_TICK_ADVANCE_FIRST : PSK_TICK_FUSED;
         if (feature_format == PSK_FEATURES_U8) {
-            // compact frame: features of the pre-step state as bytes, then teacher + advance
-            rc = psk_craft_features_u8(&c->tables, state, reinterpret_cast<uint8_t *>(c->d_feat[s]), st);
-            if (rc) return rc;
+            // compact frame: the feature kernel writes bytes; it runs on the state the features
+            // describe — before the tick in observe-then-step order, after it in step-then-observe
+            if (!advance_first) {
+                rc = psk_craft_features_u8(&c->tables, state, reinterpret_cast<uint8_t *>(c->d_feat[s]), st);
+                if (rc) return rc;
+            }
             rc = psk_craft_tick(&c->tables, state, ep, act, nullptr, c->r_expert + off, c->r_done + off,
-                                c->r_success + off, c->d_stats, c->d_err, 1, st);
+                                c->r_success + off, c->d_stats, c->d_err, mode, st);
+            if (!rc && advance_first)
+                rc = psk_craft_features_u8(&c->tables, state, reinterpret_cast<uint8_t *>(c->d_feat[s]), st);
         } else {
             rc = psk_craft_tick(&c->tables, state, ep, act,
                                 feature_format == PSK_FEATURES_F32 ? c->d_feat[s] : nullptr,
                                 c->r_expert + off, c->r_done + off, c->r_success + off, c->d_stats,
-                                c->d_err, 1, st);
+                                c->d_err, mode, st);
         }
         if (rc) return rc;
         if (feature_format != PSK_FEATURES_NONE)

@@ -146,9 +146,11 @@ class HostCraft(object):
             self._features_u8 = self._pins["features_u8"].array
         return self._features_u8
 
-    def tick_resident(self, actions=None, features="f32"):
+    def tick_resident(self, actions=None, features="f32", advance_first=False):
         """psk_craft_host_tick_resident: only actions go up; features (``"f32"`` -> self.features,
-        ``"u8"`` -> self.features_u8, None), teacher actions and flags come down."""
+        ``"u8"`` -> self.features_u8, None), teacher actions and flags come down.
+        ``advance_first``: step with ``actions`` (None = no step), THEN observe — the order of a host
+        policy in the loop: ``a = policy(env.features); env.tick_resident(a, advance_first=True)``."""
         if not self.resident:
             self.upload()
         if actions is not None:
@@ -157,7 +159,7 @@ class HostCraft(object):
         buf = self.features if features == "f32" else (self.features_u8 if features == "u8" else None)
         rc = self.lib.psk_craft_host_tick_resident(
             self.ctx, _np_ptr(self.action) if actions is not None else None, _np_ptr(buf), fmt,
-            _np_ptr(self.expert), _np_ptr(self.done), _np_ptr(self.success), self.n,
+            1 if advance_first else 0, _np_ptr(self.expert), _np_ptr(self.done), _np_ptr(self.success), self.n,
             _np_ptr(self.stats), _np_ptr(self.err))
         _lib.check(rc, "psk_craft_host_tick_resident")
         self.last_h2d = self.n if actions is not None else 0

@@ -985,3 +985,39 @@ def test_rollout_kernel_craft_large_vs_oracle(tma, large_tables, large_oracle, l
         env.check_errors()
     finally:
         _lib.set_tuning(tick_tma=-1)
+
+
+@pytest.mark.parametrize("features", ["f32", "u8"])
+def test_host_in_the_loop_resident_tick(features, splits, medium_tables, medium_oracle):
+    """psk_craft_host_tick_resident in step-then-observe order: the host picks actions from what came
+    down (here: random, or the teacher action it was handed), sends them up, and receives the features /
+    teacher actions of the NEW states plus the done / success flags of the step."""
+    from psketch_b200.host import HostCraft
+    n = 3001
+    rng = np.random.RandomState(12)
+    idx = rng.randint(0, 2200, size=n)
+    args = (splits["dev_grids"], splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
+            splits["dev_inst_task"][idx])
+    env = HostCraft(medium_tables, *args, max_timesteps=14, chunk_envs=1024)
+    env.reset_resident()
+    orc = _OracleTicks(medium_oracle, *args, max_timesteps=14)
+    o = medium_oracle
+
+    def check_observation(t):
+        want_e, _, _ = o.expert(orc.grid, orc.inv, orc.pos, orc.dir, orc.task)
+        want_f = o.features(orc.grid, orc.inv, orc.pos, orc.dir)
+        assert np.array_equal(env.expert.astype(np.int32), want_e), t
+        got_f = env.features if features == "f32" else env.features_u8.astype(np.float32)
+        assert np.array_equal(got_f, want_f), t
+
+    env.tick_resident(features=features, advance_first=True)      # first observation, no step
+    check_observation(-1)
+    assert not env.done.any()
+    for t in range(35):
+        a = env.expert.copy() if t % 2 else rng.choice(6, size=n, p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8)
+        env.tick_resident(actions=a, features=features, advance_first=True)
+        ref = orc.tick(a, want_features=False)
+        assert np.array_equal(env.done, ref["done"]) and np.array_equal(env.success, ref["success"]), t
+        check_observation(t)
+    assert tuple(int(x) for x in env.stats[:3]) == tuple(orc.stats)
+    env.close()
