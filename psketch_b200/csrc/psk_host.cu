@@ -31,8 +31,9 @@ struct psk_craft_host_ctx {
     uint8_t *d_scen_grid, *d_init_agent;
     int32_t *d_scen_idx;
     int64_t n_scen, n_eps;
-    unsigned long long *d_stats;
-    int32_t *d_err;
+    unsigned long long *d_stats;   // d_stats[0..3] and d_err live in ONE 64-byte allocation (d_stats) so that
+    int32_t *d_err;                // both come down with a single copy into the pinned mailbox below
+    unsigned long long *h_mail;    // pinned, 64 bytes: stats u64[4] | err i32
     // resident mode (psk_craft_host_tick_resident): the working state and the per-env byte outputs
     // of the whole batch stay on the device; allocated on first use
     uint8_t *r_grid, *r_agent, *r_action, *r_expert, *r_done, *r_success;
@@ -82,10 +83,10 @@ static int host_ctx_alloc(psk_craft_host_ctx *c) {
         CK(cudaMalloc(&c->d_success[i], (size_t)c->chunk));
         CK(cudaMalloc(&c->d_feat[i], (size_t)c->chunk * c->nf * sizeof(float)));
     }
-    CK(cudaMalloc(&c->d_stats, 4 * sizeof(unsigned long long)));
-    CK(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
-    CK(cudaMalloc(&c->d_err, sizeof(int32_t)));
-    CK(cudaMemset(c->d_err, 0, sizeof(int32_t)));
+    CK(cudaMalloc(&c->d_stats, 64));
+    CK(cudaMemset(c->d_stats, 0, 64));
+    c->d_err = reinterpret_cast<int32_t *>(c->d_stats + 4);
+    CK(cudaHostAlloc(reinterpret_cast<void **>(&c->h_mail), 64, cudaHostAllocDefault));
     return PSK_OK;
 }
 
@@ -125,7 +126,8 @@ void psk_craft_host_destroy(psk_craft_host_ctx *c) {
         if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     }
     cudaFree(c->d_scen_grid); cudaFree(c->d_init_agent); cudaFree(c->d_scen_idx);
-    cudaFree(c->d_stats); cudaFree(c->d_err);
+    cudaFree(c->d_stats);
+    if (c->h_mail) cudaFreeHost(c->h_mail);
     cudaFree(c->r_grid); cudaFree(c->r_agent); cudaFree(c->r_action);
     cudaFree(c->r_expert); cudaFree(c->r_done); cudaFree(c->r_success);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
@@ -313,12 +315,14 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
     CK(cudaMemcpyAsync(host_expert, c->r_expert, (size_t)n, cudaMemcpyDeviceToHost, s0));
     if (host_done) CK(cudaMemcpyAsync(host_done, c->r_done, (size_t)n, cudaMemcpyDeviceToHost, s0));
     if (host_success) CK(cudaMemcpyAsync(host_success, c->r_success, (size_t)n, cudaMemcpyDeviceToHost, s0));
-    if (host_stats)
-        CK(cudaMemcpyAsync(host_stats, c->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s0));
-    if (host_err_flags)
-        CK(cudaMemcpyAsync(host_err_flags, c->d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
+    if (host_stats || host_err_flags)       // one 40-byte copy into pinned memory (pageable targets would stage)
+        CK(cudaMemcpyAsync(c->h_mail, c->d_stats, 40, cudaMemcpyDeviceToHost, s0));
     for (int i = 0; i < PSK_HOST_STREAMS; i++) CK(cudaStreamSynchronize(c->streams[i]));
-    if (host_err_flags && *host_err_flags) CK(cudaMemset(c->d_err, 0, sizeof(int32_t)));
+    if (host_stats) memcpy(host_stats, c->h_mail, 4 * sizeof(unsigned long long));
+    if (host_err_flags) {
+        memcpy(host_err_flags, c->h_mail + 4, sizeof(int32_t));
+        if (*host_err_flags) CK(cudaMemset(c->d_err, 0, sizeof(int32_t)));
+    }
     return PSK_OK;
 }
 
