@@ -784,6 +784,187 @@ craft_expert_rows_kernel(const psk_craft_tables *__restrict__ T, const uint8_t *
     if (flags && err_flags && lane == 0) atomicOr(err_flags, (int)flags);
 }
 
+// Grids up to 16 rows: TWO envs per warp.  Lanes 0-15 hold the rows of one env, lanes 16-31 those of
+// another (row x in sub-lane x, one 32-bit word per row); horizontal moves are width-16 shuffles,
+// emptiness tests are the half's 16 bits of a ballot.  The two halves usually need different numbers
+// of flood levels, so both floods run in lock-step under a warp vote (as in bfs_first_action) and
+// every shuffle / ballot is executed by all 32 lanes.  Same answers as bfs_rows (tests/test_stress_gpu.py).
+template <int W, int H> struct HalfRows {
+    static_assert(W <= 16 && H <= 32, "two envs per warp: up to 16 rows of up to 32 cells");
+    static constexpr unsigned FULL = 0xffffffffu;
+    static __device__ __forceinline__ uint32_t hmask() { return H == 32 ? ~0u : ((1u << (H % 32)) - 1u); }
+    template <int A> static __device__ __forceinline__ uint32_t shift(uint32_t r, int sub) {
+        uint32_t b;
+        if (A == 0) b = r >> 1;                                   // DOWN  (0,-1)
+        else if (A == 1) b = (r << 1) & hmask();                  // UP    (0,+1)
+        else if (A == 2) {                                        // LEFT  (-1,0): row x <- row x+1
+            const uint32_t nxt = __shfl_down_sync(FULL, r, 1, 16);
+            b = sub < 15 ? nxt : 0u;
+        } else {                                                  // RIGHT (+1,0): row x <- row x-1
+            const uint32_t prv = __shfl_up_sync(FULL, r, 1, 16);
+            b = sub > 0 ? prv : 0u;
+        }
+        return sub < W ? b : 0u;
+    }
+    template <int A> static __device__ __forceinline__ uint32_t unshift(uint32_t r, int sub) {
+        return shift<(A ^ 1)>(r, sub);
+    }
+    static __device__ __forceinline__ uint32_t spread(uint32_t r, int sub) {
+        return shift<0>(r, sub) | shift<1>(r, sub) | shift<2>(r, sub) | shift<3>(r, sub);
+    }
+    static __device__ __forceinline__ uint32_t half_ballot(bool p, int lane) {
+        return (__ballot_sync(FULL, p) >> (lane & 16)) & 0xFFFFu;
+    }
+    static __device__ __forceinline__ bool any(uint32_t r, int lane) { return half_ballot(r != 0, lane) != 0; }
+    static __device__ __forceinline__ uint32_t row(uint32_t r, int x) { return __shfl_sync(FULL, r, x & 15, 16); }
+};
+
+// returns the path length (-1 unreachable, 0 already facing); first / (gx, gy) as bfs_rows
+template <int W, int H>
+__device__ __forceinline__ int bfs_half_rows(bool need, uint32_t occ, uint32_t goal, int px, int py,
+                                             int d0, int lane, int &first, int &gx, int &gy) {
+    using HR = HalfRows<W, H>;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int sub = lane & 15;
+    const uint32_t freeb = sub < W ? (~occ & HR::hmask()) : 0u;
+    const uint32_t root = sub == px ? (1u << py) : 0u;
+    first = -1;
+    gx = gy = -1;
+    bool face0 = false;
+    {
+        const int fx = px + dx_of(d0), fy = py + dy_of(d0);
+        const bool in = fx >= 0 && fy >= 0 && fx < W && fy < H;
+        const uint32_t grow = HR::row(goal, in ? fx : 0);
+        if (need && in && ((grow >> (fy & 31)) & 1)) {
+            face0 = true;
+            gx = fx;
+            gy = fy;
+        }
+    }
+    const uint32_t T0 = HR::template unshift<0>(goal, sub), T1 = HR::template unshift<1>(goal, sub),
+                   T2 = HR::template unshift<2>(goal, sub), T3 = HR::template unshift<3>(goal, sub);
+    const uint32_t src_all = T0 | T1 | T2 | T3 | HR::template unshift<0>(freeb & T0, sub) |
+                             HR::template unshift<1>(freeb & T1, sub) |
+                             HR::template unshift<2>(freeb & T2, sub) |
+                             HR::template unshift<3>(freeb & T3, sub);
+    const bool has_goal = HR::any(goal, lane);
+    const bool run = need && !face0 && has_goal;
+    uint32_t VF = root;
+    int k = 0;
+    bool h;
+    while (true) {
+        h = HR::any(VF & src_all, lane);
+        const uint32_t nv = VF | (HR::spread(VF, sub) & freeb);
+        const bool changed = HR::any(nv ^ VF, lane);            // unchanged: queue drained (base.py:87)
+        const bool go = run && !h && changed;
+        if (!__any_sync(FULL, go)) break;
+        if (go) {
+            VF = nv;
+            k++;
+        }
+    }
+    const bool reached = run && h;
+    const uint32_t hit =
+        (HR::template shift<0>(VF & T0, sub) | HR::template shift<1>(VF & T1, sub) |
+         HR::template shift<2>(VF & T2, sub) | HR::template shift<3>(VF & T3, sub) |
+         HR::template shift<0>(HR::template shift<0>(VF, sub) & freeb & T0, sub) |
+         HR::template shift<1>(HR::template shift<1>(VF, sub) & freeb & T1, sub) |
+         HR::template shift<2>(HR::template shift<2>(VF, sub) & freeb & T2, sub) |
+         HR::template shift<3>(HR::template shift<3>(VF, sub) & freeb & T3, sub)) & goal;
+    // lowest cell of `hit` in x-major order (np.nonzero order)
+    const uint32_t hm = HR::half_ballot(hit != 0, lane);
+    const int hx = hm ? __ffs(hm) - 1 : 0;
+    const uint32_t hrow = HR::row(hit, hx);
+    const int hy = hrow ? __ffs(hrow) - 1 : 0;
+    const uint32_t g = (sub == hx) ? (1u << hy) : 0u;
+    const uint32_t g0 = HR::template unshift<0>(g, sub), g1 = HR::template unshift<1>(g, sub),
+                   g2 = HR::template unshift<2>(g, sub), g3 = HR::template unshift<3>(g, sub);
+    const uint32_t s0 = g0 | HR::template unshift<0>(freeb & g0, sub), s1 = g1 | HR::template unshift<1>(freeb & g1, sub),
+                   s2 = g2 | HR::template unshift<2>(freeb & g2, sub), s3 = g3 | HR::template unshift<3>(freeb & g3, sub);
+    const bool r0 = HR::any(root & s0, lane), r1 = HR::any(root & s1, lane), r2 = HR::any(root & s2, lane);
+    uint32_t VB = (s0 | s1 | s2 | s3) & VF;
+    const int kmax = __reduce_max_sync(FULL, reached ? k : 0);
+    for (int j = 1; j < kmax; j++) {
+        const uint32_t nb = VB | (HR::spread(VB, sub) & freeb);
+        if (j < k) VB = nb;
+    }
+    const uint32_t ok = VB & freeb;
+    const bool n0 = HR::any(HR::template shift<0>(root, sub) & ok, lane),
+               n1 = HR::any(HR::template shift<1>(root, sub) & ok, lane),
+               n2 = HR::any(HR::template shift<2>(root, sub) & ok, lane);
+    if (face0) return 0;
+    if (!reached) return -1;
+    gx = hx;
+    gy = hy;
+    if (k == 0) {
+        first = r0 ? 0 : r1 ? 1 : r2 ? 2 : 3;
+        return 1;
+    }
+    first = n0 ? 0 : n1 ? 1 : n2 ? 2 : 3;
+    return k + 1;
+}
+
+template <int W, int H>
+__global__ void __launch_bounds__(128)
+craft_expert_half_rows_kernel(const psk_craft_tables *__restrict__ T, const uint8_t *__restrict__ grid,
+                              const uint8_t *__restrict__ agent, const uint8_t *__restrict__ task,
+                              uint8_t *__restrict__ action, int16_t *__restrict__ dist_out,
+                              int32_t *err_flags, int64_t n, int cell_stride) {
+    __shared__ SharedTables st;
+    stage_tables(st, T);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int sub = lane & 15, half = lane >> 4;
+    uint32_t flags = 0;
+    const int64_t pairs = (n + 1) / 2;
+    for (int64_t pr = blockIdx.x * (int64_t)wpb + warp; pr < pairs; pr += (int64_t)gridDim.x * wpb) {
+        const bool valid = 2 * pr + half < n;
+        const int64_t e = valid ? 2 * pr + half : n - 1;          // a dead half replays the last env, unsaved
+        const Agent a = load_agent_ro(agent, e);
+        const uint8_t *row = grid + e * cell_stride;
+        const int tk = task ? task[e] : a.task();
+        const int facing = facing_kind<W, H>(a, row);
+        const uint32_t leaf = find_incomplete(st, tk, a, facing);
+        const int kind = (leaf >> 16) & 0x0F;
+        const bool need = leaf && kind == LEAF_GO;
+        const int goal_kind = need ? (leaf >> 8) & 0xFF : 0;
+        uint32_t occ = HalfRows<W, H>::hmask(), goal = 0;         // rows beyond the grid are solid
+        if (sub < W) {
+            occ = goal = 0;
+            const uint8_t *p = row + sub * H;
+            if (H % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < H / 4; i++) {
+                    const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(p + 4 * i));
+                    const uint32_t nz = nonzero_flags(w);
+                    const uint32_t eq = nonzero_flags(w ^ (uint32_t(goal_kind) * 0x01010101u)) ^ 0x80808080u;
+                    occ |= ((nz * 0x00204081u) >> 28) << (4 * i);
+                    goal |= ((eq * 0x00204081u) >> 28) << (4 * i);
+                }
+            } else {
+                for (int y = 0; y < H; y++) {
+                    const int c = p[y];
+                    occ |= uint32_t(c != 0) << y;
+                    goal |= uint32_t(c == goal_kind) << y;
+                }
+            }
+            if (!goal_kind) goal = 0;
+        }
+        int first, gx, gy;
+        const int d = bfs_half_rows<W, H>(need, occ, goal, a.x(), a.y(), a.dir(), lane, first, gx, gy);
+        int act;
+        if (!leaf) act = PSK_ACT_STOP;
+        else if (kind == LEAF_USE) act = PSK_ACT_USE;
+        else if (kind != LEAF_GO) { act = PSK_ACT_INVALID; if (valid) flags |= PSK_FLAG_BAD_LEAF; }
+        else if (d < 0) act = PSK_ACT_STOP;
+        else act = first >= 0 ? first : PSK_ACT_INVALID;
+        if (sub == 0 && valid) {
+            action[e] = (uint8_t)act;
+            if (dist_out) dist_out[e] = (int16_t)(need ? d : -1);
+        }
+    }
+    if (flags && err_flags && sub == 0) atomicOr(err_flags, (int)flags);
+}
+
 template <int W, int H>
 __global__ void __launch_bounds__(128)
 craft_find_closest_rows_kernel(const uint8_t *__restrict__ grid, const uint8_t *__restrict__ agent,
@@ -1987,6 +2168,9 @@ template <int W, int H, int WIN> struct Config {
         PSK_DT(dt);
         if constexpr (BITBOARD)
             craft_expert_kernel<W, H><<<grid_for(s.n, 128, 8), 128, 0, st>>>(
+                dt, s.grid, s.agent, task, action, dist, err, s.n, s.cell_stride);
+        else if constexpr (W <= 16 && H <= 32)      // two envs per warp (half a warp of rows each)
+            craft_expert_half_rows_kernel<W, H><<<grid_for((s.n + 1) / 2, 4, 16), 128, 0, st>>>(
                 dt, s.grid, s.agent, task, action, dist, err, s.n, s.cell_stride);
         else
             craft_expert_rows_kernel<W, H><<<grid_for(s.n, 4, 16), 128, 0, st>>>(
