@@ -91,6 +91,7 @@ class CraftWorld(object):
         self.water_index = self.cookbook.index["water"]
         self.stone_index = self.cookbook.index["stone"]
         self.random = _cfg_get(config, "random")
+        self._scenario_seed = _cfg_get(config, "seed", 123)
         self._device = device
         self._backend = None
         self._pending = []          # states whose transition has not been computed yet
@@ -104,6 +105,36 @@ class CraftWorld(object):
 
     def init_state(self, grid, pos, dir=0):
         return self.make_scenario(grid, pos, dir=dir).init()
+
+    def sample_scenario(self, ingredients=None, make_island=False, make_cave=False):
+        """``make_data.sample_scenario(world, ingredients, config)`` (make_data.py:105-144; the method
+        of the same name in worlds/craft.py:111-166 is dead code inside a string literal): boundary
+        ring, N_PRIMITIVES of every primitive, the workshops and a start cell, each placed so that
+        the free cells stay connected.  Returns ``(grid one-hot float64[W, H, K], init_pos)`` like the
+        reference.  Drawn by the Philox sampler kernel (psk_craft_sample_scenarios), 256 scenarios per
+        launch, handed out one by one; distribution checked against the reference's sampler
+        (tests/test_scenario_gpu.py), not its numpy random stream."""
+        if make_island or make_cave:
+            raise NotImplementedError("the reference's island / cave branch is broken (make_data.py:120) "
+                                      "and never taken")
+        pool = getattr(self, "_scenario_pool", None)
+        if not pool:
+            from .. import data
+            seed = int(getattr(self, "_scenario_seed", 123))
+            offset = int(getattr(self, "_scenario_offset", 0))
+            grid, pos, fails = data.sample_scenarios(self.tables, 256, seed, offset, device=self._device)
+            if fails:
+                raise _lib.PskError("scenario sampler ran out of draws")
+            self._scenario_offset = offset + 256
+            C = self.tables.W * self.tables.H
+            g, p = grid[:, :C].cpu().numpy(), pos.cpu().numpy()
+            pool = self._scenario_pool = [(g[i], tuple(int(v) for v in p[i])) for i in range(len(g))][::-1]
+        cells, init_pos = pool.pop()
+        ids = cells.reshape(self.WIDTH, self.HEIGHT)
+        onehot = np.zeros((self.WIDTH, self.HEIGHT, self.cookbook.n_kinds))
+        xs, ys = np.nonzero(ids)
+        onehot[xs, ys, ids[xs, ys]] = 1
+        return onehot, init_pos
 
     def render(self, state):
         inv = {self.cookbook.index.get(i): int(v) for i, v in enumerate(state.inventory) if v > 0}

@@ -175,3 +175,38 @@ def test_facade_under_the_reference_trainer_protocol(splits, trainer_rollouts):
                             task=world.task_manager.by_id(int(splits["dev_inst_task"][i]))))
         return out
     check_against_fixture(trainer_rollouts, make_batch, world, teacher)
+
+
+def test_world_sample_scenario():
+    """CraftWorld.sample_scenario — make_data.sample_scenario(world, ...) of the reference: every
+    scenario has the boundary ring, 2 of each primitive, the 3 workshops, a free start cell, and all
+    free cells are connected; consecutive calls give different layouts; states start from them."""
+    from psketch_b200.worlds import CraftWorld
+    world = CraftWorld()
+    cb = world.cookbook
+    seen = set()
+    for k in range(300):                               # crosses a pool refill (256 per launch)
+        grid, pos = world.sample_scenario()
+        assert grid.shape == (8, 8, cb.n_kinds) and (grid.sum(axis=2) <= 1).all()
+        ids = grid.argmax(axis=2) * (grid.sum(axis=2) > 0)
+        assert (ids[0, :] == 1).all() and (ids[7, :] == 1).all() and (ids[:, 0] == 1).all() and (ids[:, 7] == 1).all()
+        counts = np.bincount(ids.ravel(), minlength=cb.n_kinds)
+        assert counts[1] == 28 and counts[2] == counts[3] == counts[4] == 1
+        assert counts[cb.index["iron"]] == counts[cb.index["grass"]] == counts[cb.index["wood"]] == 2
+        assert counts.sum() - counts[0] == 37 and ids[pos] == 0
+        free = ids == 0                                # flood fill from the start cell
+        reach = np.zeros_like(free)
+        reach[pos] = True
+        for _ in range(40):
+            grow = reach.copy()
+            grow[1:, :] |= reach[:-1, :]; grow[:-1, :] |= reach[1:, :]
+            grow[:, 1:] |= reach[:, :-1]; grow[:, :-1] |= reach[:, 1:]
+            reach = grow & free
+        assert (reach == free).all()
+        seen.add(ids.tobytes())
+        if k < 3:
+            s = world.init_state(grid, pos)
+            assert s.pos == pos and s.features().shape == (404,)
+    assert len(seen) > 290
+    with pytest.raises(NotImplementedError):
+        world.sample_scenario(make_island=True)
