@@ -73,7 +73,7 @@ def test_medium_entry_points_stay_inside_their_buffers(n, skew, splits, medium_t
     ref = VecCraft.from_instances(tables, grids, env_idx, pos, task)
     nf = ref.n_features
     T, R = 5, 2
-    arena = Arena(256 * 1024 + n * (2 * 96 + 64 + (R + 9) * nf * 4 + 64 * 16), ref.device)
+    arena = Arena(320 * 1024 + n * (2 * 96 + 64 + (R + 11) * nf * 4 + 64 * 24), ref.device)
     env = _carved_env(tables, arena, ref)
 
     # a few teacher ticks first so that inventories / cleared cells occur
@@ -125,6 +125,25 @@ def test_medium_entry_points_stay_inside_their_buffers(n, skew, splits, medium_t
         for k in ("expert", "done", "success", "features"):
             assert _same(a[k], b[k]), (fused, k)
         assert arena.guards_intact(), "tick fused=%s" % fused
+
+    # round-2 entry points: u8 feature frame, step-then-observe tick, block of random actions
+    f8 = env.features_u8(out=arena.carve((n, nf), torch.uint8, skew=skew % 3))
+    assert _same(f8, ref.features_u8()) and _same(f8.float(), ref.features())
+    assert arena.guards_intact(), "features_u8"
+    fo = arena.carve((n, nf), torch.float32)
+    o = dict(expert=arena.carve((n,), torch.uint8, skew=skew % 3),
+             done=arena.carve((n,), torch.uint8, skew=skew % 3),
+             success=arena.carve((n,), torch.uint8, skew=skew % 3))
+    for acts_in in (None, ra):
+        b = env.tick(actions=acts_in, features_out=fo, out=o, advance_first=True)
+        a = ref.tick(actions=acts_in, advance_first=True)
+        for k in ("expert", "done", "success", "features"):
+            assert _same(a[k], b[k]), ("advance_first", k)
+        assert _same(env.grid, ref.grid) and _same(env.agent, ref.agent)
+        assert arena.guards_intact(), "tick advance_first"
+    blk = env.random_actions(t=11, ticks=3, out=arena.carve((3, n), torch.uint8, skew=skew % 3))
+    assert _same(blk, ref.random_actions(t=11, ticks=3))
+    assert arena.guards_intact(), "random_actions block"
 
     # multi-tick rollout with a feature ring (frames are n*nf*4 bytes apart: not 16-byte
     # multiples for odd n, which is the alignment case the vector path has to refuse)
