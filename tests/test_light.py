@@ -238,3 +238,40 @@ def test_light_tick_matches_oracle(light_states):
         assert np.array_equal(got[:, :3], cur) and np.array_equal(got[:, 3], elapsed), t
     s = v.stats.cpu().numpy()
     assert (s[0], s[1], s[2]) == tuple(tot) and tot[1] > 0
+
+
+@pytest.mark.gpu
+def test_light_table_and_tick_stay_inside_their_buffers(light_states):
+    """Canary-arena check (compute-sanitizer is closed on the pool): the teacher table (distances +
+    per-cell maps), the state and every output of psk_light_tick are carved out of a canary-filled
+    arena with guard bands; results equal those of ordinary allocations and the guards stay intact."""
+    import torch
+    from test_bounds_gpu import Arena
+    L = light_states
+    for n in (1, 33, 4099):
+        v, st, scen_idx, state = _vec(L)
+        ref, _, _, _ = _vec(L)
+        sub = np.arange(n) % len(st)
+        for obj in (v, ref):
+            obj.scen_idx = torch.as_tensor(scen_idx[sub].astype(np.int32)).to(obj.device)
+            obj.n = n
+            obj.state = torch.zeros((n, 4), dtype=torch.uint8, device=obj.device)
+            obj.set_state(st[sub])
+        nbytes = v.lib.psk_light_teacher_table_bytes(v.scen.shape[0], v.max_keys)
+        arena = Arena(nbytes + n * (4 + 48 + 3 + 64) + 64 * 1024, v.device)
+        v._table = arena.carve((nbytes // 2,), torch.int16)
+        v.state = arena.carve((n, 4), torch.uint8).copy_(v.state)
+        v.stats = arena.carve((4,), torch.int64).zero_()
+        rc = v.lib.psk_light_teacher_build(v._p(v.scen), v.scen.shape[0], v.max_keys, v._p(v._table), v._stream())
+        assert rc == 0
+        assert torch.equal(v._table, ref.teacher_table()) and arena.guards_intact()
+        out = dict(expert=arena.carve((n,), torch.uint8), done=arena.carve((n,), torch.uint8),
+                   success=arena.carve((n,), torch.uint8))
+        feats = arena.carve((n, 12), torch.float32)
+        for t in range(5):
+            a = ref.tick(max_timesteps=7)
+            b = v.tick(features_out=feats, out=out, max_timesteps=7)
+            for k in ("expert", "done", "success", "features"):
+                assert torch.equal(a[k], b[k]), (n, t, k)
+            assert torch.equal(v.state, ref.state)
+            assert arena.guards_intact(), (n, t)
