@@ -157,6 +157,16 @@ def set_tuning(**knobs):
     return old
 
 
+def raw_stream(torch, device):
+    """cudaStream_t of torch's current stream on ``device`` as a c_void_p — the fast path
+    (torch._C._cuda_getCurrentRawStream, no Stream object) where this torch has it."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    get = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if get is not None:
+        return ctypes.c_void_p(get(idx))
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
 def check_max_timesteps(max_timesteps):
     """The episode timer is one byte of the agent record (include/psk_craft.h: PSK_AG_TIMER); the
     reference's is an unbounded Python int (trainers/imitation.py:30)."""

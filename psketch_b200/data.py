@@ -93,7 +93,7 @@ def save_json(path, packed, tables):
 
 # ------------------------------------------------------------------------------- generation
 def _stream(torch, device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return _lib.raw_stream(torch, device)
 
 
 def default_placement(tables):

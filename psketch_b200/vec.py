@@ -115,7 +115,7 @@ class VecCraft(object):
                                    self.init_agent.data_ptr())
 
     def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return _lib.raw_stream(torch, self.device)
 
     def _u8(self, x):
         if x is None:

@@ -416,7 +416,7 @@ class _Backend(object):
         grid[0, :self.C] = cells
         agent = np.array(agent, np.uint8).reshape(1, _lib.AGENT_BYTES)
         with torch.cuda.device(self.device):
-            stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            stream = _lib.raw_stream(torch, self.device)
             d_grid = torch.from_numpy(grid).to(self.device)
             d_agent = torch.from_numpy(agent).to(self.device)
             d_kind = torch.full((1,), int(kind), dtype=torch.uint8, device=self.device)

@@ -205,7 +205,7 @@ class VecLight(object):
         return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
     def _stream(self):
-        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+        return _lib.raw_stream(self.torch, self.device)
 
     def _u8(self, x):
         if x is None:
