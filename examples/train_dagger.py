@@ -66,7 +66,7 @@ class Batches(object):
         return env, self.d_task[rows]
 
 
-def evaluate(policy, tables, split, device, cache={}):
+def evaluate(policy, tables, split, device, cache={}, traj=None):
     key = id(split)
     if key not in cache:
         env = VecCraft.from_instances(tables, split["grids"], split["inst_env"], split["inst_pos"],
@@ -78,6 +78,10 @@ def evaluate(policy, tables, split, device, cache={}):
         mem = policy.encode(task_tokens(tables, env.task))
     roll.run(mem)
     policy.train()
+    if traj:                             # the reference's <split>.traj (trainers/imitation.py:204-207,228-231)
+        from psketch_b200 import data
+        data.save_eval_info(traj, data.eval_info(split["inst_id"], roll.acts.t().cpu().numpy(),
+                                                 roll.success.cpu().numpy()))
     return float(roll.success.float().mean())
 
 
@@ -144,6 +148,8 @@ def train(args):
                              "20 k iterations of batch 32 (640 k episodes, :280); best dev 84.5 % at ~109 k (:928)")
     if args.save:
         torch.save({"model_state_dict": policy.to_reference_state_dict(), "optim_state_dict": {}}, args.save)
+    if getattr(args, "traj", None):
+        evaluate(policy, tables, dev_split, device, traj=args.traj)
     return log, policy, summary
 
 
@@ -159,6 +165,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--tf32", action="store_true", help="TF32 tensor cores for the student's matmuls")
     ap.add_argument("--save", default=None, help="write a reference-format checkpoint (students/imitation.py:100-104)")
+    ap.add_argument("--traj", default=None, help="write the final dev evaluation as a reference-format .traj file")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
     log, _, summary = train(args)

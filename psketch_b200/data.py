@@ -92,6 +92,30 @@ def save_json(path, packed, tables):
 
 
 # ------------------------------------------------------------------------------- generation
+# ------------------------------------------------------------------------------- .traj files
+def eval_info(instance_ids, action_seqs, success):
+    """The evaluation record the reference's trainers write as ``<split>.traj`` / ``best_dev.traj``
+    (trainers/imitation.py:204-207,228-231): ``{instance id: {"actions": [...], "success": 0/1}}``.
+    ``instance_ids``: ints or ``"instance_<n>"`` strings; ``action_seqs``: u8[N, L] padded with 255
+    (or a list of lists); ``success``: bool[N]."""
+    info = {}
+    for iid, seq, ok in zip(instance_ids, action_seqs, success):
+        key = iid if isinstance(iid, str) else "instance_%d" % int(iid)
+        assert key not in info, key                                  # trainers/imitation.py:201
+        info[key] = {"actions": [int(a) for a in seq if int(a) != 255], "success": int(bool(ok))}
+    return info
+
+
+def save_eval_info(path, info):
+    with open(path, "w") as f:                                       # trainers/imitation.py:228-231
+        json.dump(info, f)
+
+
+def load_eval_info(path):
+    with open(path) as f:
+        return json.load(f)
+
+
 def _stream(torch, device):
     return _lib.raw_stream(torch, device)
 

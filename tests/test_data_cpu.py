@@ -1,5 +1,6 @@
 """Dataset wire format (data/dataset.py:39-67) <-> packed arrays; CPU only."""
 import numpy as np
+import pytest
 
 
 def test_wire_format_reads_reference_goldens(splits, medium_tables):
@@ -71,3 +72,19 @@ def test_dataset_mirror_batches_like_the_reference(splits, medium_tables, tmp_pa
     assert [[it["id"] for it in b] for b in rb] == [[it["id"] for it in b] for b in batches]
     assert all(a["init_pos"] == b["init_pos"] and a["ref_actions"] == b["ref_actions"]
                for a, b in zip(rds.data, ds.data))
+
+
+def test_traj_files_have_the_reference_format(tmp_path):
+    """trainers/imitation.py:204-207,228-231: {instance id: {'actions': [...], 'success': 0/1}}."""
+    import json
+    from psketch_b200 import data
+    acts = np.asarray([[3, 3, 4, 5, 255, 255], [0, 5, 255, 255, 255, 255], [1, 1, 1, 1, 1, 1]], np.uint8)
+    info = data.eval_info([10561, "instance_7", 3], acts, [True, False, True])
+    assert info == {"instance_10561": {"actions": [3, 3, 4, 5], "success": 1},
+                    "instance_7": {"actions": [0, 5], "success": 0},
+                    "instance_3": {"actions": [1, 1, 1, 1, 1, 1], "success": 1}}
+    path = str(tmp_path / "dev.traj")
+    data.save_eval_info(path, info)
+    assert json.load(open(path)) == info == data.load_eval_info(path)
+    with pytest.raises(AssertionError):
+        data.eval_info([1, 1], acts[:2], [True, True])
