@@ -30,6 +30,25 @@ def teacher_rollouts(env, max_len=64):
     return acts[:, :L].cpu().numpy(), length.cpu().numpy(), ok.cpu().numpy()
 
 
+def _distances(env, success, final_agent):
+    """The trainers' ``distances`` metric (trainers/imitation.py:83-91): for get-tasks that failed, the
+    teacher's path length to the closest resource from the FINAL pose on the ORIGINAL grid (empty
+    inventory), 0 for successful ones, -1 for other tasks.  Leaves the env at its episode starts."""
+    dev = env.device
+    tm = env.tables.task_manager
+    env.reset()                                   # original grids, empty inventories, task ids
+    task = env.task.long()
+    is_get = torch.from_numpy(env.tables.task_is_get.astype(np.bool_)).to(dev)[task]
+    goal_kind = torch.from_numpy(np.asarray(
+        [0] + [env.tables.cookbook.index[tm.by_id(i).goal_arg] or 0 for i in range(1, len(tm.tasks))],
+        np.uint8)).to(dev)[task]
+    env.agent[:, 24:27] = final_agent[:, 24:27]   # x, y, dir of the state the rollout ended in
+    _, length, _ = env.find_closest(goal_kind)
+    env.reset()
+    return torch.where(is_get, torch.where(success, torch.zeros_like(length), length),
+                       torch.full_like(length, -1))
+
+
 def policy_rollouts(env, policy, max_timesteps=40, is_eval=True, mix=None, poll_every=8):
     """trainers/imitation.py:18-101 for every env at once.
 
@@ -85,19 +104,79 @@ def policy_rollouts(env, policy, max_timesteps=40, is_eval=True, mix=None, poll_
     num_inter, num_steps = (int(v) for v in counts.tolist())
     if is_eval:
         num_steps = 0
-    # distances for get-tasks that failed: closest resource from the final pose, original grid
-    tm = env.tables.task_manager
-    is_get = torch.from_numpy(env.tables.task_is_get.astype(np.bool_)).to(dev)[env.task.long()]
-    goal_kind = torch.from_numpy(np.asarray(
-        [0] + [env.tables.cookbook.index[tm.by_id(i).goal_arg] or 0 for i in range(1, len(tm.tasks))],
-        np.uint8)).to(dev)[env.task.long()]
-    # the pose each env was in when it finished, on the original grid
-    env.reset()
-    env.agent[:, 24:27] = final_agent[:, 24:27]
-    _, length, _ = env.find_closest(goal_kind)
-    env.reset()
-    dist = torch.where(is_get, torch.where(success, torch.zeros_like(length), length),
-                       torch.full_like(length, -1))
+    dist = _distances(env, success, final_agent)
     return dict(action_seqs=acts.cpu().numpy(), ref_seqs=refs.cpu().numpy(),
                 success=success.cpu().numpy(), distances=dist.cpu().numpy(),
                 num_steps=num_steps, num_interactions=num_inter, timesteps=t)
+
+
+def language_decode(env, policy, max_timesteps=40, record=True, poll_every=8):
+    """One decoding pass of trainers/primitive_language.py:47-70 (and :93-113) for the whole batch,
+    from the envs' episode starts.  Unlike the imitation trainer, EVERY action of a running env is
+    executed — the terminating one too (STOP is a no-op step, the 40th action still moves,
+    :56-60) — and a finished env keeps its state.  ``policy(features, t) -> u8[N]``.
+    Returns dict(actions u8[N, T] padded with 255, lengths i64[N], agents u8[L + 1, N, 32] (the agent
+    records before every action and after the last one; None unless ``record``), steps int)."""
+    from . import _lib
+    T = _lib.check_max_timesteps(max_timesteps)
+    n, dev = env.n, env.device
+    env.reset()
+    done = torch.zeros(n, dtype=torch.bool, device=dev)
+    acts = torch.full((n, T), 255, dtype=torch.uint8, device=dev)
+    lengths = torch.zeros(n, dtype=torch.int64, device=dev)
+    feats = torch.empty((n, env.n_features), dtype=torch.float32, device=dev)
+    agents = [env.agent.clone()] if record else None
+    steps = torch.zeros((), dtype=torch.int64, device=dev)
+    t = 0
+    while t < T:
+        env.features(out=feats)
+        a = policy(feats, t).to(device=dev, dtype=torch.uint8)
+        live = ~done
+        acts[:, t] = torch.where(live, a, acts[:, t])
+        a_exec = torch.where(live, a, torch.full_like(a, STOP))
+        env.step(a_exec, active=live.to(torch.uint8))
+        steps += live.sum()
+        lengths += live
+        if record:
+            agents.append(env.agent.clone())
+        done |= (a == STOP) | (t == T - 1)
+        t += 1
+        if t % poll_every == 0 and bool(done.all()):
+            break
+    env.check_errors()
+    return dict(actions=acts, lengths=lengths, agents=torch.stack(agents) if record else None,
+                steps=int(steps.item()), timesteps=t)
+
+
+def language_rollouts(env, teacher, policy, ref_actions, max_timesteps=40, is_eval=False,
+                      greedy_policy=None, on_descriptions=None):
+    """trainers/primitive_language.py:16-143 for the whole batch.
+
+    Training: instructions = the teacher's words for the instances' ``ref_actions`` (u8[N, L] padded
+    with 255, ``instruct_batch``); pass 1: ``policy`` (the instructed, exploring student) decodes from
+    the episode starts; the teacher describes what the executed actions did (``describe_batch`` over
+    the recorded agent records — tensor operations, the same words and random-stream consumption as
+    the per-rollout ``describe``); ``on_descriptions(words)`` lets the student receive them; pass 2:
+    ``greedy_policy`` decodes again from the SAME episode starts (:78-113).  Evaluation: one pass of
+    ``policy``.  success / distances come from the states the last pass ended in (:120-133)."""
+    from .teachers.primitive_language import instruct_batch
+    ref = torch.as_tensor(np.asarray(ref_actions, np.uint8))
+    instructions = instruct_batch(ref)                      # word ids, 0 = padding
+    first = language_decode(env, policy, max_timesteps, record=not is_eval)
+    out = dict(instructions=instructions, num_interactions=0 if is_eval else int((ref != 255).sum()),
+               num_steps=0 if is_eval else first["steps"], descriptions=None)
+    last = first
+    if not is_eval:
+        L = int(first["lengths"].max().item())
+        out["descriptions"] = teacher.describe_batch(first["actions"][:, :L].long(), first["agents"][:L + 1],
+                                                     first["lengths"], n_kinds=env.K)
+        if on_descriptions is not None:
+            on_descriptions(out["descriptions"])
+        last = language_decode(env, greedy_policy if greedy_policy is not None else policy,
+                               max_timesteps, record=False)
+    success = env.satisfies() == 1
+    final_agent = env.agent.clone()
+    dist = _distances(env, success, final_agent)
+    out.update(first_pass_actions=first["actions"].cpu().numpy(), action_seqs=last["actions"].cpu().numpy(),
+               success=success.cpu().numpy(), distances=dist.cpu().numpy())
+    return out

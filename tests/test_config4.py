@@ -292,3 +292,48 @@ def test_config4_interactive_replay_on_the_gpu(config4_interactive, splits):
     checked, learned = replay_interactive(world, teacher, splits, fx, order, rng)
     assert checked == len(order)
     assert learned == fx["final_action_map"].tolist()
+
+
+@pytest.mark.gpu
+def test_batched_language_rollouts_reproduce_the_reference_trainer(config4_language, splits, medium_tables):
+    """psketch_b200.rollout.language_rollouts — trainers/primitive_language.py:16-143 for a whole batch
+    as device ops (instruct_batch, two decoding passes with every action executed, describe_batch on
+    the recorded agent records, distances on the original grids) — driven by the recorded actions of
+    the reference's own PrimitiveLanguageTrainer run: instructions, descriptions (incl. the random
+    words drawn while the teacher still learns the student's action ids), final action sequences,
+    success, distances and counters must equal the record."""
+    import torch
+    from psketch_b200.rollout import language_rollouts
+    from psketch_b200.teachers import PrimitiveLanguageTeacher
+    from psketch_b200.vec import VecCraft
+    fx = config4_language
+    rng = np.random.RandomState(123)
+    teacher = PrimitiveLanguageTeacher(type("Cfg", (), {"random": rng})())
+    order = list(range(len(splits["train_inst_env"])))
+    rng.shuffle(order)                                             # data/dataset.py:70-72
+    for r in range(12):                                            # the first training iterations
+        B, T, T2 = int(fx["n_env"][r]), int(fx["n_t"][r]), int(fx["phase2_n_t"][r])
+        rows = order[32 * r:32 * r + 32]
+        assert rows == fx["batch"][r, :B].tolist()
+        env = VecCraft.from_instances(medium_tables, splits["train_grids"], splits["train_inst_env"][rows],
+                                      splits["train_inst_pos"][rows], splits["train_inst_task"][rows],
+                                      max_timesteps=40)
+        p1 = torch.from_numpy(fx["acts"][r]).to(env.device)        # [40, 32], 255 = terminated
+        p2 = torch.from_numpy(fx["phase2_acts"][r]).to(env.device)
+        got = language_rollouts(env, teacher, lambda f, t: p1[t, :B], splits["train_ref_actions"][rows],
+                                greedy_policy=lambda f, t: p2[t, :B])
+        instr = got["instructions"].numpy() - 1                    # instruct_batch: 1 + action index, 0 = padding
+        for i in range(B):
+            want = [int(w) for w in fx["instructions"][r, i] if w != 255]
+            assert instr[i][instr[i] >= 0].tolist() == want, (r, i)
+            wd = [int(w) for w in fx["descriptions"][r, i] if w != 255]
+            gd = got["descriptions"][i].cpu().numpy()
+            assert gd[gd >= 0].tolist() == wd, (r, i)
+            L = int(fx["seq_len"][r, i])
+            assert got["action_seqs"][i, :L].tolist() == fx["phase2_acts"][r, :L, i].tolist(), (r, i)
+            assert (got["action_seqs"][i, L:] == 255).all()
+        assert got["success"].tolist() == fx["success"][r, :B].astype(bool).tolist(), r
+        d = got["distances"]
+        assert d[d >= 0].tolist() == fx["distances"][r, :int(fx["n_dist"][r])].tolist(), r
+        assert got["num_steps"] == int(fx["num_steps"][r]) and got["num_interactions"] == int(fx["num_interactions"][r]), r
+    assert len(teacher.student_action_map) >= 5
