@@ -337,3 +337,40 @@ def test_batched_language_rollouts_reproduce_the_reference_trainer(config4_langu
         assert d[d >= 0].tolist() == fx["distances"][r, :int(fx["n_dist"][r])].tolist(), r
         assert got["num_steps"] == int(fx["num_steps"][r]) and got["num_interactions"] == int(fx["num_interactions"][r]), r
     assert len(teacher.student_action_map) >= 5
+
+
+@pytest.mark.gpu
+def test_batched_policy_rollouts_reproduce_the_reference_trainer(config4, splits, medium_tables):
+    """psketch_b200.rollout.policy_rollouts — ImitationTrainer.do_rollout for a whole batch, one
+    step-then-observe tick per timestep — driven by the student's recorded actions from the reference's
+    own ImitationTrainer run: teacher labels, executed action sequences, success, distances and
+    counters of all 30 training rollouts and of the first evaluation of the dev split must equal the
+    record."""
+    import torch
+    from psketch_b200.rollout import policy_rollouts
+    from psketch_b200.vec import VecCraft
+    fx = config4
+    n_train = int(fx["n_train_iters"])
+    for r in list(range(n_train)) + list(range(n_train, n_train + int(fx["eval_sizes"][0]))):
+        B, T, is_eval = int(fx["n_env"][r]), int(fx["n_t"][r]), bool(fx["is_eval"][r])
+        split = "dev" if is_eval else "train"
+        rows = fx["batch"][r, :B]
+        env = VecCraft.from_instances(medium_tables, splits[split + "_grids"], splits[split + "_inst_env"][rows],
+                                      splits[split + "_inst_pos"][rows], splits[split + "_inst_task"][rows],
+                                      max_timesteps=40)
+        script = torch.from_numpy(fx["acts"][r]).to(env.device)             # [40, 32]
+        got = policy_rollouts(env, lambda f, t: script[t, :B], max_timesteps=40, is_eval=is_eval, poll_every=4)
+        for i in range(B):
+            L = int(fx["seq_len"][r, i])
+            assert got["action_seqs"][i, :L].tolist() == fx["acts"][r, :L, i].tolist(), (r, i)
+            assert (got["action_seqs"][i, L:] == 255).all(), (r, i)
+            if not is_eval:
+                want = fx["refs"][r, :T, i]
+                live = want >= 0
+                assert got["ref_seqs"][i, :T][live].tolist() == want[live].tolist(), (r, i)
+                assert (got["ref_seqs"][i, :T][~live] == 255).all(), (r, i)
+        assert got["success"].tolist() == fx["success"][r, :B].astype(bool).tolist(), r
+        d = got["distances"]
+        assert d[d >= 0].tolist() == fx["distances"][r, :int(fx["n_dist"][r])].tolist(), r
+        assert got["num_steps"] == int(fx["num_steps"][r]), r
+        assert got["num_interactions"] == int(fx["num_interactions"][r]), r
