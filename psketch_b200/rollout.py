@@ -180,3 +180,57 @@ def language_rollouts(env, teacher, policy, ref_actions, max_timesteps=40, is_ev
     out.update(first_pass_actions=first["actions"].cpu().numpy(), action_seqs=last["actions"].cpu().numpy(),
                success=success.cpu().numpy(), distances=dist.cpu().numpy())
     return out
+
+
+def interactive_rollouts(env, teacher, policy, max_timesteps=40, is_eval=False, on_step=None, poll_every=8):
+    """trainers/interactive_primitive_language.py:16-106 for the whole batch.  Per timestep: the
+    teacher's one-word instruction for EVERY env — also the finished ones, :49-51 — (the CUDA teacher's
+    action; training only), ``policy(features, t, instruction_actions) -> u8[N]``, the step of every
+    running env (the terminating action is executed too, :58-61), and the teacher's one-word description
+    of what each executed action did (``describe_batch`` with rollouts of length 1, in env order, so the
+    action map and the random stream evolve exactly as in the reference — in evaluation as well, :64-66).
+    ``on_step(t, instructions, descriptions, live)`` hands the words to the student.
+    Returns dict(action_seqs, instructions u8[T, N] (action index = word), descriptions i64[T, N]
+    (-1 where the env was finished), success, distances, num_interactions, num_steps)."""
+    from . import _lib
+    T = _lib.check_max_timesteps(max_timesteps)
+    n, dev = env.n, env.device
+    env.reset()
+    done = torch.zeros(n, dtype=torch.bool, device=dev)
+    acts = torch.full((n, T), 255, dtype=torch.uint8, device=dev)
+    instr = torch.full((T, n), 255, dtype=torch.uint8, device=dev)
+    desc = torch.full((T, n), -1, dtype=torch.int64, device=dev)
+    feats = torch.empty((n, env.n_features), dtype=torch.float32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    t = 0
+    while t < T:
+        live = ~done
+        words = None
+        if not is_eval:
+            words = env.expert()                       # asked for finished envs too
+            instr[t] = words
+            counts[0] += live.sum()
+        env.features(out=feats)
+        a = policy(feats, t, words).to(device=dev, dtype=torch.uint8)
+        before = env.agent.clone()
+        acts[:, t] = torch.where(live, a, acts[:, t])
+        env.step(torch.where(live, a, torch.full_like(a, STOP)), active=live.to(torch.uint8))
+        if not is_eval:
+            counts[1] += live.sum()
+        d = teacher.describe_batch(a.long().unsqueeze(1), torch.stack([before, env.agent]), live.long(),
+                                   n_kinds=env.K)
+        desc[t] = d[:, 0]
+        if on_step is not None:
+            on_step(t, words, desc[t], live)
+        done |= (a == STOP) | (t == T - 1)
+        t += 1
+        if t % poll_every == 0 and bool(done.all()):
+            break
+    env.check_errors()
+    success = env.satisfies() == 1
+    final_agent = env.agent.clone()
+    dist = _distances(env, success, final_agent)
+    ni, ns = (int(v) for v in counts.tolist())
+    return dict(action_seqs=acts.cpu().numpy(), instructions=instr[:t].cpu().numpy(),
+                descriptions=desc[:t].cpu().numpy(), success=success.cpu().numpy(),
+                distances=dist.cpu().numpy(), num_interactions=ni, num_steps=ns, timesteps=t)

@@ -374,3 +374,40 @@ def test_batched_policy_rollouts_reproduce_the_reference_trainer(config4, splits
         assert d[d >= 0].tolist() == fx["distances"][r, :int(fx["n_dist"][r])].tolist(), r
         assert got["num_steps"] == int(fx["num_steps"][r]), r
         assert got["num_interactions"] == int(fx["num_interactions"][r]), r
+
+
+@pytest.mark.gpu
+def test_batched_interactive_rollouts_reproduce_the_reference_trainer(config4_interactive, splits, medium_tables):
+    """psketch_b200.rollout.interactive_rollouts against the record of the reference's own
+    InteractivePrimitiveLanguageTrainer run (first training iterations): per-timestep instructions
+    for every env, per-step descriptions (with the random draws of the learning phase), action
+    sequences, success, distances, counters."""
+    import torch
+    from psketch_b200.rollout import interactive_rollouts
+    from psketch_b200.teachers import InteractivePrimitiveLanguageTeacher
+    from psketch_b200.vec import VecCraft
+    fx = config4_interactive
+    rng = np.random.RandomState(123)
+    teacher = InteractivePrimitiveLanguageTeacher(type("Cfg", (), {"random": rng})())
+    order = list(range(len(splits["train_inst_env"])))
+    rng.shuffle(order)
+    for r in range(12):
+        B, T = int(fx["n_env"][r]), int(fx["n_t"][r])
+        rows = order[32 * r:32 * r + 32]
+        assert rows == fx["batch"][r, :B].tolist()
+        env = VecCraft.from_instances(medium_tables, splits["train_grids"], splits["train_inst_env"][rows],
+                                      splits["train_inst_pos"][rows], splits["train_inst_task"][rows],
+                                      max_timesteps=40)
+        script = torch.from_numpy(fx["acts"][r]).to(env.device)
+        got = interactive_rollouts(env, teacher, lambda f, t, w: script[t, :B], max_timesteps=40, poll_every=1)
+        assert got["timesteps"] == T, r
+        assert np.array_equal(got["instructions"], fx["instr_steps"][r, :T, :B]), r
+        for i in range(B):
+            L = int(fx["seq_len"][r, i])
+            assert got["action_seqs"][i, :L].tolist() == fx["acts"][r, :L, i].tolist(), (r, i)
+            assert got["descriptions"][:L, i].tolist() == fx["desc_steps"][r, :L, i].tolist(), (r, i)
+            assert (got["descriptions"][L:, i] == -1).all(), (r, i)
+        assert got["success"].tolist() == fx["success"][r, :B].astype(bool).tolist(), r
+        d = got["distances"]
+        assert d[d >= 0].tolist() == fx["distances"][r, :int(fx["n_dist"][r])].tolist(), r
+        assert got["num_steps"] == int(fx["num_steps"][r]) and got["num_interactions"] == int(fx["num_interactions"][r]), r
