@@ -441,12 +441,15 @@ def test_rollout_kernel_variants_vs_oracle(n, splits, medium_tables, medium_orac
         _lib.set_tuning(rollout_variant=-1, rollout_tma=-1)
 
 
+@pytest.mark.parametrize("tma", [-1, 1])
 @pytest.mark.parametrize("n,with_actions", [(6007, False), (4099, True), (65, False)])
-def test_multi_tick_rollout_equals_single_ticks(n, with_actions, splits, medium_tables, medium_oracle):
+def test_multi_tick_rollout_equals_single_ticks(n, with_actions, tma, splits, medium_tables, medium_oracle):
     """psk_craft_rollout (tick loop inside the kernel, state in shared memory) against the same
     number of psk_craft_tick launches AND against the oracle advanced tick by tick: every per-tick
     output, the final state and the counters."""
+    from psketch_b200 import _lib
     from psketch_b200.vec import VecCraft
+    _lib.set_tuning(rollout_tma=tma, tick_tma=tma)          # ragged sizes through the TMA store path too
     rng = np.random.RandomState(n)
     idx = rng.randint(0, 2200, size=n)
     grids = splits["dev_grids"]
@@ -481,6 +484,7 @@ def test_multi_tick_rollout_equals_single_ticks(n, with_actions, splits, medium_
     c.rollout(T, actions=acts, features_out=ring, want_flags=False)
     assert torch.equal(ring[(T - 1) % 2], feats[T - 1]) and torch.equal(ring[(T - 2) % 2], feats[T - 2])
     a.check_errors()
+    _lib.set_tuning(rollout_tma=-1, tick_tma=-1)
 
 
 def test_multi_tick_rollout_other_geometry_falls_back(large_tables, large_states):
