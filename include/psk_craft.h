@@ -177,6 +177,14 @@ int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episo
                    uint8_t *done_out, uint8_t *success_out, unsigned long long *stats,
                    int32_t *err_flags, int fused, void *stream);
 
+/* psk_craft_tick with the feature rows as bytes (features_out u8[n][n_features], see
+ * psk_craft_features_u8) — same fused kernel, a quarter of the output traffic; order =
+ * PSK_TICK_FUSED or PSK_TICK_ADVANCE_FIRST. */
+int psk_craft_tick_u8(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
+                      const uint8_t *action_in, uint8_t *features_out, uint8_t *expert_out,
+                      uint8_t *done_out, uint8_t *success_out, unsigned long long *stats,
+                      int32_t *err_flags, int order, void *stream);
+
 /* `ticks` consecutive rollout ticks in ONE launch (same per-tick semantics as psk_craft_tick):
  * every CTA keeps its envs' state in shared memory across the ticks, so HBM sees one state read,
  * one state write and `ticks` output frames.  For rollouts whose actions do not depend on
@@ -188,6 +196,13 @@ int psk_craft_rollout(const psk_craft_tables *t, psk_craft_state s, psk_craft_ep
                       int32_t feat_ring, uint8_t *expert_out, uint8_t *done_out,
                       uint8_t *success_out, unsigned long long *stats, int32_t *err_flags,
                       void *stream);
+
+/* psk_craft_rollout with byte frames: features_out u8[feat_ring][n][n_features]. */
+int psk_craft_rollout_u8(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
+                         int32_t ticks, const uint8_t *action_in, uint8_t *features_out,
+                         int32_t feat_ring, uint8_t *expert_out, uint8_t *done_out,
+                         uint8_t *success_out, unsigned long long *stats, int32_t *err_flags,
+                         void *stream);
 
 /* Scenario sampling (make_data.py:74-144, `random_free` / `sample_scenario`) with a counter-based
  * Philox4x32-10 generator: boundary ring, then place_kinds[0..n_place) in order, then the agent,

@@ -25,6 +25,7 @@ CRAFT_EXPORTS = (
     "psk_random_actions", "psk_craft_rollout", "psk_set_tuning", "psk_get_tuning",
     "psk_craft_features_u8", "psk_craft_host_reset", "psk_craft_host_put_state",
     "psk_craft_host_get_state", "psk_craft_host_tick_resident", "psk_random_actions_block",
+    "psk_craft_tick_u8", "psk_craft_rollout_u8",
 )
 FEATURES_NONE, FEATURES_F32, FEATURES_U8 = 0, 1, 2
 
@@ -88,6 +89,8 @@ def load():
                                    i32, vp]
     i64 = ctypes.c_int64
     lib.psk_craft_rollout.argtypes = [tp, CraftStateC, CraftEpisodesC, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.psk_craft_rollout_u8.argtypes = [tp, CraftStateC, CraftEpisodesC, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.psk_craft_tick_u8.argtypes = [tp, CraftStateC, CraftEpisodesC, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.psk_host_alloc.argtypes = [ctypes.c_size_t]
     lib.psk_host_alloc.restype = ctypes.c_void_p
     lib.psk_host_free.argtypes = [vp]

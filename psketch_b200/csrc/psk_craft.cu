@@ -1622,12 +1622,14 @@ craft_advance_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
 //                    (warp_feature_chunk: zero-fill + scatter into its smem buffers, TMA store).
 // The integer-ALU-bound teacher and the store-bound feature stream therefore overlap inside
 // every CTA instead of alternating.
-template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA>
+// OUT = float: the reference's f32 feature rows; OUT = uint8_t: the compact byte frame
+// (psk_craft_tick_u8 / psk_craft_rollout_u8; vector-store path only: the tile IS the frame).
+template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA, typename OUT = float>
 __global__ void __launch_bounds__(NE + NFW * 32)
 craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                   uint8_t *__restrict__ agent, const uint8_t *__restrict__ action_in,
                   const uint8_t *__restrict__ scen_grid, const int32_t *__restrict__ scen_idx,
-                  const uint8_t *__restrict__ init_agent, float *__restrict__ features_out,
+                  const uint8_t *__restrict__ init_agent, OUT *__restrict__ features_out,
                   uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
                   uint8_t *__restrict__ success_out, unsigned long long *stats,
                   int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int adv_first,
@@ -1795,8 +1797,14 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
                 }
                 RowChunks<W, H, TPE> cells;
                 cells.load(s_rows + se * CP, lane % TPE);
-                warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
-                    wbuf_s, it, features_out + (e_base + s0) * nf, ne, cells, b, K, nf);
+                if constexpr (sizeof(OUT) == 1) {
+                    static_assert(sizeof(OUT) != 1 || (!USE_TMA && PSK_ESZ_FUSED_KERNELS == 1), "u8 frame: vector path, u8 tile");
+                    warp_feature_chunk_u8<W, H, WIN, TPE, KC>(wbuf_s, features_out + (e_base + s0) * nf, ne,
+                                                              cells, b, K, nf);
+                } else {
+                    warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
+                        wbuf_s, it, features_out + (e_base + s0) * nf, ne, cells, b, K, nf);
+                }
                 it++;
             }
         }
@@ -1823,13 +1831,13 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
 // 9 CTAs of 32 + 2 warps (96 threads); one register more and a CTA less fits per SM (17.5 -> 21 us
 // per tick at 65,536 envs when a change pushed the kernel to 80 registers).
 __host__ __device__ constexpr int rollout_threads(int ne, int nfw) { return (ne + 31) / 32 * 32 + nfw * 32; }
-template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA>
+template <int W, int H, int WIN, int NE, int NFW, int KC, bool USE_TMA, typename OUT = float>
 __global__ void __launch_bounds__(rollout_threads(NE, NFW),
                                   (W * H <= 64 && rollout_threads(NE, NFW) <= 128) ? 896 / rollout_threads(NE, NFW) : 1)
 craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ grid,
                      uint8_t *__restrict__ agent, const uint8_t *__restrict__ action_in,
                      const uint8_t *__restrict__ scen_grid, const int32_t *__restrict__ scen_idx,
-                     const uint8_t *__restrict__ init_agent, float *__restrict__ features_out,
+                     const uint8_t *__restrict__ init_agent, OUT *__restrict__ features_out,
                      int feat_ring, uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
                      uint8_t *__restrict__ success_out, unsigned long long *stats,
                      int32_t *err_flags, int64_t n, int cell_stride, int K, int nf, int ticks,
@@ -1934,7 +1942,7 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
                 const int fw = (tid - NEW) >> 5, lane = tid & 31;
                 const uint32_t wbuf_s = smem_u32(smem_raw) +
                                         (uint32_t)fw * feature_buffer_bytes(USE_TMA, EPW, nf, PSK_ESZ_FUSED_KERNELS);
-                float *fout = features_out + (int64_t)(t % feat_ring) * n * nf;
+                OUT *fout = features_out + (int64_t)(t % feat_ring) * n * nf;
                 for (int c = 0; c < SPW / EPW; c++) {
                     const int s0 = fw * SPW + c * EPW;
                     if (s0 >= ne_sp) break;
@@ -1949,8 +1957,14 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
                     }
                     RowChunks<W, H, TPE> cells;
                     cells.load(s_rows[cur] + se * CP, lane % TPE);
-                    warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
-                        wbuf_s, it, fout + (e_base + s0) * nf, ne, cells, b, K, nf);
+                    if constexpr (sizeof(OUT) == 1) {
+                        static_assert(sizeof(OUT) != 1 || (!USE_TMA && PSK_ESZ_FUSED_KERNELS == 1), "u8 frame: vector path, u8 tile");
+                        warp_feature_chunk_u8<W, H, WIN, TPE, KC>(wbuf_s, fout + (e_base + s0) * nf, ne, cells,
+                                                                  b, K, nf);
+                    } else {
+                        warp_feature_chunk<W, H, WIN, TPE, KC, USE_TMA, PSK_ESZ_FUSED_KERNELS>(
+                            wbuf_s, it, fout + (e_base + s0) * nf, ne, cells, b, K, nf);
+                    }
                     it++;
                 }
             }
@@ -2237,22 +2251,22 @@ template <int W, int H, int WIN> struct Config {
             stats, err, s.n, s.cell_stride);
         return check(cudaGetLastError());
     }
-    template <int NE, int NFW, bool TMA>
+    template <int NE, int NFW, bool TMA, typename OUT = float>
     static int tick_variant(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
-                            const uint8_t *action_in, float *features_out, uint8_t *expert_out,
+                            const uint8_t *action_in, OUT *features_out, uint8_t *expert_out,
                             uint8_t *done, uint8_t *success, unsigned long long *stats,
                             int32_t *err, cudaStream_t st, int adv_first) {
         constexpr int EPW = 32 / TPE;
         const int f = nf(t);
         const size_t smem = (size_t)NFW * feature_buffer_bytes(TMA, EPW, f, PSK_ESZ_FUSED_KERNELS);
-        auto kern = t->n_kinds == 21 ? craft_tick_kernel<W, H, WIN, NE, NFW, 21, TMA>
-                                     : craft_tick_kernel<W, H, WIN, NE, NFW, 0, TMA>;
+        auto kern = t->n_kinds == 21 ? craft_tick_kernel<W, H, WIN, NE, NFW, 21, TMA, OUT>
+                                     : craft_tick_kernel<W, H, WIN, NE, NFW, 0, TMA, OUT>;
         static size_t configured_on[PSK_MAX_DEVICES] = {0};   // the attribute is per device
         size_t &configured = configured_on[current_device()];
         if (configured != smem) {
-            if (cudaFuncSetAttribute(craft_tick_kernel<W, H, WIN, NE, NFW, 21, TMA>,
+            if (cudaFuncSetAttribute(craft_tick_kernel<W, H, WIN, NE, NFW, 21, TMA, OUT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-                cudaFuncSetAttribute(craft_tick_kernel<W, H, WIN, NE, NFW, 0, TMA>,
+                cudaFuncSetAttribute(craft_tick_kernel<W, H, WIN, NE, NFW, 0, TMA, OUT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return PSK_ERR_CUDA;
             configured = smem;
@@ -2288,23 +2302,23 @@ template <int W, int H, int WIN> struct Config {
                                         success, stats, err, s.n, cell_stride, K, f, adv_first, chain,
                                         chain_g0));
     }
-    template <int NE, int NFW, bool TMA>
+    template <int NE, int NFW, bool TMA, typename OUT = float>
     static int rollout_variant(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
-                               int ticks, const uint8_t *action_in, float *features_out,
+                               int ticks, const uint8_t *action_in, OUT *features_out,
                                int feat_ring, uint8_t *expert_out, uint8_t *done,
                                uint8_t *success, unsigned long long *stats, int32_t *err,
                                cudaStream_t st) {
         constexpr int EPW = 32 / TPE;
         const int f = nf(t);
         const size_t smem = (size_t)NFW * feature_buffer_bytes(TMA, EPW, f, PSK_ESZ_FUSED_KERNELS);
-        auto kern = t->n_kinds == 21 ? craft_rollout_kernel<W, H, WIN, NE, NFW, 21, TMA>
-                                     : craft_rollout_kernel<W, H, WIN, NE, NFW, 0, TMA>;
+        auto kern = t->n_kinds == 21 ? craft_rollout_kernel<W, H, WIN, NE, NFW, 21, TMA, OUT>
+                                     : craft_rollout_kernel<W, H, WIN, NE, NFW, 0, TMA, OUT>;
         static size_t configured_on[PSK_MAX_DEVICES] = {0};   // the attribute is per device
         size_t &configured = configured_on[current_device()];
         if (configured != smem) {
-            if (cudaFuncSetAttribute(craft_rollout_kernel<W, H, WIN, NE, NFW, 21, TMA>,
+            if (cudaFuncSetAttribute(craft_rollout_kernel<W, H, WIN, NE, NFW, 21, TMA, OUT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-                cudaFuncSetAttribute(craft_rollout_kernel<W, H, WIN, NE, NFW, 0, TMA>,
+                cudaFuncSetAttribute(craft_rollout_kernel<W, H, WIN, NE, NFW, 0, TMA, OUT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return PSK_ERR_CUDA;
             configured = smem;
@@ -2363,6 +2377,32 @@ template <int W, int H, int WIN> struct Config {
             return tma ? rollout_variant<64, 2, true>(PSK_ROLLOUT_ARGS)
                        : rollout_variant<64, 2, false>(PSK_ROLLOUT_ARGS);
 #undef PSK_ROLLOUT_ARGS
+        }
+    }
+    // the byte frame through the fused kernels: one CTA shape (32 + 2), vector stores
+    static int tick_u8(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
+                       const uint8_t *action_in, uint8_t *features_out, uint8_t *expert_out, uint8_t *done,
+                       uint8_t *success, unsigned long long *stats, int32_t *err, cudaStream_t st,
+                       int adv_first) {
+        if constexpr (!BITBOARD) {
+            return PSK_ERR_UNSUPPORTED;
+        } else if constexpr (WIN != 3) {
+            return tick_variant<64, 2, false, uint8_t>(t, s, ep, action_in, features_out, expert_out, done,
+                                                       success, stats, err, st, adv_first);
+        } else {
+            return tick_variant<32, 2, false, uint8_t>(t, s, ep, action_in, features_out, expert_out, done,
+                                                       success, stats, err, st, adv_first);
+        }
+    }
+    static int rollout_u8(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep, int ticks,
+                          const uint8_t *action_in, uint8_t *features_out, int feat_ring,
+                          uint8_t *expert_out, uint8_t *done, uint8_t *success,
+                          unsigned long long *stats, int32_t *err, cudaStream_t st) {
+        if constexpr (!BITBOARD || WIN != 3) {
+            return PSK_ERR_UNSUPPORTED;
+        } else {
+            return rollout_variant<32, 2, false, uint8_t>(t, s, ep, ticks, action_in, features_out, feat_ring,
+                                                          expert_out, done, success, stats, err, st);
         }
     }
     static int tick_fused(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
@@ -2564,6 +2604,57 @@ int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episo
     }
     const uint8_t *act = action_in ? action_in : expert_out;
     PSK_DISPATCH(t, advance(t, s, ep, act, done_out, success_out, stats, err_flags, st));
+}
+
+int psk_craft_tick_u8(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
+                      const uint8_t *action_in, uint8_t *features_out, uint8_t *expert_out,
+                      uint8_t *done_out, uint8_t *success_out, unsigned long long *stats,
+                      int32_t *err_flags, int order, void *stream) {
+    if (!state_ok(t, s)) return PSK_ERR_BADARG;
+    if (s.n == 0) return PSK_OK;
+    if (!expert_out || !features_out || !ep.scen_grid || !ep.scen_idx || !ep.init_agent) return PSK_ERR_BADARG;
+    if (reinterpret_cast<uintptr_t>(features_out) & 3) return PSK_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int adv_first = order == PSK_TICK_ADVANCE_FIRST;
+    if (t->width * t->height <= 128)
+        PSK_DISPATCH(t, tick_u8(t, s, ep, action_in, features_out, expert_out, done_out, success_out, stats,
+                                err_flags, st, adv_first));
+    // grids above 128 cells: the feature kernel writes the bytes, the tick does the rest
+    if (!adv_first) {
+        const int rc = psk_craft_features_u8(t, s, features_out, stream);
+        if (rc) return rc;
+    }
+    int rc = psk_craft_tick(t, s, ep, action_in, nullptr, expert_out, done_out, success_out, stats, err_flags,
+                            order, stream);
+    if (!rc && adv_first) rc = psk_craft_features_u8(t, s, features_out, stream);
+    return rc;
+}
+
+int psk_craft_rollout_u8(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,
+                         int32_t ticks, const uint8_t *action_in, uint8_t *features_out,
+                         int32_t feat_ring, uint8_t *expert_out, uint8_t *done_out,
+                         uint8_t *success_out, unsigned long long *stats, int32_t *err_flags,
+                         void *stream) {
+    if (!state_ok(t, s) || ticks < 0 || !features_out || feat_ring <= 0) return PSK_ERR_BADARG;
+    if (s.n == 0 || ticks == 0) return PSK_OK;
+    if (!expert_out || !ep.scen_grid || !ep.scen_idx || !ep.init_agent) return PSK_ERR_BADARG;
+    if (reinterpret_cast<uintptr_t>(features_out) & 3) return PSK_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = PSK_ERR_UNSUPPORTED;
+    if (Medium::matches(t))
+        rc = Medium::rollout_u8(t, s, ep, ticks, action_in, features_out, feat_ring, expert_out, done_out,
+                                success_out, stats, err_flags, st);
+    if (rc != PSK_ERR_UNSUPPORTED) return rc;
+    const int nfeat = psk_craft_n_features(t);
+    for (int k = 0; k < ticks; k++) {
+        const int64_t o = (int64_t)k * s.n;
+        rc = psk_craft_tick_u8(t, s, ep, action_in ? action_in + o : nullptr,
+                               features_out + (int64_t)(k % feat_ring) * s.n * nfeat, expert_out + o,
+                               done_out ? done_out + o : nullptr, success_out ? success_out + o : nullptr,
+                               stats, err_flags, PSK_TICK_FUSED, stream);
+        if (rc) return rc;
+    }
+    return PSK_OK;
 }
 
 int psk_craft_rollout(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,

@@ -286,16 +286,10 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
         int rc;
         const int mode = advance_first ? PSK_TICK_ADVANCE_FIRST : PSK_TICK_FUSED;
         if (feature_format == PSK_FEATURES_U8) {
-            // compact frame: the feature kernel writes bytes; it runs on the state the features
-            // describe — before the tick in observe-then-step order, after it in step-then-observe
-            if (!advance_first) {
-                rc = psk_craft_features_u8(&c->tables, state, reinterpret_cast<uint8_t *>(c->d_feat[s]), st);
-                if (rc) return rc;
-            }
-            rc = psk_craft_tick(&c->tables, state, ep, act, nullptr, c->r_expert + off, c->r_done + off,
-                                c->r_success + off, c->d_stats, c->d_err, mode, st);
-            if (!rc && advance_first)
-                rc = psk_craft_features_u8(&c->tables, state, reinterpret_cast<uint8_t *>(c->d_feat[s]), st);
+            // compact frame: the fused kernel writes its u8 tile as it is
+            rc = psk_craft_tick_u8(&c->tables, state, ep, act, reinterpret_cast<uint8_t *>(c->d_feat[s]),
+                                   c->r_expert + off, c->r_done + off, c->r_success + off, c->d_stats,
+                                   c->d_err, mode, st);
         } else {
             rc = psk_craft_tick(&c->tables, state, ep, act,
                                 feature_format == PSK_FEATURES_F32 ? c->d_feat[s] : nullptr,

@@ -204,7 +204,8 @@ class VecCraft(object):
         """One rollout tick (see psk_craft_tick).  Returns dict(expert, done, success, features).
         ``advance_first``: "step, then observe" — ``actions`` (None = no step) are applied first and
         expert / features describe the state AFTER the step (PSK_TICK_ADVANCE_FIRST): the order a
-        policy in the loop needs, one launch per timestep."""
+        policy in the loop needs, one launch per timestep.  A ``features_out`` tensor of dtype uint8
+        selects the compact byte frame (psk_craft_tick_u8)."""
         actions = self._u8(actions)
         if out is None:
             out = {}
@@ -215,12 +216,18 @@ class VecCraft(object):
             features_out = torch.empty((self.n, self.n_features), dtype=torch.float32,
                                        device=self.device)
         out["features"] = features_out
+        order = 2 if advance_first else (1 if fused else 0)
         with torch.cuda.device(self.device):
-            rc = self.lib.psk_craft_tick(ctypes.byref(self.ct), self._state(), self._episodes(),
-                                         _ptr(actions), _ptr(features_out), _ptr(out["expert"]),
-                                         _ptr(out["done"]), _ptr(out["success"]),
-                                         _ptr(self.stats), _ptr(self.err_flags),
-                                         2 if advance_first else (1 if fused else 0), self._stream())
+            if features_out is not None and features_out.dtype == torch.uint8:
+                rc = self.lib.psk_craft_tick_u8(ctypes.byref(self.ct), self._state(), self._episodes(),
+                                                _ptr(actions), _ptr(features_out), _ptr(out["expert"]),
+                                                _ptr(out["done"]), _ptr(out["success"]), _ptr(self.stats),
+                                                _ptr(self.err_flags), order or 1, self._stream())
+            else:
+                rc = self.lib.psk_craft_tick(ctypes.byref(self.ct), self._state(), self._episodes(),
+                                             _ptr(actions), _ptr(features_out), _ptr(out["expert"]),
+                                             _ptr(out["done"]), _ptr(out["success"]),
+                                             _ptr(self.stats), _ptr(self.err_flags), order, self._stream())
         _lib.check(rc, "psk_craft_tick")
         return out
 
@@ -239,8 +246,10 @@ class VecCraft(object):
         if features_out is not None:
             assert features_out.dim() == 3 and features_out.is_contiguous()
             ring = features_out.shape[0]
+        entry = (self.lib.psk_craft_rollout_u8 if features_out is not None and features_out.dtype == torch.uint8
+                 else self.lib.psk_craft_rollout)            # byte frames: u8[R, N, n_features]
         with torch.cuda.device(self.device):
-            rc = self.lib.psk_craft_rollout(ctypes.byref(self.ct), self._state(), self._episodes(),
+            rc = entry(ctypes.byref(self.ct), self._state(), self._episodes(),
                                             int(ticks), _ptr(actions), _ptr(features_out), ring,
                                             _ptr(out["expert"]), _ptr(out.get("done")),
                                             _ptr(out.get("success")), _ptr(self.stats),

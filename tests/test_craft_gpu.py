@@ -1025,3 +1025,62 @@ def test_host_in_the_loop_resident_tick(features, splits, medium_tables, medium_
         check_observation(t)
     assert tuple(int(x) for x in env.stats[:3]) == tuple(orc.stats)
     env.close()
+
+
+@pytest.mark.parametrize("which,n", [("medium", 6007), ("medium", 65), ("large", 1500), ("stress16", 700)])
+def test_u8_frame_through_the_fused_kernels(which, n, splits, medium_tables, medium_oracle, large_tables,
+                                            large_oracle, large_states):
+    """psk_craft_tick_u8 / psk_craft_rollout_u8: the feature rows leave the fused kernels as bytes
+    (every feature is an exact integer <= 255).  Both tick orders and the multi-tick rollout against
+    the oracle; 16x16 goes through the launch-sequence fallback."""
+    from psketch_b200.vec import VecCraft
+    rng = np.random.RandomState(n)
+    if which == "medium":
+        idx = rng.randint(0, 2200, size=n)
+        tables, oracle, grids = medium_tables, medium_oracle, splits["dev_grids"]
+        ienv, ipos, itask = splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx], splits["dev_inst_task"][idx]
+    elif which == "large":
+        tables, oracle, grids = large_tables, large_oracle, large_states["grid"][:n]
+        ienv, ipos = np.arange(n), large_states["pos"][:n]
+        itask = rng.choice([13, 14, 15, 19, 20, 21, 22, 23, 24, 25, 26], size=n)
+    else:
+        from oracle.craft_oracle import CraftOracle
+        from psketch_b200.tables import CraftTables
+        tables = CraftTables(world_config=dict(WIDTH=16, HEIGHT=16, WINDOW_WIDTH=3, WINDOW_HEIGHT=3,
+                                               N_WORKSHOPS=3, N_PRIMITIVES=4))
+        oracle = CraftOracle(tables)
+        g = np.zeros((n, 16, 16), np.uint8)
+        g[:, 0, :] = g[:, 15, :] = g[:, :, 0] = g[:, :, 15] = 1
+        ipos = np.zeros((n, 2), np.int64)
+        for i in range(n):
+            cells = rng.permutation(14 * 14)
+            for j, kind in enumerate([7, 7, 8, 8, 9, 9, 2, 3, 4, 5, 6, 6]):
+                g[i, 1 + cells[j] // 14, 1 + cells[j] % 14] = kind
+            ipos[i] = (1 + cells[20] // 14, 1 + cells[20] % 14)
+        grids, ienv = g.reshape(n, 256), np.arange(n)
+        itask = rng.choice([13, 14, 15, 19, 20, 21, 22, 23, 24, 25, 26], size=n)
+    nf = tables.n_features
+    env = VecCraft.from_instances(tables, grids, ienv, ipos, itask, max_timesteps=17)
+    orc = _OracleTicks(oracle, grids, ienv, ipos, itask, max_timesteps=17)
+    f8 = torch.empty((n, nf), dtype=torch.uint8, device=env.device)
+    for t in range(12):                                   # observe, then step (teacher or random actions)
+        a = rng.choice(6, size=n, p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8) if t % 2 else None
+        out = env.tick(actions=None if a is None else torch.from_numpy(a), features_out=f8)
+        ref = orc.tick(a)
+        assert np.array_equal(_np(out["expert"]), ref["expert"]) and np.array_equal(_np(out["done"]), ref["done"]), t
+        assert np.array_equal(_np(f8).astype(np.float32), ref["features"]), t
+    for t in range(8):                                    # step, then observe
+        a = rng.choice(6, size=n, p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8)
+        out = env.tick(actions=torch.from_numpy(a), features_out=f8, advance_first=True)
+        ref = orc.tick(a, want_features=False)
+        assert np.array_equal(_np(out["done"]), ref["done"]), t
+        assert np.array_equal(_np(f8).astype(np.float32), oracle.features(orc.grid, orc.inv, orc.pos, orc.dir)), t
+    T = 7
+    ring = torch.empty((T, n, nf), dtype=torch.uint8, device=env.device)
+    out = env.rollout(T, features_out=ring)
+    for t in range(T):
+        ref = orc.tick()
+        assert np.array_equal(_np(out["expert"][t]), ref["expert"]), t
+        assert np.array_equal(_np(ring[t]).astype(np.float32), ref["features"]), t
+    orc.assert_state_equals(env)
+    env.check_errors()
