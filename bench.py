@@ -553,6 +553,8 @@ def run_ours(args):
                             "peak_source": peak_src, "algorithmic_bytes_per_env_step": BYTES_FEATURES}
     line["single_tick"] = dict(line["kernels"].pop("tick_fused"), kernel="craft_tick_kernel (one tick per "
                                "launch: the student-in-the-loop path)", algorithmic_bytes_per_env_step=BYTES_FUSED)
+    if fused and world == 1:
+        line["u8_frame"] = u8_frame_record(torch, env, n, nf, dev, peak)
     del env, feat_ring, feats
     torch.cuda.empty_cache()
     if world == 1 and not args.no_1m:
@@ -624,6 +626,37 @@ def per_kernel_table(torch, env, n, nf, dev, peak, n_bufs):
     env.restore(snap)
     del big
     return kern
+
+
+def u8_frame_record(torch, env, n, nf, dev, peak, ticks=8, ring=16):
+    """Secondary record: the same rollout with the opt-in byte frame (psk_craft_rollout_u8 /
+    psk_craft_tick_u8) — every feature is an exact integer <= 255, so the frame is the f32 one cast.
+    407 B per env-step instead of 1,619: the kernel is no longer write-bound, and the fraction of the
+    copy bandwidth says how far the BFS + window arithmetic is from being hidden behind it."""
+    snap = env.snapshot()
+    frames = torch.empty((ring, n, nf), dtype=torch.uint8, device=dev)    # 16 x 26 MB > L2
+    out, cnt = {}, [0]
+
+    def roll():
+        s = (cnt[0] * ticks) % ring
+        env.rollout(ticks, features_out=frames[s:s + ticks], out=out)
+        cnt[0] += 1
+
+    def tick():
+        env.tick(features_out=frames[cnt[0] % ring], out=out)
+        cnt[0] += 1
+
+    rec = {}
+    for name, fn, per_launch in (("rollout", roll, ticks), ("single_tick", tick, 1)):
+        env.restore(snap)
+        dt = time_kernel(fn, torch, inner=ring // per_launch if per_launch > 1 else ring)
+        b = (nf + 3) + (2 * 96 + 4) / per_launch
+        rec[name] = {"us_per_tick": dt * 1e6 / per_launch, "env_steps_per_s": n * per_launch / dt,
+                     "algorithmic_bytes_per_env_step": b, "GBps": b * n * per_launch / dt / 1e9,
+                     "frac": b * n * per_launch / dt / 1e9 / peak, "ticks_per_launch": per_launch}
+    env.restore(snap)
+    del frames
+    return rec
 
 
 def light_record(torch, dev, peak):
@@ -790,8 +823,10 @@ def measure_config3(torch, dist, pdist, tables, rank, world, dev, args):
 def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
     """The same tick through the reference-facing C ABI with HOST buffers, copies inside the timed
     region, MAX over ranks.  Four forms, all checked against the step counter:
-      host_in_loop_f32 (headline)  psk_craft_host_tick_resident, step-then-observe: the host's actions
+      host_in_loop_f32         psk_craft_host_tick_resident, step-then-observe: the host's actions
                                go up every step, the f32[n,404] frame + teacher actions + flags come down
+      host_in_loop_f32_wire_u8 the same f32 host frame, but bytes cross PCIe and host threads widen them
+                               (headline = the faster of these two)
       resident_f32             the same without an action upload (teacher-driven inside the kernel)
       roundtrip_f32            psk_craft_host_tick: additionally the states go up and come back
       resident_u8              the compact u8[n,404] frame instead of f32 (opt-in format)
@@ -831,20 +866,36 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
         variants[name] = {"value": n * steps * world / wall, "unit": UNIT,
                           "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
     # host in the loop: the host's policy (here: follow the teacher action it was handed) picks the
-    # actions, they go UP with every call, the step is applied, the new observation comes DOWN
-    env.reset_resident()
-    env.tick_resident(features="f32", advance_first=True)          # first observation, no step yet
-    acts = env.expert.copy()
+    # actions, they go UP with every call, the step is applied, the new observation comes DOWN as an
+    # f32[n,404] host array — over PCIe as f32, or as bytes widened by host threads (f32_wire_u8)
+    for name, fmt in (("host_in_loop_f32", "f32"), ("host_in_loop_f32_wire_u8", "f32_wire_u8")):
+        if fmt == "f32_wire_u8" and args.e2e_wire_chunk != args.e2e_chunk:
+            # smaller chunks: the widening of the last chunk is the exposed tail of the pipeline
+            env.close()
+            env = HostCraft(tables, wl["grids"], wl["env"], wl["pos"], wl["task"], max_timesteps=40,
+                            chunk_envs=args.e2e_wire_chunk)
+        env.reset_resident()
+        env.features[:] = -1.0
+        env.tick_resident(features=fmt, advance_first=True)        # first observation, no step yet
+        acts = env.expert.copy()
 
-    def host_loop_step():
-        env.tick_resident(actions=acts, features="f32", advance_first=True)
-        acts[:] = env.expert                                        # the host "policy": np copy of n bytes
+        def host_loop_step():
+            env.tick_resident(actions=acts, features=fmt, advance_first=True)
+            acts[:] = env.expert                                    # the host "policy": np copy of n bytes
 
-    before = int(env.stats[2])
-    wall = timed(host_loop_step, steps)
-    assert int(env.stats[2]) - before == (steps + 3) * n
-    variants["host_in_loop_f32"] = {"value": n * steps * world / wall, "unit": UNIT,
-                                    "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
+        before = int(env.stats[2])
+        wall = timed(host_loop_step, steps)
+        assert int(env.stats[2]) - before == (steps + 3) * n
+        variants[name] = {"value": n * steps * world / wall, "unit": UNIT,
+                          "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
+        if fmt == "f32":
+            frame_f32 = env.features.copy()
+            state_f32 = (env.expert.copy(), env.done.copy(), int(env.stats[2]) - before)
+        else:   # both forms ran the same number of steps from the same reset: identical host frames
+            assert np.array_equal(env.features, frame_f32) and np.array_equal(env.expert, state_f32[0])
+            variants[name]["host_threads"] = int(env.lib.psk_craft_host_threads(env.ctx))
+            variants[name]["chunk_envs"] = args.e2e_wire_chunk
+            variants[name]["frame_equals_f32_path"] = True
     # PCIe ceiling for the f32 frame: the same bytes, pinned, nothing else
     frame = torch.empty((n, env.n_features), dtype=torch.float32, device=dev)
     host = torch.empty((n, env.n_features), dtype=torch.float32, pin_memory=True)
@@ -852,14 +903,20 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
     gbs = frame.numel() * 4 * steps / wall / 1e9
     ceiling = {"d2h_GBps_per_gpu": gbs, "env_steps_per_s": n * steps * world / wall,
                "how": "pinned cudaMemcpy D2H of one f32[%d,%d] frame per step, all %d ranks at once" % (n, env.n_features, world)}
-    head = dict(variants["host_in_loop_f32"])
-    head.update({"steps": steps, "pcie_ceiling": ceiling,
-                 "frac_of_pcie_ceiling": head["value"] / ceiling["env_steps_per_s"],
-                 "how": "psk_craft_host_tick_resident (C ABI, pinned host numpy buffers), host in the loop: per step "
+    best = max(("host_in_loop_f32", "host_in_loop_f32_wire_u8"), key=lambda k: variants[k]["value"])
+    head = dict(variants[best])
+    head.update({"steps": steps, "form": best, "pcie_ceiling": ceiling,
+                 "frac_of_pcie_ceiling": variants["host_in_loop_f32"]["value"] / ceiling["env_steps_per_s"],
+                 "vs_f32_frame_over_pcie_ceiling": head["value"] / ceiling["env_steps_per_s"],
+                 "how": "psk_craft_host_tick_resident (C ABI, host numpy buffers), host in the loop: per step "
                         "H2D the actions the host chose (u8[n]), fused step-then-observe tick in %d-env chunks over "
-                        "3 streams, D2H f32 features + teacher actions + done/success of the new states; the "
-                        "environments stay in HBM (e2e_variants: without the action upload, with the state round "
-                        "trip of round 1, with the u8 frame)" % args.e2e_chunk})
+                        "3 streams, f32[n,404] features + teacher actions + done/success of the new states land in "
+                        "host memory; the environments stay in HBM.  form = the faster of host_in_loop_f32 (the "
+                        "f32 frame crosses PCIe; frac_of_pcie_ceiling is that form's) and host_in_loop_f32_wire_u8 "
+                        "(the u8 frame crosses PCIe, host threads widen each chunk to f32 while the next is in "
+                        "flight; same host frame, checked equal in this run).  e2e_variants: both, plus no action "
+                        "upload, the state round trip of round 1, and the raw u8 frame" %
+                        (args.e2e_wire_chunk if best.endswith("wire_u8") else args.e2e_chunk)})
     env.close()
     return {"headline": head, "variants": variants}
 
@@ -875,6 +932,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=16384)
+    ap.add_argument("--e2e-wire-chunk", type=int, default=4096,
+                    help="chunk size of the u8-on-the-wire e2e form (profiles/bench_runs/r2_e2e_wire_sweep.txt)")
     ap.add_argument("--ticks-per-launch", type=int, default=8,
                     help="teacher-driven rollouts run this many ticks per kernel launch (1 = one tick per launch)")
     ap.add_argument("--min-seconds", type=float, default=0.06,

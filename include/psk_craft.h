@@ -276,6 +276,18 @@ int psk_craft_host_tick(psk_craft_host_ctx *ctx, uint8_t *host_grid, uint8_t *ho
 #define PSK_FEATURES_NONE 0
 #define PSK_FEATURES_F32 1
 #define PSK_FEATURES_U8 2
+/* host_features is f32[n][nf] exactly as with PSK_FEATURES_F32, but PCIe carries the u8 frame: it
+ * lands in a pinned buffer the context owns and host threads (env PSK_HOST_THREADS, default
+ * min(8, cores / 2) including the caller) widen each chunk into host_features while the next chunk
+ * is in flight.  host_features need not be pinned.  psk_craft_host_set_threads: the number of
+ * widening threads, the caller included (>= 1; several contexts on one box should share the cores);
+ * psk_craft_host_threads: threads in use (0 before the first such call).
+ * psk_host_widen_u8_f32: the widening alone (dst[i] = src[i]) for callers that keep
+ * PSK_FEATURES_U8 frames; no CUDA call. */
+#define PSK_FEATURES_F32_WIRE_U8 3
+int psk_craft_host_threads(const psk_craft_host_ctx *ctx);
+int psk_craft_host_set_threads(psk_craft_host_ctx *ctx, int32_t threads);
+int psk_host_widen_u8_f32(const uint8_t *src, float *dst, size_t n, int threads);
 int psk_craft_host_reset(psk_craft_host_ctx *ctx, int64_t n);
 int psk_craft_host_put_state(psk_craft_host_ctx *ctx, const uint8_t *host_grid,
                              const uint8_t *host_agent, int64_t n);

@@ -25,9 +25,10 @@ CRAFT_EXPORTS = (
     "psk_random_actions", "psk_craft_rollout", "psk_set_tuning", "psk_get_tuning",
     "psk_craft_features_u8", "psk_craft_host_reset", "psk_craft_host_put_state",
     "psk_craft_host_get_state", "psk_craft_host_tick_resident", "psk_random_actions_block",
-    "psk_craft_tick_u8", "psk_craft_rollout_u8",
+    "psk_craft_tick_u8", "psk_craft_rollout_u8", "psk_craft_host_threads", "psk_craft_host_set_threads",
+    "psk_host_widen_u8_f32",
 )
-FEATURES_NONE, FEATURES_F32, FEATURES_U8 = 0, 1, 2
+FEATURES_NONE, FEATURES_F32, FEATURES_U8, FEATURES_F32_WIRE_U8 = 0, 1, 2, 3
 
 
 class CraftTablesC(ctypes.Structure):
@@ -110,6 +111,9 @@ def load():
     lib.psk_craft_host_put_state.argtypes = [vp, vp, vp, i64]
     lib.psk_craft_host_get_state.argtypes = [vp, vp, vp, i64]
     lib.psk_craft_host_tick_resident.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i64, vp, vp]
+    lib.psk_craft_host_threads.argtypes = [vp]
+    lib.psk_craft_host_set_threads.argtypes = [vp, i32]
+    lib.psk_host_widen_u8_f32.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_int]
     lib.psk_set_tuning.argtypes = [ctypes.c_char_p, i32]
     lib.psk_get_tuning.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32)]
     for name in CRAFT_EXPORTS[1:]:

@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libpsk_b200.so")
-SOURCES = ["psk_craft.cu", "psk_scenario.cu", "psk_light.cu", "psk_host.cu"]
-HEADERS = ["psk_common.cuh", os.path.join("..", "..", "include", "psk_craft.h"),
+SOURCES = ["psk_craft.cu", "psk_scenario.cu", "psk_light.cu", "psk_host.cu", "psk_hostcpu.cpp"]
+HEADERS = ["psk_common.cuh", "psk_hostcpu.h", os.path.join("..", "..", "include", "psk_craft.h"),
            os.path.join("..", "..", "include", "psk_light.h")]
 
 NVCC_FLAGS = [
@@ -15,7 +15,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
 ]
-LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", "-lpthread"]
 OBJ_DIR = os.path.join(HERE, "build")          # git-ignored; objects are rebuilt per source file
 
 
@@ -24,6 +24,10 @@ def nvcc_path():
         if cand and os.path.exists(cand):
             return cand
     return "nvcc"
+
+
+def _obj(src):
+    return os.path.splitext(src)[0] + ".o"
 
 
 def needs_build():
@@ -60,7 +64,7 @@ def build(force=False, verbose=False, out=None, extra=()):
         sp = os.path.join(HERE, src)
         if not os.path.exists(sp):
             continue
-        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, _obj(src))
         if force or out is not None or _stale(obj, [sp] + common):
             cmd = ([nvcc_path()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) +
                    ["-c", "-o", obj, sp])
@@ -69,7 +73,7 @@ def build(force=False, verbose=False, out=None, extra=()):
         for rc in pool.map(lambda c: subprocess.call(c, cwd=HERE), jobs):
             if rc:
                 raise subprocess.CalledProcessError(rc, "nvcc -c")
-    objs = [os.path.join(obj_dir, s.replace(".cu", ".o")) for s in SOURCES
+    objs = [os.path.join(obj_dir, _obj(s)) for s in SOURCES
             if os.path.exists(os.path.join(HERE, s))]
     subprocess.check_call([nvcc_path()] + LINK_FLAGS + ["-o", target] + objs, cwd=HERE)
     return target

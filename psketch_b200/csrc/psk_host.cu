@@ -14,8 +14,10 @@
 #include <cuda_runtime.h>
 
 #include "../../include/psk_craft.h"
+#include "psk_hostcpu.h"
 
 #define PSK_HOST_STREAMS 3
+#define PSK_WIDEN_BLOCK (64u << 10)     // bytes of u8 per widening job (256 KB of f32 written)
 
 struct psk_craft_host_ctx {
     psk_craft_tables tables;
@@ -39,6 +41,13 @@ struct psk_craft_host_ctx {
     uint8_t *r_grid, *r_agent, *r_action, *r_expert, *r_done, *r_success;
     cudaEvent_t ev_in, ev_chunk[PSK_HOST_STREAMS];
     bool resident_ready;
+    // PSK_FEATURES_F32_WIRE_U8: pinned u8 landing zone for the whole batch, one event per chunk,
+    // host threads that widen to the caller's f32 buffer; allocated on first use
+    uint8_t *h_wire;
+    cudaEvent_t *ev_wire;
+    int64_t n_wire_events;
+    PskWidenPool *pool;
+    int host_threads;           // psk_craft_host_set_threads; 0 = PskWidenPool::default_threads()
 };
 
 #define CK(x)                                   \
@@ -133,6 +142,10 @@ void psk_craft_host_destroy(psk_craft_host_ctx *c) {
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     for (int i = 0; i < PSK_HOST_STREAMS; i++)
         if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+    delete c->pool;
+    if (c->h_wire) cudaFreeHost(c->h_wire);
+    for (int64_t i = 0; i < c->n_wire_events; i++) cudaEventDestroy(c->ev_wire[i]);
+    delete[] c->ev_wire;
     delete c;
 }
 
@@ -257,18 +270,41 @@ int psk_craft_host_get_state(psk_craft_host_ctx *c, uint8_t *host_grid, uint8_t 
     return PSK_OK;
 }
 
+static int wire_alloc(psk_craft_host_ctx *c) {
+    const int64_t chunks = (c->max_envs + c->chunk - 1) / c->chunk;
+    const size_t frame = (size_t)c->max_envs * c->nf;
+    if (!c->h_wire) CK(cudaHostAlloc(reinterpret_cast<void **>(&c->h_wire), frame, cudaHostAllocDefault));
+    if (!c->ev_wire) {
+        c->ev_wire = new (std::nothrow) cudaEvent_t[chunks];
+        if (!c->ev_wire) return PSK_ERR_BADARG;
+    }
+    for (; c->n_wire_events < chunks; c->n_wire_events++)
+        CK(cudaEventCreateWithFlags(&c->ev_wire[c->n_wire_events], cudaEventDisableTiming));
+    if (!c->pool) {
+        const int th = c->host_threads > 0 ? c->host_threads - 1 : PskWidenPool::default_threads();
+        c->pool = new (std::nothrow) PskWidenPool(th, frame / PSK_WIDEN_BLOCK + (size_t)chunks + 8);
+    }
+    return c->pool ? PSK_OK : PSK_ERR_BADARG;
+}
+
 int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_action_in,
                                  void *host_features, int32_t feature_format, int32_t advance_first,
                                  uint8_t *host_expert, uint8_t *host_done, uint8_t *host_success,
                                  int64_t n, unsigned long long *host_stats, int32_t *host_err_flags) {
     if (!c || !c->resident_ready || !host_expert || n < 0 || n > c->n_eps) return PSK_ERR_BADARG;
     if (feature_format != PSK_FEATURES_NONE && feature_format != PSK_FEATURES_F32 &&
-        feature_format != PSK_FEATURES_U8)
+        feature_format != PSK_FEATURES_U8 && feature_format != PSK_FEATURES_F32_WIRE_U8)
         return PSK_ERR_BADARG;
     if (!host_features) feature_format = PSK_FEATURES_NONE;
     DeviceScope scope(c->device);
+    const bool wire = feature_format == PSK_FEATURES_F32_WIRE_U8;
+    if (wire) {
+        const int rc = wire_alloc(c);
+        if (rc) return rc;
+    }
     const int cs = c->cell_stride;
-    const size_t fsz = feature_format == PSK_FEATURES_U8 ? 1 : 4;
+    const size_t fsz = (feature_format == PSK_FEATURES_U8 || wire) ? 1 : 4;
+    uint8_t *const landing = wire ? c->h_wire : static_cast<uint8_t *>(host_features);
     cudaStream_t s0 = c->streams[0];
     if (host_action_in) {       // one copy for the whole batch, the other streams wait for it
         CK(cudaMemcpyAsync(c->r_action, host_action_in, (size_t)n, cudaMemcpyHostToDevice, s0));
@@ -285,7 +321,7 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
         const uint8_t *act = host_action_in ? c->r_action + off : nullptr;
         int rc;
         const int mode = advance_first ? PSK_TICK_ADVANCE_FIRST : PSK_TICK_FUSED;
-        if (feature_format == PSK_FEATURES_U8) {
+        if (fsz == 1) {
             // compact frame: the fused kernel writes its u8 tile as it is
             rc = psk_craft_tick_u8(&c->tables, state, ep, act, reinterpret_cast<uint8_t *>(c->d_feat[s]),
                                    c->r_expert + off, c->r_done + off, c->r_success + off, c->d_stats,
@@ -298,8 +334,9 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
         }
         if (rc) return rc;
         if (feature_format != PSK_FEATURES_NONE)
-            CK(cudaMemcpyAsync(static_cast<uint8_t *>(host_features) + (size_t)off * c->nf * fsz, c->d_feat[s],
+            CK(cudaMemcpyAsync(landing + (size_t)off * c->nf * fsz, c->d_feat[s],
                                (size_t)m * c->nf * fsz, cudaMemcpyDeviceToHost, st));
+        if (wire) CK(cudaEventRecord(c->ev_wire[k], st));
     }
     // the per-env byte outputs of the whole batch: one copy each, after every chunk's kernel
     for (int i = 1; i < PSK_HOST_STREAMS; i++) {
@@ -311,12 +348,42 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
     if (host_success) CK(cudaMemcpyAsync(host_success, c->r_success, (size_t)n, cudaMemcpyDeviceToHost, s0));
     if (host_stats || host_err_flags)       // one 40-byte copy into pinned memory (pageable targets would stage)
         CK(cudaMemcpyAsync(c->h_mail, c->d_stats, 40, cudaMemcpyDeviceToHost, s0));
+    if (wire) {
+        // widen chunk k on the host threads as soon as its bytes have landed, while chunks k+1..
+        // are still being computed and copied
+        int done_chunks = 0;
+        cudaError_t err = cudaSuccess;
+        for (int64_t off = 0; off < n && err == cudaSuccess; off += c->chunk, done_chunks++) {
+            const int64_t m = (n - off) < c->chunk ? (n - off) : c->chunk;
+            err = cudaEventSynchronize(c->ev_wire[done_chunks]);
+            if (err == cudaSuccess)
+                c->pool->submit(c->h_wire + (size_t)off * c->nf,
+                                static_cast<float *>(host_features) + (size_t)off * c->nf,
+                                (size_t)m * c->nf, PSK_WIDEN_BLOCK);
+        }
+        c->pool->finish();
+        if (err != cudaSuccess) return PSK_ERR_CUDA;
+    }
     for (int i = 0; i < PSK_HOST_STREAMS; i++) CK(cudaStreamSynchronize(c->streams[i]));
     if (host_stats) memcpy(host_stats, c->h_mail, 4 * sizeof(unsigned long long));
     if (host_err_flags) {
         memcpy(host_err_flags, c->h_mail + 4, sizeof(int32_t));
         if (*host_err_flags) CK(cudaMemset(c->d_err, 0, sizeof(int32_t)));
     }
+    return PSK_OK;
+}
+
+int psk_craft_host_threads(const psk_craft_host_ctx *c) {
+    return c && c->pool ? c->pool->threads() + 1 : 0;
+}
+
+int psk_craft_host_set_threads(psk_craft_host_ctx *c, int32_t threads) {
+    if (!c || threads < 1 || threads > 256) return PSK_ERR_BADARG;
+    if (c->pool && c->pool->threads() + 1 != threads) {     // between calls: no job is outstanding
+        delete c->pool;
+        c->pool = nullptr;
+    }
+    c->host_threads = threads;
     return PSK_OK;
 }
 

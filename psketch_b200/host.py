@@ -6,6 +6,7 @@ CraftState on the CPU): numpy arrays in pinned memory go through ``psk_craft_hos
 several CUDA streams.  No torch tensors cross this boundary.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -40,7 +41,9 @@ class PinnedArray(object):
 
 class HostCraft(object):
     def __init__(self, tables, scen_grids, scen_idx, init_pos, task, init_dir=None,
-                 max_timesteps=40, chunk_envs=16384):
+                 max_timesteps=40, chunk_envs=16384, host_threads=None):
+        """host_threads: threads that widen the u8 wire frame (``features="f32_wire_u8"``), this one
+        included; default min(8, cores / 2) divided among the ranks torchrun started on this box."""
         self.lib = _lib.load()
         self.tables = tables if tables is not None else CraftTables()
         self.ct = _lib.make_tables(self.tables)
@@ -63,6 +66,10 @@ class HostCraft(object):
         _lib.check(self.lib.psk_craft_host_create(ctypes.byref(self.ct), n, chunk_envs,
                                                   ctypes.byref(ctx)), "psk_craft_host_create")
         self.ctx = ctx
+        if host_threads is None:
+            local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            host_threads = max(1, min(8, (os.cpu_count() or 2) // 2 // local))
+        _lib.check(self.lib.psk_craft_host_set_threads(self.ctx, int(host_threads)), "psk_craft_host_set_threads")
         _lib.check(self.lib.psk_craft_host_set_episodes(self.ctx, _np_ptr(sg), len(sg),
                                                         _np_ptr(scen_idx), _np_ptr(ia), n),
                    "psk_craft_host_set_episodes")
@@ -148,22 +155,27 @@ class HostCraft(object):
 
     def tick_resident(self, actions=None, features="f32", advance_first=False):
         """psk_craft_host_tick_resident: only actions go up; features (``"f32"`` -> self.features,
-        ``"u8"`` -> self.features_u8, None), teacher actions and flags come down.
+        ``"u8"`` -> self.features_u8, ``"f32_wire_u8"`` -> self.features again, but PCIe carries the
+        byte frame and host threads widen it; None), teacher actions and flags come down.
         ``advance_first``: step with ``actions`` (None = no step), THEN observe — the order of a host
         policy in the loop: ``a = policy(env.features); env.tick_resident(a, advance_first=True)``."""
         if not self.resident:
             self.upload()
         if actions is not None:
             self.action[:] = actions
-        fmt = {None: _lib.FEATURES_NONE, "f32": _lib.FEATURES_F32, "u8": _lib.FEATURES_U8}[features]
-        buf = self.features if features == "f32" else (self.features_u8 if features == "u8" else None)
+        fmt = {None: _lib.FEATURES_NONE, "f32": _lib.FEATURES_F32, "u8": _lib.FEATURES_U8,
+               "f32_wire_u8": _lib.FEATURES_F32_WIRE_U8}[features]
+        buf = {None: None, "f32": self.features, "f32_wire_u8": self.features}.get(features)
+        if features == "u8":
+            buf = self.features_u8
         rc = self.lib.psk_craft_host_tick_resident(
             self.ctx, _np_ptr(self.action) if actions is not None else None, _np_ptr(buf), fmt,
             1 if advance_first else 0, _np_ptr(self.expert), _np_ptr(self.done), _np_ptr(self.success), self.n,
             _np_ptr(self.stats), _np_ptr(self.err))
         _lib.check(rc, "psk_craft_host_tick_resident")
         self.last_h2d = self.n if actions is not None else 0
-        self.last_d2h = self.n * 3 + (0 if buf is None else buf.nbytes) + 36
+        wire = 0 if buf is None else (buf.nbytes // 4 if features == "f32_wire_u8" else buf.nbytes)
+        self.last_d2h = self.n * 3 + wire + 36
         self._raise_flags()
         return self.expert
 

@@ -148,3 +148,26 @@ def test_c_host_runs_rollouts(tmp_path):
     assert "sm_100a" in out
     assert "episodes=24576 successes=24576 env_steps=98304 err=0" in out, out
     assert out.strip().endswith("teacher: 3 3 4 5 3 3 4 5"), out
+
+
+def test_host_widening_of_byte_frames():
+    """psk_host_widen_u8_f32 (the host half of PSK_FEATURES_F32_WIRE_U8): dst[i] == src[i] for every
+    length and alignment, single-threaded and through the thread pool.  No CUDA call: runs here."""
+    from psketch_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(5)
+    src = rng.randint(0, 256, size=(1 << 22) + 77).astype(np.uint8)
+    dst = np.empty(len(src) + 16, np.float32)
+    for n, so, do, threads in ((0, 0, 0, 1), (1, 3, 1, 1), (31, 1, 3, 1), (404, 0, 0, 1), (4099, 5, 7, 2),
+                               ((1 << 20) + 13, 1, 1, 4), (len(src) - 9, 9, 5, 3), (len(src), 0, 0, 8)):
+        dst[:] = -1.0
+        rc = lib.psk_host_widen_u8_f32(ctypes.c_void_p(src.ctypes.data + so), ctypes.c_void_p(dst.ctypes.data + 4 * do),
+                                       n, threads)
+        assert rc == 0
+        assert np.array_equal(dst[do:do + n], src[so:so + n].astype(np.float32)), (n, so, do, threads)
+        assert (dst[:do] == -1).all() and (dst[do + n:] == -1).all(), (n, so, do, threads)
+    assert lib.psk_host_widen_u8_f32(None, None, 5, 1) != 0
+    for _ in range(20):         # pools are created and joined without leaking or hanging
+        assert lib.psk_host_widen_u8_f32(ctypes.c_void_p(src.ctypes.data), ctypes.c_void_p(dst.ctypes.data),
+                                         1 << 21, 4) == 0
+    assert np.array_equal(dst[:1 << 21], src[:1 << 21].astype(np.float32))

@@ -641,7 +641,7 @@ def test_million_env_rollout_kernel(splits, medium_tables, medium_oracle):
     env.check_errors()
 
 
-@pytest.mark.parametrize("features", ["f32", "u8", None])
+@pytest.mark.parametrize("features", ["f32", "u8", "f32_wire_u8", None])
 def test_host_resident_tick_matches_oracle(features, splits, medium_tables, medium_oracle):
     """psk_craft_host_tick_resident: the environments stay on the device, only actions go up and
     features (f32 or the compact u8 frame) / teacher actions / flags come down; student-style
@@ -658,12 +658,14 @@ def test_host_resident_tick_matches_oracle(features, splits, medium_tables, medi
     orc = _OracleTicks(medium_oracle, grids, ienv, ipos, itask, max_timesteps=17)
     for t in range(40):
         a = rng.choice(6, size=n, p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8) if t % 2 == 0 else None
+        if features == "f32_wire_u8":
+            env.features[:] = -1.0                  # every row must be rewritten by the host threads
         env.tick_resident(actions=a, features=features)
         ref = orc.tick(a)
         assert np.array_equal(env.expert, ref["expert"]), t
         assert np.array_equal(env.done, ref["done"]), t
         assert np.array_equal(env.success, ref["success"]), t
-        if features == "f32":
+        if features in ("f32", "f32_wire_u8"):
             assert np.array_equal(env.features, ref["features"]), t
         elif features == "u8":
             assert np.array_equal(env.features_u8.astype(np.float32), ref["features"]), t
@@ -991,7 +993,7 @@ def test_rollout_kernel_craft_large_vs_oracle(tma, large_tables, large_oracle, l
         _lib.set_tuning(tick_tma=-1)
 
 
-@pytest.mark.parametrize("features", ["f32", "u8"])
+@pytest.mark.parametrize("features", ["f32", "u8", "f32_wire_u8"])
 def test_host_in_the_loop_resident_tick(features, splits, medium_tables, medium_oracle):
     """psk_craft_host_tick_resident in step-then-observe order: the host picks actions from what came
     down (here: random, or the teacher action it was handed), sends them up, and receives the features /
@@ -1002,7 +1004,8 @@ def test_host_in_the_loop_resident_tick(features, splits, medium_tables, medium_
     idx = rng.randint(0, 2200, size=n)
     args = (splits["dev_grids"], splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
             splits["dev_inst_task"][idx])
-    env = HostCraft(medium_tables, *args, max_timesteps=14, chunk_envs=1024)
+    env = HostCraft(medium_tables, *args, max_timesteps=14, chunk_envs=1024,
+                    host_threads=3 if features == "f32_wire_u8" else None)
     env.reset_resident()
     orc = _OracleTicks(medium_oracle, *args, max_timesteps=14)
     o = medium_oracle
@@ -1011,7 +1014,7 @@ def test_host_in_the_loop_resident_tick(features, splits, medium_tables, medium_
         want_e, _, _ = o.expert(orc.grid, orc.inv, orc.pos, orc.dir, orc.task)
         want_f = o.features(orc.grid, orc.inv, orc.pos, orc.dir)
         assert np.array_equal(env.expert.astype(np.int32), want_e), t
-        got_f = env.features if features == "f32" else env.features_u8.astype(np.float32)
+        got_f = env.features if features != "u8" else env.features_u8.astype(np.float32)
         assert np.array_equal(got_f, want_f), t
 
     env.tick_resident(features=features, advance_first=True)      # first observation, no step
@@ -1024,6 +1027,8 @@ def test_host_in_the_loop_resident_tick(features, splits, medium_tables, medium_
         assert np.array_equal(env.done, ref["done"]) and np.array_equal(env.success, ref["success"]), t
         check_observation(t)
     assert tuple(int(x) for x in env.stats[:3]) == tuple(orc.stats)
+    if features == "f32_wire_u8":
+        assert env.lib.psk_craft_host_threads(env.ctx) == 3
     env.close()
 
 
