@@ -869,11 +869,13 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
     # actions, they go UP with every call, the step is applied, the new observation comes DOWN as an
     # f32[n,404] host array — over PCIe as f32, or as bytes widened by host threads (f32_wire_u8)
     for name, fmt in (("host_in_loop_f32", "f32"), ("host_in_loop_f32_wire_u8", "f32_wire_u8")):
-        if fmt == "f32_wire_u8" and args.e2e_wire_chunk != args.e2e_chunk:
+        if fmt == "f32_wire_u8":
             # smaller chunks: the widening of the last chunk is the exposed tail of the pipeline
             env.close()
+            local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            threads = args.e2e_host_threads or max(1, min(8, (os.cpu_count() or 2) // local))
             env = HostCraft(tables, wl["grids"], wl["env"], wl["pos"], wl["task"], max_timesteps=40,
-                            chunk_envs=args.e2e_wire_chunk)
+                            chunk_envs=args.e2e_wire_chunk, host_threads=threads)
         env.reset_resident()
         env.features[:] = -1.0
         env.tick_resident(features=fmt, advance_first=True)        # first observation, no step yet
@@ -932,6 +934,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=16384)
+    ap.add_argument("--e2e-host-threads", type=int, default=0,
+                    help="widening threads per rank of the u8-on-the-wire form; 0 = min(8, cores / ranks on this box)")
     ap.add_argument("--e2e-wire-chunk", type=int, default=4096,
                     help="chunk size of the u8-on-the-wire e2e form (profiles/bench_runs/r2_e2e_wire_sweep.txt)")
     ap.add_argument("--ticks-per-launch", type=int, default=8,
