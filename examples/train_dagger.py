@@ -59,6 +59,7 @@ class Batches(object):
             self.cursor = 0
         rows = torch.from_numpy(self.order[self.cursor:self.cursor + self.batch]).to(self.env.device)
         self.cursor += self.batch
+        self.rows = rows                                    # instance indices of this batch (device)
         env = self.env
         env.scen_idx.copy_(self.d_env[rows])
         env.init_agent[:, 24:26] = self.d_pos[rows]
