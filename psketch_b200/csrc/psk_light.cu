@@ -421,6 +421,7 @@ light_tick_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__
                   uint8_t *__restrict__ success_out, unsigned long long *stats, int max_timesteps,
                   int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned n_done = 0, n_succ = 0, n_live = 0;        // per thread, over its grid-stride iterations
     for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
         const int64_t e = base + (threadIdx.x & 31);
         bool live = e < n, done = false, success = false;
@@ -472,15 +473,27 @@ light_tick_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__
             if (done_out) done_out[e] = done;
             if (success_out) success_out[e] = success;
         }
-        if (stats) {
-            const int nd = __popc(__ballot_sync(0xffffffffu, done));
-            const int ns = __popc(__ballot_sync(0xffffffffu, success));
-            const int nl = __popc(__ballot_sync(0xffffffffu, live));
-            if ((threadIdx.x & 31) == 0) {
-                if (nd) atomicAdd(stats + 0, (unsigned long long)nd);
-                if (ns) atomicAdd(stats + 1, (unsigned long long)ns);
-                if (nl) atomicAdd(stats + 2, (unsigned long long)nl);
-            }
+        n_done += done;
+        n_succ += success;
+        n_live += live;
+    }
+    // statistics: one atomic per counter per BLOCK (per-warp atomics on three addresses serialise in
+    // L2 and were most of the kernel at 1 M envs: 98 k atomics per launch)
+    if (stats) {
+        __shared__ unsigned red[3][8];
+        const unsigned d = __reduce_add_sync(0xffffffffu, n_done);
+        const unsigned sc = __reduce_add_sync(0xffffffffu, n_succ);
+        const unsigned lv = __reduce_add_sync(0xffffffffu, n_live);
+        if ((threadIdx.x & 31) == 0) {
+            red[0][threadIdx.x >> 5] = d;
+            red[1][threadIdx.x >> 5] = sc;
+            red[2][threadIdx.x >> 5] = lv;
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            unsigned tot = 0;
+            for (int w = 0; w < int(blockDim.x >> 5); w++) tot += red[threadIdx.x][w];
+            if (tot) atomicAdd(stats + threadIdx.x, (unsigned long long)tot);
         }
     }
 }
