@@ -281,7 +281,8 @@ int psk_craft_host_tick(psk_craft_host_ctx *ctx, uint8_t *host_grid, uint8_t *ho
  * min(8, cores / 2) including the caller) widen each chunk into host_features while the next chunk
  * is in flight.  host_features need not be pinned.  psk_craft_host_set_threads: the number of
  * widening threads, the caller included (>= 1; several contexts on one box should share the cores);
- * psk_craft_host_threads: threads in use (0 before the first such call).
+ * psk_craft_host_threads: threads in use (0 before the first such call).  A host context is not
+ * thread-safe: one thread at a time may call into it.
  * psk_host_widen_u8_f32: the widening alone (dst[i] = src[i]) for callers that keep
  * PSK_FEATURES_U8 frames; no CUDA call. */
 #define PSK_FEATURES_F32_WIRE_U8 3
