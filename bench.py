@@ -688,6 +688,22 @@ def light_record(torch, dev, peak):
         r = {"tick_us": dt * 1e6, "env_steps_per_s": n / dt, "GBps": 63 * n / dt / 1e9,
              "frac": 63 * n / dt / 1e9 / peak, "teacher_lookup_us": dt_lookup * 1e6,
              "teacher_table_build_ms_wall": build_ms}
+        # T ticks per launch (psk_light_rollout): state, scenario and table pointers stay in registers
+        T = 8
+        slices = max(2, int(np.ceil(1.5 * 126e6 / (n * 48 * T))))          # ring of slices > L2
+        ring = torch.empty((slices * T, n, 12), dtype=torch.float32, device=dev)
+        rout = {}
+
+        def g():
+            k = cnt[0] % slices
+            v.rollout(T, features_out=ring[k * T:(k + 1) * T], out=rout, max_timesteps=100)
+            cnt[0] += 1
+        dt_r = time_kernel(g, torch, inner=slices if slices <= 8 else 8, reps=20) / T
+        b_r = 51 + 12 / T
+        r.update({"rollout_ticks_per_launch": T, "rollout_us_per_tick": dt_r * 1e6,
+                  "rollout_env_steps_per_s": n / dt_r, "rollout_GBps": b_r * n / dt_r / 1e9,
+                  "rollout_frac": b_r * n / dt_r / 1e9 / peak})
+        del ring
         if n == 65536:
             dt_search = time_kernel(lambda: v.expert(search=True), torch, inner=2, reps=3)
             r["teacher_search_kernel_us"] = dt_search * 1e6       # round 1: one flood per env

@@ -56,11 +56,14 @@ int psk_light_expert(const psk_light_scenario *scen, const int32_t *scen_idx,
 
 /* The teacher as a table.  Its answer depends only on (scenario, x, y, keys on the map) — at most
  * 32 x 32 x 2^n_keys states per scenario, shared by all envs of the scenario — so the backward
- * flood of psk_light_expert runs once per scenario (one CTA each) and every later query is a few
- * loads.  Per scenario the table holds u16[1 << max_keys][32][32] — fewest actions to the goal room
+ * flood of psk_light_expert runs once per scenario (one CTA each) and every later query is ONE byte
+ * load.  Per scenario the table holds u16[1 << max_keys][32][32] — fewest actions to the goal room
  * from cell (x, y) with key subset m on the map, 0xFFFF = unreachable — followed by three u8[32][32]
  * per-cell maps (keys locking the door here, keys lying here, doors here) that replace the door / key
- * loops of step and features in the fused tick; psk_light_teacher_table_bytes gives the total size.  psk_light_expert_table answers like psk_light_expert (same actions, same dist). */
+ * loops of step and features in the fused tick, and by u8[1 << max_keys][32][32]: the teacher's action
+ * for every state, derived from the distances when the table is built;
+ * psk_light_teacher_table_bytes gives the total size.  psk_light_expert_table answers like
+ * psk_light_expert (same actions, same dist). */
 int64_t psk_light_teacher_table_bytes(int64_t n_scen, int32_t max_keys);
 int psk_light_teacher_build(const psk_light_scenario *scen, int64_t n_scen, int32_t max_keys,
                             uint16_t *table, void *stream);
@@ -80,6 +83,16 @@ int psk_light_tick(const psk_light_scenario *scen, const int32_t *scen_idx, uint
                    const uint16_t *table, int32_t max_keys, const uint8_t *action_in,
                    float *features_out, uint8_t *expert_out, uint8_t *done_out, uint8_t *success_out,
                    unsigned long long *stats, int32_t max_timesteps, int64_t n, void *stream);
+
+/* `ticks` ticks in ONE launch (the contract of psk_craft_rollout on this world): tick t reads
+ * action_in[t][n] (NULL = follow the teacher), writes expert_out[t][n], done_out[t][n] / success_out[t][n]
+ * (may be NULL) and the feature frame (t % feat_ring) of features_out f32[feat_ring][n][12] (may be
+ * NULL).  The final states equal `ticks` calls of psk_light_tick. */
+int psk_light_rollout(const psk_light_scenario *scen, const int32_t *scen_idx, uint8_t *state,
+                      const uint16_t *table, int32_t max_keys, int32_t ticks, const uint8_t *action_in,
+                      float *features_out, int32_t feat_ring, uint8_t *expert_out, uint8_t *done_out,
+                      uint8_t *success_out, unsigned long long *stats, int32_t max_timesteps, int64_t n,
+                      void *stream);
 
 #ifdef __cplusplus
 }

@@ -124,7 +124,8 @@ def load():
 
 
 LIGHT_EXPORTS = ("psk_light_reset", "psk_light_step", "psk_light_features", "psk_light_satisfies",
-                 "psk_light_expert", "psk_light_teacher_build", "psk_light_expert_table", "psk_light_tick")
+                 "psk_light_expert", "psk_light_teacher_build", "psk_light_expert_table", "psk_light_tick",
+                 "psk_light_rollout")
 _light_bound = False
 
 
@@ -145,6 +146,7 @@ def load_light():
         lib.psk_light_teacher_build.argtypes = [vp, i64, i32, vp, vp]
         lib.psk_light_expert_table.argtypes = [vp, vp, vp, vp, i32, vp, vp, i64, vp]
         lib.psk_light_tick.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i64, vp]
+        lib.psk_light_rollout.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, i32, i64, vp]
         for name in LIGHT_EXPORTS:
             getattr(lib, name).restype = ctypes.c_int
         _light_bound = True

@@ -265,31 +265,38 @@ light_expert_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *
 //   cell_lock[x*32+y]   bitmask of the keys that lock the door at this cell (0: no door here)
 //   cell_keys[x*32+y]   bitmask of the keys lying on this cell
 //   cell_doors[x*32+y]  number of doors at this cell
+// and last the teacher's ANSWER per state, so that a query is one byte load instead of six distance
+// loads and their wall / lock tests:
+//   act u8[layer_cap][32][32]   254 in the goal room, 255 unreachable, else the first action
 #define PSK_LIGHT_AUX_BYTES (3 * 1024)
 __host__ __device__ constexpr size_t light_block_u16(int layer_cap) {
-    return (size_t)layer_cap * 1024 + PSK_LIGHT_AUX_BYTES / 2;
+    return (size_t)layer_cap * 1024 + PSK_LIGHT_AUX_BYTES / 2 + (size_t)layer_cap * 512;
 }
 struct LightAux {
-    const uint8_t *lock, *keys, *doors;
+    const uint8_t *lock, *keys, *doors, *act;
     __device__ __forceinline__ LightAux(const uint16_t *block, int layer_cap) {
         lock = reinterpret_cast<const uint8_t *>(block + (size_t)layer_cap * 1024);
         keys = lock + 1024;
         doors = keys + 1024;
+        act = doors + 1024;
     }
     __device__ __forceinline__ bool locked(int x, int y, uint32_t alive) const {     // light.py:233
         return (lock[(x & 31) * 32 + (y & 31)] & alive) != 0;
     }
 };
 
+__device__ __forceinline__ void light_teacher_flood(const psk_light_scenario &s, uint16_t *T, uint32_t *s_boards,
+                                                    int layer_cap);
+__device__ __forceinline__ int light_action_from_dist(const psk_light_scenario &s, const uint16_t *T,
+                                                      const LightAux &aux, int x, int y, uint32_t alive,
+                                                      int &dist);
+
 __global__ void __launch_bounds__(256)
 light_teacher_build_kernel(const psk_light_scenario *__restrict__ scen, uint16_t *__restrict__ table,
                            int layer_cap) {
     extern __shared__ uint32_t s_boards[];           // [2][layer_cap][32]
     const psk_light_scenario &s = scen[blockIdx.x];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    constexpr unsigned FULL = 0xffffffffu;
-    const int nk = s.n_keys;
-    const int n_layers = 1 << nk;
+    const int n_layers = 1 << s.n_keys;
     uint16_t *T = table + (size_t)blockIdx.x * light_block_u16(layer_cap);
     for (int i = threadIdx.x; i < layer_cap * 1024; i += blockDim.x) T[i] = 0xFFFFu;
     {   // per-cell maps
@@ -309,7 +316,25 @@ light_teacher_build_kernel(const psk_light_scenario *__restrict__ scen, uint16_t
         }
     }
     __syncthreads();
-    if (n_layers > layer_cap) return;               // more keys than announced: everything unreachable
+    // more keys than announced: no flood, everything outside the goal room stays unreachable
+    if (n_layers <= layer_cap) light_teacher_flood(s, T, s_boards, layer_cap);
+    __syncthreads();                                 // the distances of this scenario are complete
+    {   // the teacher's answer for every (key subset, cell), from the distances
+        const LightAux aux(T, layer_cap);
+        uint8_t *A = const_cast<uint8_t *>(aux.act);
+        for (int i = threadIdx.x; i < layer_cap * 1024; i += blockDim.x) {
+            int d;
+            A[i] = (uint8_t)light_action_from_dist(s, T, aux, (i >> 5) & 31, i & 31, (uint32_t)(i >> 10), d);
+        }
+    }
+}
+
+__device__ __forceinline__ void light_teacher_flood(const psk_light_scenario &s, uint16_t *T, uint32_t *s_boards,
+                                                    int layer_cap) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int nk = s.n_keys;
+    const int n_layers = 1 << nk;
     const uint32_t wall_row = s.walls[lane];
     uint32_t goal_row = 0;
     if (lane / PSK_LIGHT_ROOM == s.goal_rx)
@@ -356,11 +381,12 @@ light_teacher_build_kernel(const psk_light_scenario *__restrict__ scen, uint16_t
     }
 }
 
-// Teacher query against the table (thread per env).  dist 0 = in the goal room (action 254),
-// 0xFFFF = unreachable (action 255); else the smallest action whose successor is one level closer.
-__device__ __forceinline__ int light_table_action(const psk_light_scenario &s, const uint16_t *T,
-                                                  const LightAux &aux, int x, int y, uint32_t alive,
-                                                  int &dist) {
+// The teacher's answer from the distances (used ONCE per state, when the table is built).  dist 0 = in
+// the goal room (action 254), 0xFFFF = unreachable (action 255); else the smallest action whose
+// successor is one level closer.
+__device__ __forceinline__ int light_action_from_dist(const psk_light_scenario &s, const uint16_t *T,
+                                                      const LightAux &aux, int x, int y, uint32_t alive,
+                                                      int &dist) {
     if (x / PSK_LIGHT_ROOM == s.goal_rx && y / PSK_LIGHT_ROOM == s.goal_ry && !light_wall(s, x, y)) {
         dist = 0;
         return 254;
@@ -388,6 +414,16 @@ __device__ __forceinline__ int light_table_action(const psk_light_scenario &s, c
     return 255;
 }
 
+// Teacher query against the table (thread per env): one byte load; the distance only on request.
+__device__ __forceinline__ int light_table_action(const LightAux &aux, int x, int y, uint32_t alive) {
+    return aux.act[((alive & 0xFF) * 32 + (x & 31)) * 32 + (y & 31)];
+}
+__device__ __forceinline__ int light_table_dist(const uint16_t *T, int action, int x, int y, uint32_t alive) {
+    if (action == 254) return 0;
+    const int d = T[((alive & 0xFF) * 32 + (x & 31)) * 32 + (y & 31)];
+    return d == 0xFFFF ? -1 : d;
+}
+
 __global__ void __launch_bounds__(256)
 light_expert_table_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
                           const uint8_t *__restrict__ state, const uint16_t *__restrict__ table,
@@ -396,14 +432,14 @@ light_expert_table_kernel(const psk_light_scenario *__restrict__ scen, const int
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int si = scen_idx[e];
-        const psk_light_scenario &s = scen[si];
         const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
-        int d;
         const uint16_t *T = table + (size_t)si * light_block_u16(layer_cap);
         const LightAux aux(T, layer_cap);
-        const int a = light_table_action(s, T, aux, st & 0xFF, (st >> 8) & 0xFF, (st >> 16) & 0xFF, d);
+        const int x = st & 0xFF, y = (st >> 8) & 0xFF;
+        const uint32_t alive = (st >> 16) & 0xFF;
+        const int a = light_table_action(aux, x, y, alive);
         action[e] = (uint8_t)a;
-        if (dist_out) dist_out[e] = (int16_t)d;
+        if (dist_out) dist_out[e] = (int16_t)light_table_dist(T, a, x, y, alive);
     }
 }
 
@@ -413,6 +449,82 @@ light_expert_table_kernel(const psk_light_scenario *__restrict__ scen, const int
 //                          "unreachable" 255) or elapsed >= max_timesteps
 //     done -> success = s.satisfies(goal); s <- LightScenario.init()      !done -> s = s.step(a)
 // state byte 3 counts the steps of the running episode.
+// One env, one tick: teacher action, the three feature values (each is written four times,
+// light.py:191-204), done / success, and the next state word.
+struct LightTickOut {
+    int ref;
+    float locked, open, key;
+    bool done, success;
+    uint32_t next;
+};
+
+__device__ __forceinline__ LightTickOut light_tick_env(const psk_light_scenario &s, const uint16_t *T,
+                                                       const LightAux &aux, uint32_t st, int action_in,
+                                                       int max_timesteps) {
+    LightTickOut o;
+    const int x = st & 0xFF, y = (st >> 8) & 0xFF;
+    const uint32_t alive = (st >> 16) & 0xFF;
+    o.ref = light_table_action(aux, x, y, alive);
+    const int cell = (x & 31) * 32 + (y & 31);
+    const float doors_here = (float)aux.doors[cell];
+    const bool lk = aux.locked(x, y, alive);
+    o.locked = lk ? doors_here : 0.f;
+    o.open = lk ? 0.f : doors_here;
+    o.key = 0.f;
+    if (x % PSK_LIGHT_ROOM != 0 && y % PSK_LIGHT_ROOM != 0)
+        o.key = (float)__popc((uint32_t)aux.keys[cell] & alive);
+    const int a = action_in >= 0 ? action_in : o.ref;
+    const int elapsed = (int)(st >> 24) + 1;
+    o.done = a >= PSK_LIGHT_N_ACTIONS || elapsed >= max_timesteps;
+    o.success = false;
+    if (o.done) {
+        o.success = (x / PSK_LIGHT_ROOM == s.goal_rx) && (y / PSK_LIGHT_ROOM == s.goal_ry);
+        const uint32_t all = s.n_keys >= 8 ? 0xFFu : ((1u << s.n_keys) - 1u);
+        o.next = uint32_t(s.init_x) | (uint32_t(s.init_y) << 8) | (all << 16);
+    } else {
+        uint32_t n_alive = alive;
+        int nx = x, ny = y;
+        if (a < 4) {
+            nx = x + dx_of(a);
+            ny = y + dy_of(a);
+            if (light_wall(s, nx, ny) || aux.locked(nx, ny, alive)) { nx = x; ny = y; }
+        } else {
+            n_alive = alive & ~(uint32_t)aux.keys[cell];
+        }
+        o.next = uint32_t(nx) | (uint32_t(ny) << 8) | (n_alive << 16) | (uint32_t(elapsed) << 24);
+    }
+    return o;
+}
+
+__device__ __forceinline__ void light_store_features(float *row, const LightTickOut &o) {
+    float4 *p = reinterpret_cast<float4 *>(row);
+    __stcs(p, make_float4(o.locked, o.locked, o.locked, o.locked));
+    __stcs(p + 1, make_float4(o.open, o.open, o.open, o.open));
+    __stcs(p + 2, make_float4(o.key, o.key, o.key, o.key));
+}
+
+// statistics: one atomic per counter per BLOCK (per-warp atomics on three addresses serialise in
+// L2 and were a third of the kernel at 1 M envs: 98 k atomics per launch)
+__device__ __forceinline__ void light_block_stats(unsigned long long *stats, unsigned n_done, unsigned n_succ,
+                                                  unsigned n_live) {
+    if (!stats) return;
+    __shared__ unsigned red[3][8];
+    const unsigned d = __reduce_add_sync(0xffffffffu, n_done);
+    const unsigned sc = __reduce_add_sync(0xffffffffu, n_succ);
+    const unsigned lv = __reduce_add_sync(0xffffffffu, n_live);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = d;
+        red[1][threadIdx.x >> 5] = sc;
+        red[2][threadIdx.x >> 5] = lv;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned tot = 0;
+        for (int w = 0; w < int(blockDim.x >> 5); w++) tot += red[threadIdx.x][w];
+        if (tot) atomicAdd(stats + threadIdx.x, (unsigned long long)tot);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 light_tick_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
                   uint8_t *__restrict__ state, const uint16_t *__restrict__ table, int layer_cap,
@@ -422,80 +534,60 @@ light_tick_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__
                   int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned n_done = 0, n_succ = 0, n_live = 0;        // per thread, over its grid-stride iterations
-    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
-        const int64_t e = base + (threadIdx.x & 31);
-        bool live = e < n, done = false, success = false;
-        if (live) {
-            const int si = scen_idx[e];
-            const psk_light_scenario &s = scen[si];
-            const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
-            const int x = st & 0xFF, y = (st >> 8) & 0xFF;
-            const uint32_t alive = (st >> 16) & 0xFF;
-            int d;
-            const uint16_t *T = table + (size_t)si * light_block_u16(layer_cap);
-            const LightAux aux(T, layer_cap);
-            const int ref = light_table_action(s, T, aux, x, y, alive, d);
-            expert_out[e] = (uint8_t)ref;
-            const int cell = (x & 31) * 32 + (y & 31);
-            if (features_out) {                                   // light.py:191-204, see light_features_kernel
-                const float doors_here = (float)aux.doors[cell];
-                const bool lk = aux.locked(x, y, alive);
-                const float locked = lk ? doors_here : 0.f, open = lk ? 0.f : doors_here;
-                float key = 0.f;
-                if (x % PSK_LIGHT_ROOM != 0 && y % PSK_LIGHT_ROOM != 0)
-                    key = (float)__popc((uint32_t)aux.keys[cell] & alive);
-                float4 *o = reinterpret_cast<float4 *>(features_out + e * PSK_LIGHT_N_FEATURES);
-                __stcs(o, make_float4(locked, locked, locked, locked));
-                __stcs(o + 1, make_float4(open, open, open, open));
-                __stcs(o + 2, make_float4(key, key, key, key));
-            }
-            const int a = action_in ? action_in[e] : ref;
-            const int elapsed = (int)(st >> 24) + 1;
-            done = a >= PSK_LIGHT_N_ACTIONS || elapsed >= max_timesteps;
-            uint32_t nst;
-            if (done) {
-                success = (x / PSK_LIGHT_ROOM == s.goal_rx) && (y / PSK_LIGHT_ROOM == s.goal_ry);
-                const uint32_t all = s.n_keys >= 8 ? 0xFFu : ((1u << s.n_keys) - 1u);
-                nst = uint32_t(s.init_x) | (uint32_t(s.init_y) << 8) | (all << 16);
-            } else {
-                uint32_t n_alive = alive;
-                int nx = x, ny = y;
-                if (a < 4) {
-                    nx = x + dx_of(a);
-                    ny = y + dy_of(a);
-                    if (light_wall(s, nx, ny) || aux.locked(nx, ny, alive)) { nx = x; ny = y; }
-                } else {
-                    n_alive = alive & ~(uint32_t)aux.keys[cell];
-                }
-                nst = uint32_t(nx) | (uint32_t(ny) << 8) | (n_alive << 16) | (uint32_t(elapsed) << 24);
-            }
-            reinterpret_cast<uint32_t *>(state)[e] = nst;
-            if (done_out) done_out[e] = done;
-            if (success_out) success_out[e] = success;
-        }
-        n_done += done;
-        n_succ += success;
-        n_live += live;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
+        const int si = scen_idx[e];
+        const uint16_t *T = table + (size_t)si * light_block_u16(layer_cap);
+        const LightAux aux(T, layer_cap);
+        const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
+        const LightTickOut o = light_tick_env(scen[si], T, aux, st, action_in ? (int)action_in[e] : -1,
+                                              max_timesteps);
+        expert_out[e] = (uint8_t)o.ref;
+        if (features_out) light_store_features(features_out + e * PSK_LIGHT_N_FEATURES, o);
+        reinterpret_cast<uint32_t *>(state)[e] = o.next;
+        if (done_out) done_out[e] = o.done;
+        if (success_out) success_out[e] = o.success;
+        n_done += o.done;
+        n_succ += o.success;
+        n_live += 1;
     }
-    // statistics: one atomic per counter per BLOCK (per-warp atomics on three addresses serialise in
-    // L2 and were most of the kernel at 1 M envs: 98 k atomics per launch)
-    if (stats) {
-        __shared__ unsigned red[3][8];
-        const unsigned d = __reduce_add_sync(0xffffffffu, n_done);
-        const unsigned sc = __reduce_add_sync(0xffffffffu, n_succ);
-        const unsigned lv = __reduce_add_sync(0xffffffffu, n_live);
-        if ((threadIdx.x & 31) == 0) {
-            red[0][threadIdx.x >> 5] = d;
-            red[1][threadIdx.x >> 5] = sc;
-            red[2][threadIdx.x >> 5] = lv;
+    light_block_stats(stats, n_done, n_succ, n_live);
+}
+
+// `ticks` rollout ticks in one launch (the Craft rollout's contract, psk_craft_rollout): the state word,
+// the scenario and its table pointers stay in registers; per tick only the outputs are written —
+// row t of expert_out / done_out / success_out and frame t % feat_ring of features_out.
+__global__ void __launch_bounds__(256)
+light_rollout_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
+                     uint8_t *__restrict__ state, const uint16_t *__restrict__ table, int layer_cap,
+                     const uint8_t *__restrict__ action_in, float *__restrict__ features_out, int feat_ring,
+                     uint8_t *__restrict__ expert_out, uint8_t *__restrict__ done_out,
+                     uint8_t *__restrict__ success_out, unsigned long long *stats, int max_timesteps,
+                     int ticks, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned n_done = 0, n_succ = 0, n_live = 0;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
+        const int si = scen_idx[e];
+        const psk_light_scenario &s = scen[si];
+        const uint16_t *T = table + (size_t)si * light_block_u16(layer_cap);
+        const LightAux aux(T, layer_cap);
+        uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
+        for (int t = 0; t < ticks; t++) {
+            const int64_t row = (int64_t)t * n + e;
+            const LightTickOut o = light_tick_env(s, T, aux, st, action_in ? (int)action_in[row] : -1,
+                                                  max_timesteps);
+            expert_out[row] = (uint8_t)o.ref;
+            if (features_out)
+                light_store_features(features_out + ((int64_t)(t % feat_ring) * n + e) * PSK_LIGHT_N_FEATURES, o);
+            if (done_out) done_out[row] = o.done;
+            if (success_out) success_out[row] = o.success;
+            n_done += o.done;
+            n_succ += o.success;
+            st = o.next;
         }
-        __syncthreads();
-        if (threadIdx.x < 3) {
-            unsigned tot = 0;
-            for (int w = 0; w < int(blockDim.x >> 5); w++) tot += red[threadIdx.x][w];
-            if (tot) atomicAdd(stats + threadIdx.x, (unsigned long long)tot);
-        }
+        reinterpret_cast<uint32_t *>(state)[e] = st;
+        n_live += ticks;
     }
+    light_block_stats(stats, n_done, n_succ, n_live);
 }
 
 static inline int lblocks(int64_t n, int per) {
@@ -621,6 +713,23 @@ int psk_light_tick(const psk_light_scenario *scen, const int32_t *scen_idx, uint
     light_tick_kernel<<<lblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
         scen, scen_idx, state, table, 1 << max_keys, action_in, features_out, expert_out, done_out,
         success_out, stats, max_timesteps, n);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
+}
+
+int psk_light_rollout(const psk_light_scenario *scen, const int32_t *scen_idx, uint8_t *state,
+                      const uint16_t *table, int32_t max_keys, int32_t ticks, const uint8_t *action_in,
+                      float *features_out, int32_t feat_ring, uint8_t *expert_out, uint8_t *done_out,
+                      uint8_t *success_out, unsigned long long *stats, int32_t max_timesteps, int64_t n,
+                      void *stream) {
+    if (!light_args_ok(scen, scen_idx, state, n) || (n && (!expert_out || !table)) || max_keys < 0 ||
+        max_keys > PSK_LIGHT_MAX_KEYS || max_timesteps <= 0 || max_timesteps > 255 || ticks < 0 ||
+        (features_out && feat_ring < 1))
+        return PSK_ERR_BADARG;
+    if (features_out && (reinterpret_cast<uintptr_t>(features_out) & 15)) return PSK_ERR_BADARG;
+    if (n == 0 || ticks == 0) return PSK_OK;
+    light_rollout_kernel<<<lblocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        scen, scen_idx, state, table, 1 << max_keys, action_in, features_out, feat_ring, expert_out, done_out,
+        success_out, stats, max_timesteps, ticks, n);
     return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
 }
 

@@ -306,6 +306,33 @@ class VecLight(object):
         _lib.check(rc, "psk_light_tick")
         return out
 
+    def rollout(self, ticks, actions=None, features_out=None, out=None, max_timesteps=100):
+        """``ticks`` rollout ticks in ONE launch (psk_light_rollout).  actions: u8[ticks, N] or None
+        (follow the teacher); features_out: f32[R, N, 12] ring or None (tick t writes frame t % R).
+        Returns dict(expert u8[ticks, N], done, success)."""
+        torch = self.torch
+        actions = self._u8(actions)
+        if out is None:
+            out = {}
+        for k in ("expert", "done", "success"):
+            if k not in out or out[k].shape[0] != ticks:
+                out[k] = torch.empty((ticks, self.n), dtype=torch.uint8, device=self.device)
+        ring = 0
+        if features_out is not None:
+            assert features_out.dim() == 3 and features_out.is_contiguous() and features_out.dtype == torch.float32
+            ring = features_out.shape[0]
+        if getattr(self, "stats", None) is None:
+            self.stats = torch.zeros(4, dtype=torch.int64, device=self.device)
+        table = self.teacher_table()
+        with torch.cuda.device(self.device):
+            rc = self.lib.psk_light_rollout(self._p(self.scen), self._p(self.scen_idx), self._p(self.state),
+                                            self._p(table), self.max_keys, int(ticks), self._p(actions),
+                                            self._p(features_out), ring, self._p(out["expert"]),
+                                            self._p(out["done"]), self._p(out["success"]), self._p(self.stats),
+                                            int(max_timesteps), self.n, self._stream())
+        _lib.check(rc, "psk_light_rollout")
+        return out
+
     def check_errors(self):
         flags = int(self.err.item())
         if flags:

@@ -275,3 +275,50 @@ def test_light_table_and_tick_stay_inside_their_buffers(light_states):
                 assert torch.equal(a[k], b[k]), (n, t, k)
             assert torch.equal(v.state, ref.state)
             assert arena.guards_intact(), (n, t)
+
+
+@pytest.mark.gpu
+def test_light_rollout_equals_ticks(light_states):
+    """psk_light_rollout (T ticks in one launch) against T calls of the oracle-pinned psk_light_tick:
+    teacher-driven and with an action block, feature ring shorter than T, ragged batch sizes, outputs
+    carved out of a canary arena."""
+    import torch
+    from test_bounds_gpu import Arena
+    L = light_states
+    rng = np.random.RandomState(9)
+    n_all = len(_states(L)[0])
+    for n, T, R in ((n_all, 9, 9), (4099, 12, 5), (33, 7, 1), (1, 3, 2)):
+        v, st, scen_idx, state = _vec(L)
+        ref, _, _, _ = _vec(L)
+        sub = np.arange(n) % len(st)
+        for obj in (v, ref):
+            obj.scen_idx = torch.as_tensor(scen_idx[sub].astype(np.int32)).to(obj.device)
+            obj.n = n
+            obj.state = torch.zeros((n, 4), dtype=torch.uint8, device=obj.device)
+            obj.set_state(st[sub])
+            obj.stats = None
+        arena = Arena(n * (4 + R * 48 + 3 * T) + 64 * 1024, v.device)
+        v.state = arena.carve((n, 4), torch.uint8).copy_(v.state)
+        ring = arena.carve((R, n, 12), torch.float32)
+        out = dict(expert=arena.carve((T, n), torch.uint8), done=arena.carve((T, n), torch.uint8),
+                   success=arena.carve((T, n), torch.uint8))
+        for use_actions in (False, True):
+            acts = torch.from_numpy(rng.randint(0, 5, size=(T, n)).astype(np.uint8)).to(v.device) if use_actions else None
+            got = v.rollout(T, actions=acts, features_out=ring, out=out, max_timesteps=11)
+            assert arena.guards_intact()
+            for t in range(T):
+                want = ref.tick(actions=None if acts is None else acts[t], max_timesteps=11)
+                for k in ("expert", "done", "success"):
+                    assert torch.equal(got[k][t], want[k]), (n, t, k)
+                if t >= T - R:                      # frame not overwritten later in the launch
+                    assert torch.equal(ring[t % R], want["features"]), (n, t)
+            assert torch.equal(v.state, ref.state)
+            assert torch.equal(v.stats, ref.stats) and int(v.stats[2]) > 0
+    # no features, no flags
+    got = v.lib.psk_light_rollout(v._p(v.scen), v._p(v.scen_idx), v._p(v.state), v._p(v.teacher_table()), v.max_keys,
+                                  2, None, None, 0, v._p(out["expert"]), None, None, None, 11, v.n, v._stream())
+    assert got == 0
+    for t in range(2):
+        want = ref.tick(max_timesteps=11)
+        assert torch.equal(out["expert"][t], want["expert"])
+    assert torch.equal(v.state, ref.state)
