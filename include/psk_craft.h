@@ -40,6 +40,9 @@ extern "C" {
 #define PSK_FLAG_INV_OVERFLOW 2 /* an inventory count would exceed 255 (u8 storage) */
 #define PSK_FLAG_BAD_LEAF 4     /* teacher: leaf is neither 'use' nor 'go', demonstration.py:18 */
 #define PSK_FLAG_OFF_GRID 8     /* agent position outside the grid */
+#define PSK_FLAG_CHAIN_TIMEOUT 16 /* fused kernels: the previous launch on the same envs never finished
+                                     (aborted launch / overwritten counters); the kernel went on instead
+                                     of hanging, results of that call are not to be trusted */
 
 #define PSK_AGENT_BYTES 32
 #define PSK_AG_X 24
@@ -176,6 +179,12 @@ int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episo
                    const uint8_t *action_in, float *features_out, uint8_t *expert_out,
                    uint8_t *done_out, uint8_t *success_out, unsigned long long *stats,
                    int32_t *err_flags, int fused, void *stream);
+
+/* Testing hook (fault injection for PSK_FLAG_CHAIN_TIMEOUT): takes one ticket of the chaining group
+ * that owns env `env` of this batch and never finishes it, like an aborted launch would.  The next
+ * fused launch on these envs raises PSK_FLAG_CHAIN_TIMEOUT after a few seconds instead of hanging;
+ * the one after that runs normally.  PSK_ERR_UNSUPPORTED if the batch does not chain. */
+int psk_debug_chain_skip_ticket(psk_craft_state s, int64_t env, void *stream);
 
 /* psk_craft_tick with the feature rows as bytes (features_out u8[n][n_features], see
  * psk_craft_features_u8) — same fused kernel, a quarter of the output traffic; order =

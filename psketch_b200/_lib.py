@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpsk_b200.so")
 
 PSK_OK, PSK_ERR_UNSUPPORTED, PSK_ERR_BADARG, PSK_ERR_CUDA = 0, 1, 2, 3
-FLAG_BAD_ACTION, FLAG_INV_OVERFLOW, FLAG_BAD_LEAF, FLAG_OFF_GRID = 1, 2, 4, 8
+FLAG_BAD_ACTION, FLAG_INV_OVERFLOW, FLAG_BAD_LEAF, FLAG_OFF_GRID, FLAG_CHAIN_TIMEOUT = 1, 2, 4, 8, 16
 AGENT_BYTES = 32
 AG_X, AG_Y, AG_DIR, AG_TASK, AG_TIMER = 24, 25, 26, 27, 28
 MAX_INV = 24
@@ -26,7 +26,7 @@ CRAFT_EXPORTS = (
     "psk_craft_features_u8", "psk_craft_host_reset", "psk_craft_host_put_state",
     "psk_craft_host_get_state", "psk_craft_host_tick_resident", "psk_random_actions_block",
     "psk_craft_tick_u8", "psk_craft_rollout_u8", "psk_craft_host_threads", "psk_craft_host_set_threads",
-    "psk_host_widen_u8_f32",
+    "psk_host_widen_u8_f32", "psk_debug_chain_skip_ticket",
 )
 FEATURES_NONE, FEATURES_F32, FEATURES_U8, FEATURES_F32_WIRE_U8 = 0, 1, 2, 3
 
@@ -111,6 +111,7 @@ def load():
     lib.psk_craft_host_put_state.argtypes = [vp, vp, vp, i64]
     lib.psk_craft_host_get_state.argtypes = [vp, vp, vp, i64]
     lib.psk_craft_host_tick_resident.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i64, vp, vp]
+    lib.psk_debug_chain_skip_ticket.argtypes = [CraftStateC, i64, vp]
     lib.psk_craft_host_threads.argtypes = [vp]
     lib.psk_craft_host_set_threads.argtypes = [vp, i32]
     lib.psk_host_widen_u8_f32.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_int]

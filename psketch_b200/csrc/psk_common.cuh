@@ -194,13 +194,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 __device__ __forceinline__ uint32_t chain_enter(uint32_t *chain, int64_t g) {
     return atomicAdd(chain + 2 * g, 1u);
 }
-__device__ __forceinline__ void chain_wait(const uint32_t *chain, int64_t g, uint32_t ticket) {
+// Returns false if the predecessor did not finish within PSK_CHAIN_SPIN_LIMIT polls (seconds; a healthy
+// wait is microseconds): something outside this scheme went wrong — a previous launch on these envs was
+// aborted, or the counters were overwritten.  The caller raises PSK_FLAG_CHAIN_TIMEOUT and goes on
+// instead of hanging the GPU; its chain_leave puts the counter back in step for its successors.
+#define PSK_CHAIN_SPIN_LIMIT (1u << 22)
+__device__ __forceinline__ bool chain_wait(const uint32_t *chain, int64_t g, uint32_t ticket) {
     uint32_t v;
-    while (true) {
+    for (uint32_t spins = 0; spins < PSK_CHAIN_SPIN_LIMIT; spins++) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(chain + 2 * g + 1) : "memory");
-        if (v == ticket) break;
+        if (v == ticket) return true;
         __nanosleep(64);
     }
+    return false;
 }
 __device__ __forceinline__ void chain_leave(uint32_t *chain, int64_t g, uint32_t ticket) {
     // st.release.gpu IS fence + store (SASS: MEMBAR.ALL.GPU; ST): with the CTA barrier before it, it

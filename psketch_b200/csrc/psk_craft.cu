@@ -1680,7 +1680,8 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
     for (int k = 0; k < (TW + NT - 1) / NT; k++)
         if (tid + k * NT < TW) reinterpret_cast<uint4 *>(st.words)[tid + k * NT] = tv[k];
     if (chain) {
-        if (chain_thread) chain_wait(chain, grp(tid), s_ticket[tid]);
+        if (chain_thread && !chain_wait(chain, grp(tid), s_ticket[tid]) && err_flags)
+            atomicOr(err_flags, PSK_FLAG_CHAIN_TIMEOUT);
         __syncthreads();            // nobody touches the state before the chain threads' acquire
     } else {
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1871,7 +1872,8 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
             smem_u32(smem_raw) + (uint32_t)((tid - NEW) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
             nf);
     if (chain) {
-        if (chain_thread) chain_wait(chain, grp(tid), s_ticket[tid]);
+        if (chain_thread && !chain_wait(chain, grp(tid), s_ticket[tid]) && err_flags)
+            atomicOr(err_flags, PSK_FLAG_CHAIN_TIMEOUT);
         __syncthreads();
     } else {
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -2604,6 +2606,22 @@ int psk_craft_tick(const psk_craft_tables *t, psk_craft_state s, psk_craft_episo
     }
     const uint8_t *act = action_in ? action_in : expert_out;
     PSK_DISPATCH(t, advance(t, s, ep, act, done_out, success_out, stats, err_flags, st));
+}
+
+// Fault injection for the tile-chaining safety net (tests only): hands out one ticket of the group that
+// owns env `env` of this batch without ever finishing it — what an aborted launch leaves behind.  The
+// next fused launch on these envs must time out on that group (PSK_FLAG_CHAIN_TIMEOUT), not hang, and
+// leave the counters in step again.
+__global__ void chain_skip_ticket_kernel(uint32_t *chain, int64_t g) { atomicAdd(chain + 2 * g, 1u); }
+
+int psk_debug_chain_skip_ticket(psk_craft_state s, int64_t env, void *stream) {
+    if (env < 0 || env >= s.n || !s.agent) return PSK_ERR_BADARG;
+    int64_t g0 = 0;
+    uint32_t *chain = chain_counters(s, &g0);
+    if (!chain) return PSK_ERR_UNSUPPORTED;          // this batch does not chain
+    const int64_t g = (g0 + env / PSK_CHAIN_GROUP) & (PSK_CHAIN_GROUPS - 1);
+    chain_skip_ticket_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(chain, g);
+    return cudaGetLastError() == cudaSuccess ? PSK_OK : PSK_ERR_CUDA;
 }
 
 int psk_craft_tick_u8(const psk_craft_tables *t, psk_craft_state s, psk_craft_episodes ep,

@@ -99,6 +99,9 @@ class HostCraft(object):
         if not flags:
             return
         self.err[0] = 0
+        if flags & _lib.FLAG_CHAIN_TIMEOUT:   # before anything else: the outputs of that call are suspect
+            raise _lib.PskError("tile chain timeout: a previous fused launch on these envs never finished "
+                                "(aborted launch?); the kernel went on instead of hanging")
         if flags & _lib.FLAG_BAD_LEAF:        # the teacher speaks before the step (imitation.py:53,72)
             raise AssertionError("teacher: subtask is neither 'use' nor 'go', or every subtask of an "
                                  "unsatisfied task is satisfied")  # demonstration.py:18, base.py:23-24

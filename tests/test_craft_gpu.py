@@ -1089,3 +1089,48 @@ def test_u8_frame_through_the_fused_kernels(which, n, splits, medium_tables, med
         assert np.array_equal(_np(ring[t]).astype(np.float32), ref["features"]), t
     orc.assert_state_equals(env)
     env.check_errors()
+
+
+def test_stuck_tile_chain_times_out_instead_of_hanging(splits, medium_tables, medium_oracle):
+    """Safety net of the tile chaining: a ticket that is never finished (what an aborted launch leaves
+    behind; injected with psk_debug_chain_skip_ticket) makes the next fused launch raise
+    PSK_FLAG_CHAIN_TIMEOUT after a few seconds — it must not hang the GPU — and the chain is in step
+    again afterwards: later ticks match the oracle."""
+    import time
+    from psketch_b200 import _lib
+    from psketch_b200.vec import VecCraft
+    n = 4096
+    rng = np.random.RandomState(21)
+    idx = rng.randint(0, 2200, size=n)
+    args = (splits["dev_grids"], splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx], splits["dev_inst_task"][idx])
+    env = VecCraft.from_instances(medium_tables, *args, max_timesteps=17)
+    orc = _OracleTicks(medium_oracle, *args, max_timesteps=17)
+    for t in range(3):
+        out, ref = env.tick(), orc.tick()
+        assert np.array_equal(_np(out["expert"]), ref["expert"])
+    env.check_errors()
+    with torch.cuda.device(env.device):
+        rc = env.lib.psk_debug_chain_skip_ticket(env._state(), 1234, env._stream())
+    if rc == 1:                                        # PSK_ERR_UNSUPPORTED
+        pytest.skip("this batch does not chain (tuning knob off)")
+    assert rc == 0
+    t0 = time.time()
+    out = env.tick()                                   # group of env 1234 waits for a holder that never comes
+    torch.cuda.synchronize()
+    waited = time.time() - t0
+    assert 0.05 < waited < 60.0, waited
+    with pytest.raises(_lib.PskError, match="tile chain timeout"):
+        env.check_errors()
+    ref = orc.tick()                                   # the predecessor it waited for never existed: results fine
+    assert np.array_equal(_np(out["expert"]), ref["expert"])
+    for t in range(4):                                 # back in step: no further waits, no flags
+        t0 = time.time()
+        out, ref = env.tick(), orc.tick()
+        torch.cuda.synchronize()
+        assert time.time() - t0 < 0.05
+        assert np.array_equal(_np(out["expert"]), ref["expert"]) and np.array_equal(_np(out["done"]), ref["done"])
+    out = env.rollout(5)
+    for t in range(5):
+        assert np.array_equal(_np(out["expert"][t]), orc.tick()["expert"])
+    env.check_errors()
+    orc.assert_state_equals(env)
