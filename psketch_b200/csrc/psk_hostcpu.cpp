@@ -49,7 +49,13 @@ void psk_widen_u8_f32(const uint8_t *src, float *dst, size_t n) {
 // ---------------------------------------------------------------------------------------------------
 
 PskWidenPool::PskWidenPool(int n_threads, size_t capacity) : ring_(capacity) {
-    for (int i = 0; i < n_threads; i++) workers_.emplace_back([this] { worker(); });
+    for (int i = 0; i < n_threads; i++) {
+        try {
+            workers_.emplace_back([this] { worker(); });
+        } catch (...) {         // thread limit reached: go on with the workers that started (the
+            break;              // calling thread widens too, so zero workers still works)
+        }
+    }
 }
 
 PskWidenPool::~PskWidenPool() {
