@@ -3,6 +3,23 @@
 #include "psk_common.cuh"
 #include "../../include/psk_light.h"
 
+// Resident blocks of 256 threads per SM asked of the compiler (same-box A/B at 1 M envs,
+// profiles/README.md): the table lookup alone gains from 8 (32 registers: 6.25 -> 5.45 us); the fused
+// tick is best at 6 (42 registers: 15.5 us; natural 56 registers 17.95, 5 blocks 16.8, 8 blocks spill:
+// 18.4), the rollout at 5 (11.5 us per tick; natural 12.4, 6 blocks 11.6, 8 blocks 12.8).
+#ifndef PSK_LIGHT_MINBLOCKS
+#define PSK_LIGHT_MINBLOCKS 6
+#endif
+#ifndef PSK_LIGHT_ROLLOUT_MINBLOCKS
+#define PSK_LIGHT_ROLLOUT_MINBLOCKS 5
+#endif
+#ifndef PSK_LIGHT_LOOKUP_MINBLOCKS
+#define PSK_LIGHT_LOOKUP_MINBLOCKS 8
+#endif
+#ifndef PSK_LIGHT_COALESCED
+#define PSK_LIGHT_COALESCED 1
+#endif
+
 namespace psk {
 
 __device__ __forceinline__ bool light_wall(const psk_light_scenario &s, int x, int y) {
@@ -424,7 +441,7 @@ __device__ __forceinline__ int light_table_dist(const uint16_t *T, int action, i
     return d == 0xFFFF ? -1 : d;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PSK_LIGHT_LOOKUP_MINBLOCKS)
 light_expert_table_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
                           const uint8_t *__restrict__ state, const uint16_t *__restrict__ table,
                           int layer_cap, uint8_t *__restrict__ action, int16_t *__restrict__ dist_out,
@@ -496,11 +513,31 @@ __device__ __forceinline__ LightTickOut light_tick_env(const psk_light_scenario 
     return o;
 }
 
-__device__ __forceinline__ void light_store_features(float *row, const LightTickOut &o) {
-    float4 *p = reinterpret_cast<float4 *>(row);
-    __stcs(p, make_float4(o.locked, o.locked, o.locked, o.locked));
-    __stcs(p + 1, make_float4(o.open, o.open, o.open, o.open));
-    __stcs(p + 2, make_float4(o.key, o.key, o.key, o.key));
+// The 12 feature floats of the 32 envs of a warp are 1,536 contiguous bytes.  Written per env (three
+// float4 at a stride of 48 bytes) every store instruction touches 48 sectors for 512 bytes; instead the
+// three values of each env are redistributed with shuffles so that every instruction writes 512
+// contiguous bytes.  All 32 lanes must call this (cnt = envs of this warp that exist).
+__device__ __forceinline__ void light_store_features_warp(float *warp_rows, const LightTickOut &o, int cnt) {
+    const int lane = threadIdx.x & 31;
+#if PSK_LIGHT_COALESCED
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int q = j * 32 + lane;                // float4 index among the warp's 96
+        const int src = q / 3, part = q - src * 3;
+        const float a = __shfl_sync(0xffffffffu, o.locked, src);
+        const float b = __shfl_sync(0xffffffffu, o.open, src);
+        const float c = __shfl_sync(0xffffffffu, o.key, src);
+        const float v = part == 0 ? a : (part == 1 ? b : c);
+        if (src < cnt) __stcs(reinterpret_cast<float4 *>(warp_rows) + q, make_float4(v, v, v, v));
+    }
+#else
+    if (lane < cnt) {
+        float4 *p = reinterpret_cast<float4 *>(warp_rows + lane * PSK_LIGHT_N_FEATURES);
+        __stcs(p, make_float4(o.locked, o.locked, o.locked, o.locked));
+        __stcs(p + 1, make_float4(o.open, o.open, o.open, o.open));
+        __stcs(p + 2, make_float4(o.key, o.key, o.key, o.key));
+    }
+#endif
 }
 
 // statistics: one atomic per counter per BLOCK (per-warp atomics on three addresses serialise in
@@ -525,7 +562,7 @@ __device__ __forceinline__ void light_block_stats(unsigned long long *stats, uns
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PSK_LIGHT_MINBLOCKS)
 light_tick_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
                   uint8_t *__restrict__ state, const uint16_t *__restrict__ table, int layer_cap,
                   const uint8_t *__restrict__ action_in, float *__restrict__ features_out,
@@ -534,21 +571,26 @@ light_tick_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__
                   int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned n_done = 0, n_succ = 0, n_live = 0;        // per thread, over its grid-stride iterations
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
-        const int si = scen_idx[e];
-        const uint16_t *T = table + (size_t)si * light_block_u16(layer_cap);
-        const LightAux aux(T, layer_cap);
-        const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
-        const LightTickOut o = light_tick_env(scen[si], T, aux, st, action_in ? (int)action_in[e] : -1,
-                                              max_timesteps);
-        expert_out[e] = (uint8_t)o.ref;
-        if (features_out) light_store_features(features_out + e * PSK_LIGHT_N_FEATURES, o);
-        reinterpret_cast<uint32_t *>(state)[e] = o.next;
-        if (done_out) done_out[e] = o.done;
-        if (success_out) success_out[e] = o.success;
-        n_done += o.done;
-        n_succ += o.success;
-        n_live += 1;
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+        const int64_t e = base + (threadIdx.x & 31);
+        LightTickOut o = {};
+        if (e < n) {
+            const int si = scen_idx[e];
+            const uint16_t *T = table + (size_t)si * light_block_u16(layer_cap);
+            const LightAux aux(T, layer_cap);
+            const uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
+            o = light_tick_env(scen[si], T, aux, st, action_in ? (int)action_in[e] : -1, max_timesteps);
+            expert_out[e] = (uint8_t)o.ref;
+            reinterpret_cast<uint32_t *>(state)[e] = o.next;
+            if (done_out) done_out[e] = o.done;
+            if (success_out) success_out[e] = o.success;
+            n_done += o.done;
+            n_succ += o.success;
+            n_live += 1;
+        }
+        if (features_out)
+            light_store_features_warp(features_out + base * PSK_LIGHT_N_FEATURES, o,
+                                      (int)(n - base < 32 ? n - base : 32));
     }
     light_block_stats(stats, n_done, n_succ, n_live);
 }
@@ -556,7 +598,7 @@ light_tick_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__
 // `ticks` rollout ticks in one launch (the Craft rollout's contract, psk_craft_rollout): the state word,
 // the scenario and its table pointers stay in registers; per tick only the outputs are written —
 // row t of expert_out / done_out / success_out and frame t % feat_ring of features_out.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PSK_LIGHT_ROLLOUT_MINBLOCKS)
 light_rollout_kernel(const psk_light_scenario *__restrict__ scen, const int32_t *__restrict__ scen_idx,
                      uint8_t *__restrict__ state, const uint16_t *__restrict__ table, int layer_cap,
                      const uint8_t *__restrict__ action_in, float *__restrict__ features_out, int feat_ring,
@@ -565,27 +607,35 @@ light_rollout_kernel(const psk_light_scenario *__restrict__ scen, const int32_t 
                      int ticks, int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned n_done = 0, n_succ = 0, n_live = 0;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += stride) {
-        const int si = scen_idx[e];
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+        const int64_t e = base + (threadIdx.x & 31);
+        const bool live = e < n;
+        const int cnt = (int)(n - base < 32 ? n - base : 32);
+        const int si = live ? scen_idx[e] : 0;
         const psk_light_scenario &s = scen[si];
         const uint16_t *T = table + (size_t)si * light_block_u16(layer_cap);
         const LightAux aux(T, layer_cap);
-        uint32_t st = reinterpret_cast<const uint32_t *>(state)[e];
+        uint32_t st = live ? reinterpret_cast<const uint32_t *>(state)[e] : 0u;
         for (int t = 0; t < ticks; t++) {
             const int64_t row = (int64_t)t * n + e;
-            const LightTickOut o = light_tick_env(s, T, aux, st, action_in ? (int)action_in[row] : -1,
-                                                  max_timesteps);
-            expert_out[row] = (uint8_t)o.ref;
+            LightTickOut o = {};
+            if (live) {
+                o = light_tick_env(s, T, aux, st, action_in ? (int)action_in[row] : -1, max_timesteps);
+                expert_out[row] = (uint8_t)o.ref;
+                if (done_out) done_out[row] = o.done;
+                if (success_out) success_out[row] = o.success;
+                n_done += o.done;
+                n_succ += o.success;
+                st = o.next;
+            }
             if (features_out)
-                light_store_features(features_out + ((int64_t)(t % feat_ring) * n + e) * PSK_LIGHT_N_FEATURES, o);
-            if (done_out) done_out[row] = o.done;
-            if (success_out) success_out[row] = o.success;
-            n_done += o.done;
-            n_succ += o.success;
-            st = o.next;
+                light_store_features_warp(features_out + ((int64_t)(t % feat_ring) * n + base) * PSK_LIGHT_N_FEATURES,
+                                          o, cnt);
         }
-        reinterpret_cast<uint32_t *>(state)[e] = st;
-        n_live += ticks;
+        if (live) {
+            reinterpret_cast<uint32_t *>(state)[e] = st;
+            n_live += ticks;
+        }
     }
     light_block_stats(stats, n_done, n_succ, n_live);
 }
