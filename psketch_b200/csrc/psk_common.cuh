@@ -199,14 +199,26 @@ __device__ __forceinline__ uint32_t chain_enter(uint32_t *chain, int64_t g) {
 // aborted, or the counters were overwritten.  The caller raises PSK_FLAG_CHAIN_TIMEOUT and goes on
 // instead of hanging the GPU; its chain_leave puts the counter back in step for its successors.
 #define PSK_CHAIN_SPIN_LIMIT (1u << 22)
+#ifndef PSK_CHAIN_BOUNDED
+#define PSK_CHAIN_BOUNDED 1
+#endif
 __device__ __forceinline__ bool chain_wait(const uint32_t *chain, int64_t g, uint32_t ticket) {
     uint32_t v;
+#if PSK_CHAIN_BOUNDED
+#pragma unroll 1        // unrolled (nvcc does, 16 x) the single tick loses 0.8 us: keep the poll loop tight
     for (uint32_t spins = 0; spins < PSK_CHAIN_SPIN_LIMIT; spins++) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(chain + 2 * g + 1) : "memory");
         if (v == ticket) return true;
         __nanosleep(64);
     }
     return false;
+#else
+    while (true) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(chain + 2 * g + 1) : "memory");
+        if (v == ticket) return true;
+        __nanosleep(64);
+    }
+#endif
 }
 __device__ __forceinline__ void chain_leave(uint32_t *chain, int64_t g, uint32_t ticket) {
     // st.release.gpu IS fence + store (SASS: MEMBAR.ALL.GPU; ST): with the CTA barrier before it, it

@@ -1664,6 +1664,7 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
 #pragma unroll
     for (int k = 0; k < (TW + NT - 1) / NT; k++)
         if (tid + k * NT < TW) tv[k] = __ldg(reinterpret_cast<const uint4 *>(T) + tid + k * NT);
+    uint32_t flags = 0;             // PSK_FLAG_* seen by this thread, OR-ed into *err_flags at the end
     if (chain) {
         if (chain_thread) s_ticket[tid] = chain_enter(chain, grp(tid));
         __syncthreads();
@@ -1680,14 +1681,12 @@ craft_tick_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict__ 
     for (int k = 0; k < (TW + NT - 1) / NT; k++)
         if (tid + k * NT < TW) reinterpret_cast<uint4 *>(st.words)[tid + k * NT] = tv[k];
     if (chain) {
-        if (chain_thread && !chain_wait(chain, grp(tid), s_ticket[tid]) && err_flags)
-            atomicOr(err_flags, PSK_FLAG_CHAIN_TIMEOUT);
+        if (chain_thread && !chain_wait(chain, grp(tid), s_ticket[tid])) flags = PSK_FLAG_CHAIN_TIMEOUT;
         __syncthreads();            // nobody touches the state before the chain threads' acquire
     } else {
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
     // (without chaining the tables become visible with the barrier that follows the state load)
-    uint32_t flags = 0;
     int it = 0;  // this feature warp's chunk counter
     const int64_t n_super = (n + NE - 1) / NE;
     for (int64_t sp = blockIdx.x; sp < n_super; sp += gridDim.x) {
@@ -1861,6 +1860,7 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
     auto grp = [&](int j) { return (chain_g0 + grp0 + j) & (PSK_CHAIN_GROUPS - 1); };
     const bool chain_thread = chain && tid < NE / PSK_CHAIN_GROUP &&
                               (grp0 + tid) * PSK_CHAIN_GROUP < n;
+    uint32_t flags = 0;
     if (chain) {
         if (chain_thread) s_ticket[tid] = chain_enter(chain, grp(tid));
         __syncthreads();
@@ -1872,13 +1872,11 @@ craft_rollout_kernel(const psk_craft_tables *__restrict__ T, uint8_t *__restrict
             smem_u32(smem_raw) + (uint32_t)((tid - NEW) >> 5) * feature_buffer_bytes(false, 4, nf, PSK_ESZ_FUSED_KERNELS),
             nf);
     if (chain) {
-        if (chain_thread && !chain_wait(chain, grp(tid), s_ticket[tid]) && err_flags)
-            atomicOr(err_flags, PSK_FLAG_CHAIN_TIMEOUT);
+        if (chain_thread && !chain_wait(chain, grp(tid), s_ticket[tid])) flags = PSK_FLAG_CHAIN_TIMEOUT;
         __syncthreads();
     } else {
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
-    uint32_t flags = 0;
     int it = 0;
     const int64_t n_super = (n + NE - 1) / NE;
     for (int64_t sp = blockIdx.x; sp < n_super; sp += gridDim.x) {
