@@ -853,31 +853,48 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
     steps = max(3, min(args.steps, 30))
 
     def timed(fn, reps):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
+        """Wall time of `reps` calls after 3 untimed ones, MAX over ranks.  fn=None, or an exception
+        inside fn on ANY rank, gives inf on EVERY rank (the collectives are still executed, so no
+        rank is left waiting): an optional form that fails is dropped, it does not take the run down."""
+        ok = fn is not None
+        try:
+            for _ in range(3 if ok else 0):
+                fn()
+            torch.cuda.synchronize()
+        except Exception as ex:  # noqa: BLE001
+            ok, timed.error = False, repr(ex)
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(reps):
-            fn()                        # returns after the D2H copies have landed
-        wall = time.perf_counter() - t0
+        try:
+            for _ in range(reps if ok else 0):
+                fn()                    # returns after the D2H copies have landed
+        except Exception as ex:  # noqa: BLE001
+            ok, timed.error = False, repr(ex)
+        wall = time.perf_counter() - t0 if ok else float("inf")
         if dist is not None:
             w = torch.tensor([wall], dtype=torch.float64, device=dev)
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
             wall = float(w.item())
         return wall
 
+    timed.error = None
+
+    def timed_or_raise(fn, reps):
+        wall = timed(fn, reps)
+        if wall == float("inf"):
+            raise RuntimeError("e2e leg failed: %s" % (timed.error or "on another rank"))
+        return wall
     variants = {}
     before = int(env.stats[2])
-    wall = timed(env.tick, steps)
+    wall = timed_or_raise(env.tick, steps)
     assert int(env.stats[2]) - before == (steps + 3) * n
     variants["roundtrip_f32"] = {"value": n * steps * world / wall, "unit": UNIT,
                                  "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
     env.reset_resident()
     for name, fmt in (("resident_f32", "f32"), ("resident_u8", "u8")):
         before = int(env.stats[2])
-        wall = timed(lambda: env.tick_resident(features=fmt), steps)
+        wall = timed_or_raise(lambda: env.tick_resident(features=fmt), steps)
         assert int(env.stats[2]) - before == (steps + 3) * n
         variants[name] = {"value": n * steps * world / wall, "unit": UNIT,
                           "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
@@ -885,39 +902,60 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
     # actions, they go UP with every call, the step is applied, the new observation comes DOWN as an
     # f32[n,404] host array — over PCIe as f32, or as bytes widened by host threads (f32_wire_u8)
     for name, fmt in (("host_in_loop_f32", "f32"), ("host_in_loop_f32_wire_u8", "f32_wire_u8")):
-        if fmt == "f32_wire_u8":
-            # smaller chunks: the widening of the last chunk is the exposed tail of the pipeline
-            env.close()
-            local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-            threads = args.e2e_host_threads or max(1, min(8, (os.cpu_count() or 2) // local))
-            env = HostCraft(tables, wl["grids"], wl["env"], wl["pos"], wl["task"], max_timesteps=40,
-                            chunk_envs=args.e2e_wire_chunk, host_threads=threads)
-        env.reset_resident()
-        env.features[:] = -1.0
-        env.tick_resident(features=fmt, advance_first=True)        # first observation, no step yet
-        acts = env.expert.copy()
+        optional = fmt != "f32"         # the wire form may fail (then it is dropped); the f32 form may not
+        step_fn, before = None, 0
+        try:
+            if fmt == "f32_wire_u8":
+                # smaller chunks: the widening of the last chunk is the exposed tail of the pipeline
+                env.close()
+                local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+                threads = args.e2e_host_threads or max(1, min(8, (os.cpu_count() or 2) // local))
+                env = HostCraft(tables, wl["grids"], wl["env"], wl["pos"], wl["task"], max_timesteps=40,
+                                chunk_envs=args.e2e_wire_chunk, host_threads=threads)
+            env.reset_resident()
+            env.features[:] = -1.0
+            env.tick_resident(features=fmt, advance_first=True)        # first observation, no step yet
+            acts = env.expert.copy()
 
-        def host_loop_step():
-            env.tick_resident(actions=acts, features=fmt, advance_first=True)
-            acts[:] = env.expert                                    # the host "policy": np copy of n bytes
+            def step_fn(fmt=fmt, acts=acts):
+                env.tick_resident(actions=acts, features=fmt, advance_first=True)
+                acts[:] = env.expert                                    # the host "policy": np copy of n bytes
 
-        before = int(env.stats[2])
-        wall = timed(host_loop_step, steps)
-        assert int(env.stats[2]) - before == (steps + 3) * n
+            before = int(env.stats[2])
+        except Exception as ex:  # noqa: BLE001
+            if not optional:
+                raise
+            step_fn, timed.error = None, repr(ex)
+        wall = timed(step_fn, steps)
+        if wall == float("inf"):
+            if not optional:
+                raise RuntimeError("e2e leg %s failed: %s" % (name, timed.error))
+            variants[name] = {"value": 0.0, "unit": UNIT, "error": timed.error or "failed on another rank"}
+            continue
+        counted = int(env.stats[2]) - before == (steps + 3) * n
         variants[name] = {"value": n * steps * world / wall, "unit": UNIT,
                           "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
         if fmt == "f32":
+            assert counted
             frame_f32 = env.features.copy()
-            state_f32 = (env.expert.copy(), env.done.copy(), int(env.stats[2]) - before)
+            state_f32 = (env.expert.copy(), env.done.copy())
         else:   # both forms ran the same number of steps from the same reset: identical host frames
-            assert np.array_equal(env.features, frame_f32) and np.array_equal(env.expert, state_f32[0])
+            same = bool(counted and np.array_equal(env.features, frame_f32) and
+                        np.array_equal(env.expert, state_f32[0]))
+            if dist is not None:         # every rank's frame must agree, not only rank 0's
+                flag = torch.tensor([1.0 if same else 0.0], dtype=torch.float64, device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                same = bool(flag.item() > 0.5)
             variants[name]["host_threads"] = int(env.lib.psk_craft_host_threads(env.ctx))
             variants[name]["chunk_envs"] = args.e2e_wire_chunk
-            variants[name]["frame_equals_f32_path"] = True
+            variants[name]["frame_equals_f32_path"] = same
+            if not same:                 # never report a number for frames that differ
+                variants[name]["measured_but_rejected"] = variants[name]["value"]
+                variants[name]["value"] = 0.0
     # PCIe ceiling for the f32 frame: the same bytes, pinned, nothing else
     frame = torch.empty((n, env.n_features), dtype=torch.float32, device=dev)
     host = torch.empty((n, env.n_features), dtype=torch.float32, pin_memory=True)
-    wall = timed(lambda: (host.copy_(frame, non_blocking=True), torch.cuda.synchronize()), steps)
+    wall = timed_or_raise(lambda: (host.copy_(frame, non_blocking=True), torch.cuda.synchronize()), steps)
     gbs = frame.numel() * 4 * steps / wall / 1e9
     ceiling = {"d2h_GBps_per_gpu": gbs, "env_steps_per_s": n * steps * world / wall,
                "how": "pinned cudaMemcpy D2H of one f32[%d,%d] frame per step, all %d ranks at once" % (n, env.n_features, world)}
