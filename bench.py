@@ -554,7 +554,10 @@ def run_ours(args):
     line["single_tick"] = dict(line["kernels"].pop("tick_fused"), kernel="craft_tick_kernel (one tick per "
                                "launch: the student-in-the-loop path)", algorithmic_bytes_per_env_step=BYTES_FUSED)
     if fused and world == 1:
-        line["u8_frame"] = u8_frame_record(torch, env, n, nf, dev, peak)
+        try:
+            line["u8_frame"] = u8_frame_record(torch, env, n, nf, dev, peak)
+        except Exception as ex:  # noqa: BLE001
+            line["u8_frame"] = {"error": repr(ex)}
     del env, feat_ring, feats
     torch.cuda.empty_cache()
     if world == 1 and not args.no_1m:
