@@ -1134,3 +1134,28 @@ def test_stuck_tile_chain_times_out_instead_of_hanging(splits, medium_tables, me
         assert np.array_equal(_np(out["expert"][t]), orc.tick()["expert"])
     env.check_errors()
     orc.assert_state_equals(env)
+
+
+def test_wire_format_contexts_come_and_go(splits, medium_tables, medium_oracle):
+    """PSK_FEATURES_F32_WIRE_U8 under churn: contexts (pinned landing zone, events, widening threads)
+    created and destroyed repeatedly, thread counts 1..5, batch sizes that are not multiples of the chunk
+    or of the widening block, fewer envs per call than the context holds; every frame against the oracle."""
+    from psketch_b200.host import HostCraft
+    rng = np.random.RandomState(31)
+    o = medium_oracle
+    for rep, (n, chunk, threads) in enumerate([(1, 128, 1), (77, 128, 2), (1000, 256, 3), (4097, 1024, 5),
+                                               (2500, 4096, 4), (333, 128, 1), (5003, 512, 2), (640, 128, 3)] * 2):
+        idx = rng.randint(0, 2200, size=n)
+        args = (splits["dev_grids"], splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
+                splits["dev_inst_task"][idx])
+        env = HostCraft(medium_tables, *args, max_timesteps=9, chunk_envs=chunk, host_threads=threads)
+        env.reset_resident()
+        orc = _OracleTicks(o, *args, max_timesteps=9)
+        for t in range(6):
+            env.features[:] = -7.0
+            env.tick_resident(features="f32_wire_u8")
+            ref = orc.tick()
+            assert np.array_equal(env.features, ref["features"]), (rep, t)
+            assert np.array_equal(env.expert, ref["expert"]), (rep, t)
+        assert env.lib.psk_craft_host_threads(env.ctx) == threads
+        env.close()
