@@ -12,7 +12,7 @@ import json
 import numpy as np
 
 from . import _lib
-from .tables import CraftTables, STOP
+from .tables import CraftTables
 
 
 # ------------------------------------------------------------------------------- wire format

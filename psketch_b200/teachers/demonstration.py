@@ -7,7 +7,6 @@
 ``state`` is a psketch_b200.worlds.craft.CraftState; the action for the state's current task is
 normally already cached by the batched flush that produced the state.
 """
-import numpy as np  # noqa: F401
 
 
 class BaseTeacher(object):

@@ -22,7 +22,7 @@ import numpy as np
 
 from .. import _lib
 from ..tables import (COORD_CHANGE, Cookbook, CraftTables, TaskManager, WORLD_CONFIGS, DOWN, UP,
-                      LEFT, RIGHT, USE, STOP, N_ACTIONS)
+                      LEFT, RIGHT, STOP, N_ACTIONS)
 
 
 class _Struct(object):
