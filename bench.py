@@ -855,13 +855,13 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
                     chunk_envs=args.e2e_chunk)
     steps = max(3, min(args.steps, 30))
 
-    def timed(fn, reps):
-        """Wall time of `reps` calls after 3 untimed ones, MAX over ranks.  fn=None, or an exception
+    def timed(fn, reps, pre=3):
+        """Wall time of `reps` calls after `pre` (>= 3) untimed ones, MAX over ranks.  fn=None, or an exception
         inside fn on ANY rank, gives inf on EVERY rank (the collectives are still executed, so no
         rank is left waiting): an optional form that fails is dropped, it does not take the run down."""
         ok = fn is not None
         try:
-            for _ in range(3 if ok else 0):
+            for _ in range(pre if ok else 0):
                 fn()
             torch.cuda.synchronize()
         except Exception as ex:  # noqa: BLE001
@@ -929,13 +929,17 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
             if not optional:
                 raise
             step_fn, timed.error = None, repr(ex)
-        wall = timed(step_fn, steps)
+        # the wire form settles its split (chunks sent as f32 while the host threads widen the rest)
+        # from measured rates over its first calls: those are untimed warm-up.  Both forms take the
+        # same number of steps from the same reset, so that their final host frames can be compared
+        pre = 12
+        wall = timed(step_fn, steps, pre)
         if wall == float("inf"):
             if not optional:
                 raise RuntimeError("e2e leg %s failed: %s" % (name, timed.error))
             variants[name] = {"value": 0.0, "unit": UNIT, "error": timed.error or "failed on another rank"}
             continue
-        counted = int(env.stats[2]) - before == (steps + 3) * n
+        counted = int(env.stats[2]) - before == (steps + pre) * n
         variants[name] = {"value": n * steps * world / wall, "unit": UNIT,
                           "h2d_bytes_per_step": env.last_h2d, "d2h_bytes_per_step": env.last_d2h}
         if fmt == "f32":
@@ -951,6 +955,8 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
                 same = bool(flag.item() > 0.5)
             variants[name]["host_threads"] = int(env.lib.psk_craft_host_threads(env.ctx))
             variants[name]["chunk_envs"] = args.e2e_wire_chunk
+            variants[name]["chunks_sent_as_f32"] = "%d of %d (last call; split follows the measured PCIe / widening rates)" % (
+                env.last_wire_direct, -(-n // env.chunk_envs))
             variants[name]["frame_equals_f32_path"] = same
             if not same:                 # never report a number for frames that differ
                 variants[name]["measured_but_rejected"] = variants[name]["value"]
@@ -973,7 +979,8 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
                         "host memory; the environments stay in HBM.  form = the faster of host_in_loop_f32 (the "
                         "f32 frame crosses PCIe; frac_of_pcie_ceiling is that form's) and host_in_loop_f32_wire_u8 "
                         "(the u8 frame crosses PCIe, host threads widen each chunk to f32 while the next is in "
-                        "flight; same host frame, checked equal in this run).  e2e_variants: both, plus no action "
+                        "flight, and the last chunks_sent_as_f32 chunks cross as f32 into the caller's pinned frame "
+                        "while the threads are still busy; same host frame, checked equal in this run).  e2e_variants: both, plus no action "
                         "upload, the state round trip of round 1, and the raw u8 frame" %
                         (args.e2e_wire_chunk if best.endswith("wire_u8") else args.e2e_chunk)})
     env.close()

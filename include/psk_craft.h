@@ -292,11 +292,20 @@ int psk_craft_host_tick(psk_craft_host_ctx *ctx, uint8_t *host_grid, uint8_t *ho
  * widening threads, the caller included (>= 1; several contexts on one box should share the cores);
  * psk_craft_host_threads: threads in use (0 before the first such call).  A host context is not
  * thread-safe: one thread at a time may call into it.
+ * Split frame: when host_features IS pinned, the last d of a call's chunks cross PCIe as f32, straight
+ * into host_features, while the host threads are still widening the byte chunks before them — the
+ * copy engine's spare time is worth that many chunks of host work.  d follows the two measured rates
+ * from call to call (d* = chunks (w - p) / (w + 3 p), w / p = widening / wire time per byte chunk;
+ * 0 on hosts that widen faster than PCIe delivers).  psk_craft_host_set_wire_direct: fix d (>= 0),
+ * or -1 = adaptive again (the default; env PSK_WIRE_DIRECT sets the initial choice);
+ * psk_craft_host_wire_direct: the d the next call will use.  The host frame is the same either way.
  * psk_host_widen_u8_f32: the widening alone (dst[i] = src[i]) for callers that keep
  * PSK_FEATURES_U8 frames; no CUDA call. */
 #define PSK_FEATURES_F32_WIRE_U8 3
 int psk_craft_host_threads(const psk_craft_host_ctx *ctx);
 int psk_craft_host_set_threads(psk_craft_host_ctx *ctx, int32_t threads);
+int psk_craft_host_wire_direct(const psk_craft_host_ctx *ctx);
+int psk_craft_host_set_wire_direct(psk_craft_host_ctx *ctx, int32_t chunks);
 int psk_host_widen_u8_f32(const uint8_t *src, float *dst, size_t n, int threads);
 int psk_craft_host_reset(psk_craft_host_ctx *ctx, int64_t n);
 int psk_craft_host_put_state(psk_craft_host_ctx *ctx, const uint8_t *host_grid,

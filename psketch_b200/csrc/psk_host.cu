@@ -6,6 +6,7 @@
 // -> D2H(features, teacher actions, flags, new state), so the copy engines and the SMs overlap
 // across chunks.  Pass pinned memory (psk_host_alloc, or any cudaHostRegister'ed / torch-pinned
 // buffer) or the copies degrade to staged synchronous ones.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -48,7 +49,18 @@ struct psk_craft_host_ctx {
     int64_t n_wire_events;
     PskWidenPool *pool;
     int host_threads;           // psk_craft_host_set_threads; 0 = PskWidenPool::default_threads()
+    // PSK_FEATURES_F32_WIRE_U8, split frame: the LAST `wire_direct` chunks of a call cross PCIe as f32
+    // straight into the caller's (pinned) buffer while the host threads are still widening the byte
+    // chunks that landed before them.  wire_direct_fixed < 0: the count follows the two measured
+    // rates (per-chunk PCIe time, per-chunk widening time) from call to call.
+    int wire_direct, wire_direct_fixed;
+    double wire_pcie_us, wire_widen_us;     // smoothed per-u8-chunk times, 0 = not measured yet
+    cudaEvent_t ev_end;
 };
+
+static inline double now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 #define CK(x)                                   \
     do {                                        \
@@ -115,6 +127,8 @@ int psk_craft_host_create(const psk_craft_tables *t, int64_t max_envs, int64_t c
     c->chunk = (chunk_envs + 127) / 128 * 128;
     c->cell_stride = ((t->width * t->height + 63) / 64) * 64;
     c->nf = psk_craft_n_features(t);
+    c->wire_direct_fixed = -1;
+    if (const char *e = getenv("PSK_WIRE_DIRECT")) c->wire_direct_fixed = atoi(e);
     const int rc = host_ctx_alloc(c);
     if (rc != PSK_OK) {             // release whatever was allocated before the failure
         psk_craft_host_destroy(c);
@@ -140,6 +154,7 @@ void psk_craft_host_destroy(psk_craft_host_ctx *c) {
     cudaFree(c->r_grid); cudaFree(c->r_agent); cudaFree(c->r_action);
     cudaFree(c->r_expert); cudaFree(c->r_done); cudaFree(c->r_success);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
     for (int i = 0; i < PSK_HOST_STREAMS; i++)
         if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     delete c->pool;
@@ -228,6 +243,7 @@ static int resident_alloc(psk_craft_host_ctx *c) {
     CK(cudaMalloc(&c->r_done, n));
     CK(cudaMalloc(&c->r_success, n));
     CK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_end, cudaEventDisableTiming));
     for (int i = 0; i < PSK_HOST_STREAMS; i++)
         CK(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     c->resident_ready = true;
@@ -287,6 +303,39 @@ static int wire_alloc(psk_craft_host_ctx *c) {
     return c->pool ? PSK_OK : PSK_ERR_BADARG;
 }
 
+// How many trailing chunks of this call go down as f32 (split frame, see the context struct).
+static int wire_direct_chunks(psk_craft_host_ctx *c, const void *host_features, int chunks) {
+    int d = c->wire_direct_fixed >= 0 ? c->wire_direct_fixed : c->wire_direct;
+    if (d > chunks) d = chunks;
+    if (d > 0) {        // an f32 chunk is copied by the DMA engine: only into pinned / registered memory
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host_features) != cudaSuccess || at.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            d = 0;
+        }
+    }
+    return d;
+}
+
+// After a call with `d` of `chunks` chunks sent as f32: PCIe finished `t_pcie` us and the widening
+// `t_widen` us after the call started.  One u8 chunk costs p on the wire (an f32 chunk 4 p) and w on
+// the host threads; the two finish together at  d* = chunks (w - p) / (w + 3 p).
+static void wire_direct_update(psk_craft_host_ctx *c, int chunks, int d, double t_pcie, double t_widen) {
+    if (c->wire_direct_fixed >= 0 || chunks < 2 || d >= chunks) {
+        if (d >= chunks && c->wire_direct_fixed < 0) c->wire_direct = chunks - 1;
+        return;
+    }
+    const double p = t_pcie / (chunks + 3.0 * d), w = t_widen / (chunks - d);
+    c->wire_pcie_us = c->wire_pcie_us > 0 ? 0.5 * (c->wire_pcie_us + p) : p;
+    c->wire_widen_us = c->wire_widen_us > 0 ? 0.5 * (c->wire_widen_us + w) : w;
+    const double ps = c->wire_pcie_us, ws = c->wire_widen_us;
+    double best = ws > ps ? chunks * (ws - ps) / (ws + 3.0 * ps) : 0.0;
+    int nd = static_cast<int>(best + 0.5);
+    if (nd > chunks - 1) nd = chunks - 1;
+    // one chunk of hysteresis: a move has to pay for more than the granularity of the split
+    if (nd > d || nd < d - 1 || (nd < d && best < d - 0.75)) c->wire_direct = nd;
+}
+
 int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_action_in,
                                  void *host_features, int32_t feature_format, int32_t advance_first,
                                  uint8_t *host_expert, uint8_t *host_done, uint8_t *host_success,
@@ -298,13 +347,15 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
     if (!host_features) feature_format = PSK_FEATURES_NONE;
     DeviceScope scope(c->device);
     const bool wire = feature_format == PSK_FEATURES_F32_WIRE_U8;
+    const int chunks = static_cast<int>((n + c->chunk - 1) / c->chunk);
+    int direct = 0;
     if (wire) {
         const int rc = wire_alloc(c);
         if (rc) return rc;
+        direct = wire_direct_chunks(c, host_features, chunks);
     }
+    const double t_start = wire ? now_us() : 0.0;
     const int cs = c->cell_stride;
-    const size_t fsz = (feature_format == PSK_FEATURES_U8 || wire) ? 1 : 4;
-    uint8_t *const landing = wire ? c->h_wire : static_cast<uint8_t *>(host_features);
     cudaStream_t s0 = c->streams[0];
     if (host_action_in) {       // one copy for the whole batch, the other streams wait for it
         CK(cudaMemcpyAsync(c->r_action, host_action_in, (size_t)n, cudaMemcpyHostToDevice, s0));
@@ -321,14 +372,18 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
         const uint8_t *act = host_action_in ? c->r_action + off : nullptr;
         int rc;
         const int mode = advance_first ? PSK_TICK_ADVANCE_FIRST : PSK_TICK_FUSED;
-        if (fsz == 1) {
+        // this chunk's frame format on the wire: bytes (compact frame, or to be widened here), or f32
+        const bool bytes = feature_format == PSK_FEATURES_U8 || (wire && k < chunks - direct);
+        const size_t fsz = bytes ? 1 : 4;
+        uint8_t *const landing = (wire && bytes) ? c->h_wire : static_cast<uint8_t *>(host_features);
+        if (bytes) {
             // compact frame: the fused kernel writes its u8 tile as it is
             rc = psk_craft_tick_u8(&c->tables, state, ep, act, reinterpret_cast<uint8_t *>(c->d_feat[s]),
                                    c->r_expert + off, c->r_done + off, c->r_success + off, c->d_stats,
                                    c->d_err, mode, st);
         } else {
             rc = psk_craft_tick(&c->tables, state, ep, act,
-                                feature_format == PSK_FEATURES_F32 ? c->d_feat[s] : nullptr,
+                                feature_format != PSK_FEATURES_NONE ? c->d_feat[s] : nullptr,
                                 c->r_expert + off, c->r_done + off, c->r_success + off, c->d_stats,
                                 c->d_err, mode, st);
         }
@@ -336,7 +391,7 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
         if (feature_format != PSK_FEATURES_NONE)
             CK(cudaMemcpyAsync(landing + (size_t)off * c->nf * fsz, c->d_feat[s],
                                (size_t)m * c->nf * fsz, cudaMemcpyDeviceToHost, st));
-        if (wire) CK(cudaEventRecord(c->ev_wire[k], st));
+        if (wire && bytes) CK(cudaEventRecord(c->ev_wire[k], st));
     }
     // the per-env byte outputs of the whole batch: one copy each, after every chunk's kernel
     for (int i = 1; i < PSK_HOST_STREAMS; i++) {
@@ -349,11 +404,12 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
     if (host_stats || host_err_flags)       // one 40-byte copy into pinned memory (pageable targets would stage)
         CK(cudaMemcpyAsync(c->h_mail, c->d_stats, 40, cudaMemcpyDeviceToHost, s0));
     if (wire) {
+        CK(cudaEventRecord(c->ev_end, s0));     // s0 waited for every stream: the last byte of the call
         // widen chunk k on the host threads as soon as its bytes have landed, while chunks k+1..
-        // are still being computed and copied
+        // are still being computed and copied (the f32 chunks at the end need no host work)
         int done_chunks = 0;
         cudaError_t err = cudaSuccess;
-        for (int64_t off = 0; off < n && err == cudaSuccess; off += c->chunk, done_chunks++) {
+        for (int64_t off = 0; done_chunks < chunks - direct && err == cudaSuccess; off += c->chunk, done_chunks++) {
             const int64_t m = (n - off) < c->chunk ? (n - off) : c->chunk;
             err = cudaEventSynchronize(c->ev_wire[done_chunks]);
             if (err == cudaSuccess)
@@ -361,15 +417,38 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
                                 static_cast<float *>(host_features) + (size_t)off * c->nf,
                                 (size_t)m * c->nf, PSK_WIDEN_BLOCK);
         }
-        c->pool->finish();
+        // help with the widening; note when the wire went quiet and when the widening did
+        double t_pcie = 0.0;
+        while (!c->pool->idle()) {
+            if (t_pcie == 0.0 && cudaEventQuery(c->ev_end) == cudaSuccess) t_pcie = now_us() - t_start;
+            c->pool->help();
+        }
+        const double t_widen = now_us() - t_start;
+        cudaGetLastError();                     // cudaErrorNotReady from the queries is not an error
         if (err != cudaSuccess) return PSK_ERR_CUDA;
+        for (int i = 0; i < PSK_HOST_STREAMS; i++) CK(cudaStreamSynchronize(c->streams[i]));
+        if (t_pcie == 0.0) t_pcie = now_us() - t_start;
+        wire_direct_update(c, chunks, direct, t_pcie, t_widen);
+    } else {
+        for (int i = 0; i < PSK_HOST_STREAMS; i++) CK(cudaStreamSynchronize(c->streams[i]));
     }
-    for (int i = 0; i < PSK_HOST_STREAMS; i++) CK(cudaStreamSynchronize(c->streams[i]));
     if (host_stats) memcpy(host_stats, c->h_mail, 4 * sizeof(unsigned long long));
     if (host_err_flags) {
         memcpy(host_err_flags, c->h_mail + 4, sizeof(int32_t));
         if (*host_err_flags) CK(cudaMemset(c->d_err, 0, sizeof(int32_t)));
     }
+    return PSK_OK;
+}
+
+int psk_craft_host_wire_direct(const psk_craft_host_ctx *c) {
+    if (!c) return 0;
+    return c->wire_direct_fixed >= 0 ? c->wire_direct_fixed : c->wire_direct;
+}
+
+int psk_craft_host_set_wire_direct(psk_craft_host_ctx *c, int32_t chunks) {
+    if (!c || chunks < -1) return PSK_ERR_BADARG;
+    c->wire_direct_fixed = chunks;
+    if (chunks < 0) c->wire_direct = 0, c->wire_pcie_us = c->wire_widen_us = 0.0;
     return PSK_OK;
 }
 

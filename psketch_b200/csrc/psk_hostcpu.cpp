@@ -130,6 +130,10 @@ void PskWidenPool::submit(const uint8_t *src, float *dst, size_t n, size_t block
     }
 }
 
+void PskWidenPool::help() {
+    if (!run_one()) _mm_pause();
+}
+
 void PskWidenPool::finish() {
     while (run_one()) {}
     const uint64_t t = tail_.load(std::memory_order_relaxed);

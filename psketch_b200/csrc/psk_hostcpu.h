@@ -20,6 +20,9 @@ class PskWidenPool {
     static int default_threads();       // env PSK_HOST_THREADS, else min(8, cores / 2) - 1
     void submit(const uint8_t *src, float *dst, size_t n, size_t block);
     void finish();                      // help, then wait until everything submitted is written
+    // the same in pieces, for a caller that watches something else while it helps
+    bool idle() const { return done_.load(std::memory_order_acquire) == tail_.load(std::memory_order_relaxed); }
+    void help();                        // widen one block if one is waiting, else pause
     int threads() const { return static_cast<int>(workers_.size()); }
 
   private:

@@ -66,6 +66,9 @@ class HostCraft(object):
         _lib.check(self.lib.psk_craft_host_create(ctypes.byref(self.ct), n, chunk_envs,
                                                   ctypes.byref(ctx)), "psk_craft_host_create")
         self.ctx = ctx
+        ce = min(int(chunk_envs) if chunk_envs and chunk_envs > 0 else 16384, n)
+        self.chunk_envs = (ce + 127) // 128 * 128       # as psk_craft_host_create rounds it
+        self.last_wire_direct = 0
         if host_threads is None:
             local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
             host_threads = max(1, min(8, (os.cpu_count() or 2) // 2 // local))
@@ -166,6 +169,7 @@ class HostCraft(object):
             self.upload()
         if actions is not None:
             self.action[:] = actions
+        direct = self.wire_direct if features == "f32_wire_u8" else 0
         fmt = {None: _lib.FEATURES_NONE, "f32": _lib.FEATURES_F32, "u8": _lib.FEATURES_U8,
                "f32_wire_u8": _lib.FEATURES_F32_WIRE_U8}[features]
         buf = {None: None, "f32": self.features, "f32_wire_u8": self.features}.get(features)
@@ -177,10 +181,26 @@ class HostCraft(object):
             _np_ptr(self.stats), _np_ptr(self.err))
         _lib.check(rc, "psk_craft_host_tick_resident")
         self.last_h2d = self.n if actions is not None else 0
-        wire = 0 if buf is None else (buf.nbytes // 4 if features == "f32_wire_u8" else buf.nbytes)
+        wire = 0 if buf is None else buf.nbytes
+        if features == "f32_wire_u8":       # bytes for the leading chunks, f32 for the last `direct` ones
+            chunks = -(-self.n // self.chunk_envs)
+            direct = min(direct, chunks) if buf.ctypes.data == self._pins["features"].ptr else 0
+            n_f32 = 0 if direct == 0 else self.n - (chunks - direct) * self.chunk_envs
+            wire = (self.n - n_f32) * self.n_features + n_f32 * self.n_features * 4
+            self.last_wire_direct = direct
         self.last_d2h = self.n * 3 + wire + 36
         self._raise_flags()
         return self.expert
+
+    @property
+    def wire_direct(self):
+        """Chunks of the next ``f32_wire_u8`` call that cross PCIe as f32 instead of bytes (the split
+        follows the measured PCIe and widening rates unless ``set_wire_direct`` fixed it)."""
+        return int(self.lib.psk_craft_host_wire_direct(self.ctx))
+
+    def set_wire_direct(self, chunks=-1):
+        """Fix the number of trailing f32 chunks of ``f32_wire_u8`` calls; -1 = adaptive (default)."""
+        _lib.check(self.lib.psk_craft_host_set_wire_direct(self.ctx, int(chunks)), "psk_craft_host_set_wire_direct")
 
     @property
     def h2d_bytes(self):

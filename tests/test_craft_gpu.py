@@ -1136,6 +1136,38 @@ def test_stuck_tile_chain_times_out_instead_of_hanging(splits, medium_tables, me
     orc.assert_state_equals(env)
 
 
+@pytest.mark.parametrize("direct", [0, 1, 3, 5, 100, -1])
+def test_wire_format_split_frame(direct, splits, medium_tables, medium_oracle):
+    """PSK_FEATURES_F32_WIRE_U8 with the last `direct` chunks crossing PCIe as f32 (split frame): the
+    host frame is the oracle's whichever chunk took which route, fixed or adaptive (-1), ragged last
+    chunk, fewer chunks than `direct`; a host buffer that is not pinned falls back to bytes only."""
+    from psketch_b200.host import HostCraft
+    n, chunk = 4500, 1024           # 5 chunks, the last one of 404 envs
+    rng = np.random.RandomState(77 + direct)
+    idx = rng.randint(0, 2200, size=n)
+    args = (splits["dev_grids"], splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
+            splits["dev_inst_task"][idx])
+    env = HostCraft(medium_tables, *args, max_timesteps=11, chunk_envs=chunk, host_threads=2)
+    env.set_wire_direct(direct)
+    assert env.wire_direct == (direct if direct >= 0 else 0)
+    env.reset_resident()
+    orc = _OracleTicks(medium_oracle, *args, max_timesteps=11)
+    pinned = env.features
+    for t in range(14):
+        if t == 9:                  # a pageable frame: every chunk goes as bytes, same result
+            env.features = np.empty_like(pinned)
+        env.features[:] = -3.0
+        env.tick_resident(features="f32_wire_u8")
+        ref = orc.tick()
+        assert np.array_equal(env.features, ref["features"]), t
+        assert np.array_equal(env.expert, ref["expert"]), t
+        assert np.array_equal(env.done, ref["done"]), t
+        assert env.last_wire_direct == (0 if t >= 9 else min(max(direct, 0), 5)) or direct < 0
+        assert 0 <= env.wire_direct <= (5 if direct < 0 else max(direct, 0))
+    env.features = pinned
+    env.close()
+
+
 def test_wire_format_contexts_come_and_go(splits, medium_tables, medium_oracle):
     """PSK_FEATURES_F32_WIRE_U8 under churn: contexts (pinned landing zone, events, widening threads)
     created and destroyed repeatedly, thread counts 1..5, batch sizes that are not multiples of the chunk
