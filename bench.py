@@ -479,6 +479,25 @@ def run_ours(args):
         parity["launch"] = "psk_craft_rollout(ticks=%d) on %d envs, same dispatch as the timed launches" % (plan[-1], n)
         env.check_errors()
 
+    # ---- yardstick for a kernel that only writes: the same ring filled by a plain store kernel (the
+    # roofline denominator is a COPY bandwidth, half reads; a store-only stream runs faster than that)
+    write_ceiling = None
+    if rank == 0:
+        try:
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            feat_ring.fill_(0.0)
+            torch.cuda.synchronize()
+            w0.record()
+            for _ in range(5):
+                feat_ring.fill_(0.0)
+            w1.record()
+            torch.cuda.synchronize()
+            gbs = 5 * feat_ring.numel() * feat_ring.element_size() / (w0.elapsed_time(w1) * 1e-3) / 1e9
+            write_ceiling = {"GBps": gbs, "how": "torch fill_ of the %.0f MB feature ring, 5 passes between CUDA "
+                                                 "events, after the timed region" % (feat_ring.numel() * feat_ring.element_size() / 1e6)}
+        except Exception as ex:  # noqa: BLE001
+            write_ceiling = {"error": repr(ex)}
+
     # ---- end to end through the public API with host buffers (rank-local, then aggregated)
     e2e = measure_e2e(torch, dist if distributed else None, tables, wl, n, dev, args, world)
 
@@ -544,6 +563,9 @@ def run_ours(args):
                             "traffic": traffic, "peak_source": peak_src,
                             "algorithmic_bytes_per_env_step": bytes_per_tick,
                             "launch_us": launch_s * 1e6, "ticks_per_launch": ticks_per_launch_eff}
+        if write_ceiling and "GBps" in write_ceiling:
+            # why frac can exceed 1: this kernel only writes; against a store-only stream it is below 1
+            line["roofline"]["write_only_ceiling"] = dict(write_ceiling, frac=achieved / write_ceiling["GBps"])
     # per-kernel numbers (north star: step and features as a fraction of the HBM roofline)
     line["kernels"] = per_kernel_table(torch, env, n, nf, dev, peak, min(ring, 8))
     if not fused:
