@@ -983,6 +983,26 @@ def measure_e2e(torch, dist, tables, wl, n, dev, args, world):
             if not same:                 # never report a number for frames that differ
                 variants[name]["measured_but_rejected"] = variants[name]["value"]
                 variants[name]["value"] = 0.0
+    # the reference's own operating point (configs/experiments/imitation.yaml: batch_size 32): latency of
+    # one host-in-the-loop tick through the same C entry point, rank-local, not part of the headline
+    try:
+        w32 = load_workload(32)
+        e32 = HostCraft(tables, w32["grids"], w32["env"], w32["pos"], w32["task"], max_timesteps=40, chunk_envs=128)
+        e32.reset_resident()
+        e32.tick_resident(features="f32", advance_first=True)
+        a32 = e32.expert.copy()
+        for i in range(20 + 400):
+            if i == 20:
+                t32 = time.perf_counter()
+            e32.tick_resident(actions=a32, features="f32", advance_first=True)
+            a32[:] = e32.expert
+        us = (time.perf_counter() - t32) / 400 * 1e6
+        variants["batch32_f32"] = {"us_per_tick": us, "env_steps_per_s_one_rank": 32 / us * 1e6,
+                                   "note": "32 envs per call (the reference's batch size), host in the loop, "
+                                           "one rank; latency-bound, not aggregated over ranks"}
+        e32.close()
+    except Exception as ex:  # noqa: BLE001
+        variants["batch32_f32"] = {"error": repr(ex)}
     # PCIe ceiling for the f32 frame: the same bytes, pinned, nothing else
     frame = torch.empty((n, env.n_features), dtype=torch.float32, device=dev)
     host = torch.empty((n, env.n_features), dtype=torch.float32, pin_memory=True)
