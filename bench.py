@@ -580,6 +580,33 @@ def run_ours(args):
             line["u8_frame"] = u8_frame_record(torch, env, n, nf, dev, peak)
         except Exception as ex:  # noqa: BLE001
             line["u8_frame"] = {"error": repr(ex)}
+    if fused and world == 1 and T > 1 and rand_act is None:
+        # SURVEY 8(d) config 2, off-policy variant: actions ~ U{0..5} from Philox(123, (env, t)); one Philox
+        # launch fills the action block of each T-tick rollout launch (the full run: --policy random)
+        try:
+            ablock, oout = torch.empty((T, n), dtype=torch.uint8, device=dev), {}
+
+            def off_policy_launch():
+                env.random_actions(0, seed=123, out=ablock, device_clock=True, ticks=T)
+                env.rollout(T, actions=ablock, features_out=feat_ring, out=oout, want_flags=True)
+
+            for _ in range(3):
+                off_policy_launch()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            o0.record()
+            for _ in range(60):
+                off_policy_launch()
+            o1.record()
+            torch.cuda.synchronize()
+            env.check_errors()
+            sec = o0.elapsed_time(o1) * 1e-3 / (60 * T)
+            bpt = (1616 + 3) + (2 * 96 + 4) / T + 1         # + the action byte read per env-tick
+            line["off_policy"] = {"value": n / sec, "unit": UNIT, "us_per_tick": sec * 1e6,
+                                  "frac": bpt * n / sec / 1e9 / peak, "launches": "60 x (Philox block + rollout of "
+                                  "%d ticks), eager, CUDA events" % T}
+        except Exception as ex:  # noqa: BLE001
+            line["off_policy"] = {"error": repr(ex)}
     del env, feat_ring, feats
     torch.cuda.empty_cache()
     if world == 1 and not args.no_1m:

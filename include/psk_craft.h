@@ -304,6 +304,14 @@ int psk_craft_host_tick(psk_craft_host_ctx *ctx, uint8_t *host_grid, uint8_t *ho
 #define PSK_FEATURES_F32_WIRE_U8 3
 int psk_craft_host_threads(const psk_craft_host_ctx *ctx);
 int psk_craft_host_set_threads(psk_craft_host_ctx *ctx, int32_t threads);
+/* Small batches (n <= max_envs, default 2048, env PSK_HOST_ZEROCOPY_MAX; 0 = never): when every buffer
+ * of a psk_craft_host_tick_resident call is pinned, the fused kernel reads the actions from and writes
+ * features / teacher actions / flags into the caller's memory itself (unified addressing): one launch and
+ * one synchronize per call instead of a copy per buffer — the reference's own batch size is 32
+ * (configs/experiments/imitation.yaml:17); measured 44 -> 31 us per call at 32 envs, 108 -> 91 at 2,048
+ * (profiles/bench_runs/r2_host_small_batch_probe.json).  Same results; pageable buffers take the copy
+ * route. */
+int psk_craft_host_set_zerocopy_max(psk_craft_host_ctx *ctx, int64_t max_envs);
 int psk_craft_host_wire_direct(const psk_craft_host_ctx *ctx);
 int psk_craft_host_set_wire_direct(psk_craft_host_ctx *ctx, int32_t chunks);
 int psk_host_widen_u8_f32(const uint8_t *src, float *dst, size_t n, int threads);

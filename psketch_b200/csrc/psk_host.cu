@@ -56,6 +56,9 @@ struct psk_craft_host_ctx {
     int wire_direct, wire_direct_fixed;
     double wire_pcie_us, wire_widen_us;     // smoothed per-u8-chunk times, 0 = not measured yet
     cudaEvent_t ev_end;
+    // small batches: the fused kernel reads the actions from and writes every output into the caller's
+    // pinned buffers itself (unified addressing) — one launch, one 40-byte copy, one synchronize
+    int64_t zerocopy_max;               // env PSK_HOST_ZEROCOPY_MAX, psk_craft_host_set_zerocopy_max
 };
 
 static inline double now_us() {
@@ -129,6 +132,8 @@ int psk_craft_host_create(const psk_craft_tables *t, int64_t max_envs, int64_t c
     c->nf = psk_craft_n_features(t);
     c->wire_direct_fixed = -1;
     if (const char *e = getenv("PSK_WIRE_DIRECT")) c->wire_direct_fixed = atoi(e);
+    c->zerocopy_max = 2048;
+    if (const char *e = getenv("PSK_HOST_ZEROCOPY_MAX")) c->zerocopy_max = atoll(e);
     const int rc = host_ctx_alloc(c);
     if (rc != PSK_OK) {             // release whatever was allocated before the failure
         psk_craft_host_destroy(c);
@@ -336,6 +341,57 @@ static void wire_direct_update(psk_craft_host_ctx *c, int chunks, int d, double 
     if (nd > d || nd < d - 1 || (nd < d && best < d - 0.75)) c->wire_direct = nd;
 }
 
+// Device alias of a pinned host pointer, NULL when the memory is pageable.  Looked up on every call
+// (well under a microsecond): an address can change hands between calls.
+static void *zc_alias(const void *host) {
+    if (!host) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost)
+        return at.devicePointer;
+    cudaGetLastError();
+    return nullptr;
+}
+
+// One launch for the whole call.  Returns PSK_ERR_UNSUPPORTED when a buffer is not pinned (the caller
+// of this helper then takes the copy-engine route).
+static int tick_resident_zerocopy(psk_craft_host_ctx *c, const uint8_t *host_action_in, void *host_features,
+                                  int32_t feature_format, int32_t advance_first, uint8_t *host_expert,
+                                  uint8_t *host_done, uint8_t *host_success, int64_t n,
+                                  unsigned long long *host_stats, int32_t *host_err_flags) {
+    const uint8_t *act = static_cast<const uint8_t *>(zc_alias(host_action_in));
+    void *feat = zc_alias(host_features);
+    uint8_t *expert = static_cast<uint8_t *>(zc_alias(host_expert));
+    uint8_t *done = static_cast<uint8_t *>(zc_alias(host_done));
+    uint8_t *success = static_cast<uint8_t *>(zc_alias(host_success));
+    if ((host_action_in && !act) || (host_features && !feat) || !expert || (host_done && !done) ||
+        (host_success && !success))
+        return PSK_ERR_UNSUPPORTED;
+    if (feature_format == PSK_FEATURES_NONE) feat = nullptr;
+    cudaStream_t s0 = c->streams[0];
+    psk_craft_state state = {c->r_grid, c->r_agent, n, c->cell_stride, 0};
+    psk_craft_episodes ep = {c->d_scen_grid, c->d_scen_idx, c->d_init_agent};
+    const int mode = advance_first ? PSK_TICK_ADVANCE_FIRST : PSK_TICK_FUSED;
+    int rc;
+    if (feature_format == PSK_FEATURES_U8)
+        rc = psk_craft_tick_u8(&c->tables, state, ep, act, static_cast<uint8_t *>(feat), expert,
+                               done ? done : c->r_done, success ? success : c->r_success, c->d_stats, c->d_err,
+                               mode, s0);
+    else        // PSK_FEATURES_F32 and PSK_FEATURES_F32_WIRE_U8 promise the same f32 host frame
+        rc = psk_craft_tick(&c->tables, state, ep, act, static_cast<float *>(feat), expert,
+                            done ? done : c->r_done, success ? success : c->r_success, c->d_stats, c->d_err,
+                            mode, s0);
+    if (rc) return rc;
+    if (host_stats || host_err_flags)
+        CK(cudaMemcpyAsync(c->h_mail, c->d_stats, 40, cudaMemcpyDeviceToHost, s0));
+    CK(cudaStreamSynchronize(s0));
+    if (host_stats) memcpy(host_stats, c->h_mail, 4 * sizeof(unsigned long long));
+    if (host_err_flags) {
+        memcpy(host_err_flags, c->h_mail + 4, sizeof(int32_t));
+        if (*host_err_flags) CK(cudaMemset(c->d_err, 0, sizeof(int32_t)));
+    }
+    return PSK_OK;
+}
+
 int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_action_in,
                                  void *host_features, int32_t feature_format, int32_t advance_first,
                                  uint8_t *host_expert, uint8_t *host_done, uint8_t *host_success,
@@ -346,6 +402,11 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
         return PSK_ERR_BADARG;
     if (!host_features) feature_format = PSK_FEATURES_NONE;
     DeviceScope scope(c->device);
+    if (n > 0 && n <= c->zerocopy_max && c->tables.width * c->tables.height <= 128) {
+        const int rc = tick_resident_zerocopy(c, host_action_in, host_features, feature_format, advance_first,
+                                              host_expert, host_done, host_success, n, host_stats, host_err_flags);
+        if (rc != PSK_ERR_UNSUPPORTED) return rc;
+    }
     const bool wire = feature_format == PSK_FEATURES_F32_WIRE_U8;
     const int chunks = static_cast<int>((n + c->chunk - 1) / c->chunk);
     int direct = 0;
@@ -437,6 +498,12 @@ int psk_craft_host_tick_resident(psk_craft_host_ctx *c, const uint8_t *host_acti
         memcpy(host_err_flags, c->h_mail + 4, sizeof(int32_t));
         if (*host_err_flags) CK(cudaMemset(c->d_err, 0, sizeof(int32_t)));
     }
+    return PSK_OK;
+}
+
+int psk_craft_host_set_zerocopy_max(psk_craft_host_ctx *c, int64_t max_envs) {
+    if (!c || max_envs < 0) return PSK_ERR_BADARG;
+    c->zerocopy_max = max_envs;
     return PSK_OK;
 }
 

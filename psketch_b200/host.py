@@ -95,6 +95,7 @@ class HostCraft(object):
         self.resident = False
         self._features_u8 = None
         self.last_h2d = self.last_d2h = 0
+        self._ptrs = {}
 
     def _raise_flags(self):
         """What the reference would have raised (worlds/craft.py:415-416, demonstration.py:18)."""
@@ -159,6 +160,18 @@ class HostCraft(object):
             self._features_u8 = self._pins["features_u8"].array
         return self._features_u8
 
+    def _p(self, a):
+        """c_void_p of a numpy array; the arrays handed over call after call are looked up once
+        (``ndarray.ctypes`` builds a new helper object on every access: ~1.5 us per pointer)."""
+        if a is None:
+            return None
+        hit = self._ptrs.get(id(a))
+        if hit is None or hit[0] is not a:
+            if len(self._ptrs) > 32:
+                self._ptrs.clear()
+            hit = self._ptrs[id(a)] = (a, ctypes.c_void_p(a.ctypes.data))
+        return hit[1]
+
     def tick_resident(self, actions=None, features="f32", advance_first=False):
         """psk_craft_host_tick_resident: only actions go up; features (``"f32"`` -> self.features,
         ``"u8"`` -> self.features_u8, ``"f32_wire_u8"`` -> self.features again, but PCIe carries the
@@ -175,10 +188,11 @@ class HostCraft(object):
         buf = {None: None, "f32": self.features, "f32_wire_u8": self.features}.get(features)
         if features == "u8":
             buf = self.features_u8
+        p = self._p
         rc = self.lib.psk_craft_host_tick_resident(
-            self.ctx, _np_ptr(self.action) if actions is not None else None, _np_ptr(buf), fmt,
-            1 if advance_first else 0, _np_ptr(self.expert), _np_ptr(self.done), _np_ptr(self.success), self.n,
-            _np_ptr(self.stats), _np_ptr(self.err))
+            self.ctx, p(self.action) if actions is not None else None, p(buf), fmt,
+            1 if advance_first else 0, p(self.expert), p(self.done), p(self.success), self.n,
+            p(self.stats), p(self.err))
         _lib.check(rc, "psk_craft_host_tick_resident")
         self.last_h2d = self.n if actions is not None else 0
         wire = 0 if buf is None else buf.nbytes
@@ -201,6 +215,11 @@ class HostCraft(object):
     def set_wire_direct(self, chunks=-1):
         """Fix the number of trailing f32 chunks of ``f32_wire_u8`` calls; -1 = adaptive (default)."""
         _lib.check(self.lib.psk_craft_host_set_wire_direct(self.ctx, int(chunks)), "psk_craft_host_set_wire_direct")
+
+    def set_zerocopy_max(self, max_envs=2048):
+        """Calls of at most ``max_envs`` envs whose buffers are all pinned run as ONE launch that reads
+        and writes host memory itself (0 = always the copy-engine route)."""
+        _lib.check(self.lib.psk_craft_host_set_zerocopy_max(self.ctx, int(max_envs)), "psk_craft_host_set_zerocopy_max")
 
     @property
     def h2d_bytes(self):

@@ -1168,6 +1168,71 @@ def test_wire_format_split_frame(direct, splits, medium_tables, medium_oracle):
     env.close()
 
 
+@pytest.mark.parametrize("features", ["f32", "u8", "f32_wire_u8", None])
+@pytest.mark.parametrize("n", [1, 32, 77, 2048])
+def test_small_batch_zero_copy_host_tick(n, features, splits, medium_tables, medium_oracle):
+    """psk_craft_host_tick_resident at the reference's batch sizes: with pinned buffers the fused kernel
+    reads the actions from and writes every output into host memory itself (one launch per call).  Both
+    tick orders against the oracle, every output poisoned before every call; the same calls with the route
+    switched off, and with a pageable frame (falls back to copies), give the same bytes."""
+    from psketch_b200.host import HostCraft
+    rng = np.random.RandomState(1000 + n)
+    idx = rng.randint(0, 2200, size=n)
+    args = (splits["dev_grids"], splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
+            splits["dev_inst_task"][idx])
+    o = medium_oracle
+    envs = [HostCraft(medium_tables, *args, max_timesteps=12, chunk_envs=256, host_threads=2) for _ in range(2)]
+    envs[1].set_zerocopy_max(0)
+    for env in envs:
+        env.reset_resident()
+    orc = _OracleTicks(o, *args, max_timesteps=12)
+
+    def frame(env):
+        return None if features is None else (env.features_u8.astype(np.float32) if features == "u8" else env.features)
+
+    def poison(env):
+        env.expert[:] = 77
+        env.done[:] = 77
+        env.success[:] = 77
+        if features == "u8":
+            env.features_u8[:] = 77
+        elif features is not None:
+            env.features[:] = -5.0
+
+    pinned = envs[0].features
+    for t in range(30):
+        a = None if t < 8 else rng.choice(6, size=n, p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8)
+        if t == 20 and features in ("f32", "f32_wire_u8"):      # pageable frame: copy route, same result
+            envs[0].features = np.empty_like(pinned)
+        for env in envs:
+            poison(env)
+            env.tick_resident(actions=a, features=features)
+        ref = orc.tick(a)
+        for env in envs:
+            assert np.array_equal(env.expert, ref["expert"]), t
+            assert np.array_equal(env.done, ref["done"]) and np.array_equal(env.success, ref["success"]), t
+            if features is not None:
+                assert np.array_equal(frame(env), ref["features"]), t
+    # step-then-observe order on the same contexts
+    for t in range(12):
+        a = rng.choice(6, size=n, p=[.19, .19, .19, .19, .2, .04]).astype(np.uint8)
+        for env in envs:
+            poison(env)
+            env.tick_resident(actions=a, features=features, advance_first=True)
+        ref = orc.tick(a, want_features=False)
+        want_e, _, _ = o.expert(orc.grid, orc.inv, orc.pos, orc.dir, orc.task)
+        for env in envs:
+            assert np.array_equal(env.done, ref["done"]) and np.array_equal(env.success, ref["success"]), t
+            assert np.array_equal(env.expert.astype(np.int32), want_e), t
+            if features is not None:
+                assert np.array_equal(frame(env), o.features(orc.grid, orc.inv, orc.pos, orc.dir)), t
+    for env in envs:
+        assert tuple(int(x) for x in env.stats[:3]) == tuple(orc.stats)
+    envs[0].features = pinned
+    for env in envs:
+        env.close()
+
+
 def test_wire_format_contexts_come_and_go(splits, medium_tables, medium_oracle):
     """PSK_FEATURES_F32_WIRE_U8 under churn: contexts (pinned landing zone, events, widening threads)
     created and destroyed repeatedly, thread counts 1..5, batch sizes that are not multiples of the chunk
@@ -1181,6 +1246,7 @@ def test_wire_format_contexts_come_and_go(splits, medium_tables, medium_oracle):
         args = (splits["dev_grids"], splits["dev_inst_env"][idx], splits["dev_inst_pos"][idx],
                 splits["dev_inst_task"][idx])
         env = HostCraft(medium_tables, *args, max_timesteps=9, chunk_envs=chunk, host_threads=threads)
+        env.set_zerocopy_max(0)         # small batches too go through the landing zone and the threads
         env.reset_resident()
         orc = _OracleTicks(o, *args, max_timesteps=9)
         for t in range(6):
