@@ -17,13 +17,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--calls", type=int, default=600)
+    ap.add_argument("--small", action="store_true")
     args = ap.parse_args()
     import bench
     from psketch_b200.host import HostCraft
     from psketch_b200.tables import CraftTables
     tables = CraftTables()
     res = {}
-    for n in (32, 128, 512, 1024, 2048, 4096):
+    for n in ((32, 128, 512, 1024, 2048, 4096) if not args.small else (32, 512)):
         wl = bench.load_workload(n)
         row = {}
         for rnd in range(2):
@@ -52,6 +53,13 @@ def main():
                     fn(*cargs)
                 us = (time.perf_counter() - t0) / args.calls * 1e6
                 row[name + "_c_call_only"] = min(row.get(name + "_c_call_only", 1e9), round(us, 2))
+                nomail = cargs[:9] + (None, None)           # no statistics / error-flag copy
+                for i in range(30 + args.calls):
+                    if i == 30:
+                        t0 = time.perf_counter()
+                    fn(*nomail)
+                us = (time.perf_counter() - t0) / args.calls * 1e6
+                row[name + "_c_call_no_mail"] = min(row.get(name + "_c_call_no_mail", 1e9), round(us, 2))
                 env.close()
         res[str(n)] = row
     line = json.dumps({"us_per_call": res, "calls": args.calls, "what": "host in the loop, f32 frame, best of 2"})

@@ -341,6 +341,14 @@ static void wire_direct_update(psk_craft_host_ctx *c, int chunks, int d, double 
     if (nd > d || nd < d - 1 || (nd < d && best < d - 0.75)) c->wire_direct = nd;
 }
 
+// The running statistics and the error flags (d_stats: u64[4] | i32) into the pinned mailbox, as a
+// kernel behind the tick on the same stream: a 40-byte cudaMemcpyAsync costs 10 us of copy-engine
+// latency at this size (17 -> 27 us per call), five 8-byte stores over PCIe cost 3.
+__global__ void mail_publish_kernel(const unsigned long long *__restrict__ d_stats,
+                                    unsigned long long *__restrict__ mail) {
+    if (threadIdx.x < 5) mail[threadIdx.x] = d_stats[threadIdx.x];
+}
+
 // Device alias of a pinned host pointer, NULL when the memory is pageable.  Looked up on every call
 // (well under a microsecond): an address can change hands between calls.
 static void *zc_alias(const void *host) {
@@ -381,8 +389,15 @@ static int tick_resident_zerocopy(psk_craft_host_ctx *c, const uint8_t *host_act
                             done ? done : c->r_done, success ? success : c->r_success, c->d_stats, c->d_err,
                             mode, s0);
     if (rc) return rc;
-    if (host_stats || host_err_flags)
-        CK(cudaMemcpyAsync(c->h_mail, c->d_stats, 40, cudaMemcpyDeviceToHost, s0));
+    if (host_stats || host_err_flags) {
+        void *mail = zc_alias(c->h_mail);
+        if (mail) {
+            mail_publish_kernel<<<1, 32, 0, s0>>>(c->d_stats, static_cast<unsigned long long *>(mail));
+            CK(cudaGetLastError());
+        } else {
+            CK(cudaMemcpyAsync(c->h_mail, c->d_stats, 40, cudaMemcpyDeviceToHost, s0));
+        }
+    }
     CK(cudaStreamSynchronize(s0));
     if (host_stats) memcpy(host_stats, c->h_mail, 4 * sizeof(unsigned long long));
     if (host_err_flags) {
