@@ -312,6 +312,7 @@ static int wire_alloc(psk_craft_host_ctx *c) {
 static int wire_direct_chunks(psk_craft_host_ctx *c, const void *host_features, int chunks) {
     int d = c->wire_direct_fixed >= 0 ? c->wire_direct_fixed : c->wire_direct;
     if (d > chunks) d = chunks;
+    if (d < 0) d = 0;
     if (d > 0) {        // an f32 chunk is copied by the DMA engine: only into pinned / registered memory
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, host_features) != cudaSuccess || at.type != cudaMemoryTypeHost) {
@@ -326,10 +327,7 @@ static int wire_direct_chunks(psk_craft_host_ctx *c, const void *host_features, 
 // `t_widen` us after the call started.  One u8 chunk costs p on the wire (an f32 chunk 4 p) and w on
 // the host threads; the two finish together at  d* = chunks (w - p) / (w + 3 p).
 static void wire_direct_update(psk_craft_host_ctx *c, int chunks, int d, double t_pcie, double t_widen) {
-    if (c->wire_direct_fixed >= 0 || chunks < 2 || d >= chunks) {
-        if (d >= chunks && c->wire_direct_fixed < 0) c->wire_direct = chunks - 1;
-        return;
-    }
+    if (c->wire_direct_fixed >= 0 || chunks < 2 || d >= chunks) return;   // nothing to balance
     const double p = t_pcie / (chunks + 3.0 * d), w = t_widen / (chunks - d);
     c->wire_pcie_us = c->wire_pcie_us > 0 ? 0.5 * (c->wire_pcie_us + p) : p;
     c->wire_widen_us = c->wire_widen_us > 0 ? 0.5 * (c->wire_widen_us + w) : w;

@@ -1165,6 +1165,15 @@ def test_wire_format_split_frame(direct, splits, medium_tables, medium_oracle):
         assert env.last_wire_direct == (0 if t >= 9 else min(max(direct, 0), 5)) or direct < 0
         assert 0 <= env.wire_direct <= (5 if direct < 0 else max(direct, 0))
     env.features = pinned
+    # an empty call changes nothing, in particular not the split
+    import ctypes
+    ptr = lambda a: ctypes.c_void_p(a.ctypes.data)
+    assert env.lib.psk_craft_host_tick_resident(env.ctx, None, ptr(env.features), 3, 0, ptr(env.expert), None,
+                                                None, 0, None, None) == 0
+    assert env.wire_direct >= 0
+    env.features[:] = -3.0
+    env.tick_resident(features="f32_wire_u8")
+    assert np.array_equal(env.features, orc.tick()["features"])
     env.close()
 
 
