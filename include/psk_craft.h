@@ -313,6 +313,11 @@ int psk_craft_host_set_threads(psk_craft_host_ctx *ctx, int32_t threads);
  * route. */
 int psk_craft_host_set_zerocopy_max(psk_craft_host_ctx *ctx, int64_t max_envs);
 int psk_craft_host_wire_direct(const psk_craft_host_ctx *ctx);
+/* Testing hook: the split rule on its own (no CUDA call).  Given a call of `chunks` chunks that sent d
+ * as f32, whose last byte landed t_pcie_us and whose widening ended t_widen_us after its start, returns the
+ * d of the next call; *p_us / *w_us hold the smoothed per-chunk rates between calls (start them at 0). */
+int psk_debug_wire_split_next(int chunks, int d, double t_pcie_us, double t_widen_us, double *p_us,
+                              double *w_us);
 int psk_craft_host_set_wire_direct(psk_craft_host_ctx *ctx, int32_t chunks);
 int psk_host_widen_u8_f32(const uint8_t *src, float *dst, size_t n, int threads);
 int psk_craft_host_reset(psk_craft_host_ctx *ctx, int64_t n);

@@ -28,6 +28,7 @@ CRAFT_EXPORTS = (
     "psk_craft_tick_u8", "psk_craft_rollout_u8", "psk_craft_host_threads", "psk_craft_host_set_threads",
     "psk_host_widen_u8_f32", "psk_debug_chain_skip_ticket", "psk_craft_host_wire_direct",
     "psk_craft_host_set_wire_direct", "psk_craft_host_set_zerocopy_max",
+    "psk_debug_wire_split_next",
 )
 FEATURES_NONE, FEATURES_F32, FEATURES_U8, FEATURES_F32_WIRE_U8 = 0, 1, 2, 3
 
@@ -118,6 +119,8 @@ def load():
     lib.psk_craft_host_wire_direct.argtypes = [vp]
     lib.psk_craft_host_set_wire_direct.argtypes = [vp, i32]
     lib.psk_craft_host_set_zerocopy_max.argtypes = [vp, i64]
+    lib.psk_debug_wire_split_next.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                              ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.psk_host_widen_u8_f32.argtypes = [vp, vp, ctypes.c_size_t, ctypes.c_int]
     lib.psk_set_tuning.argtypes = [ctypes.c_char_p, i32]
     lib.psk_get_tuning.argtypes = [ctypes.c_char_p, ctypes.POINTER(i32)]

@@ -324,19 +324,10 @@ static int wire_direct_chunks(psk_craft_host_ctx *c, const void *host_features, 
 }
 
 // After a call with `d` of `chunks` chunks sent as f32: PCIe finished `t_pcie` us and the widening
-// `t_widen` us after the call started.  One u8 chunk costs p on the wire (an f32 chunk 4 p) and w on
-// the host threads; the two finish together at  d* = chunks (w - p) / (w + 3 p).
+// `t_widen` us after the call started; the rule itself is psk_wire_split_next (psk_hostcpu.cpp).
 static void wire_direct_update(psk_craft_host_ctx *c, int chunks, int d, double t_pcie, double t_widen) {
-    if (c->wire_direct_fixed >= 0 || chunks < 2 || d >= chunks) return;   // nothing to balance
-    const double p = t_pcie / (chunks + 3.0 * d), w = t_widen / (chunks - d);
-    c->wire_pcie_us = c->wire_pcie_us > 0 ? 0.5 * (c->wire_pcie_us + p) : p;
-    c->wire_widen_us = c->wire_widen_us > 0 ? 0.5 * (c->wire_widen_us + w) : w;
-    const double ps = c->wire_pcie_us, ws = c->wire_widen_us;
-    double best = ws > ps ? chunks * (ws - ps) / (ws + 3.0 * ps) : 0.0;
-    int nd = static_cast<int>(best + 0.5);
-    if (nd > chunks - 1) nd = chunks - 1;
-    // one chunk of hysteresis: a move has to pay for more than the granularity of the split
-    if (nd > d || nd < d - 1 || (nd < d && best < d - 0.75)) c->wire_direct = nd;
+    if (c->wire_direct_fixed >= 0 || chunks < 2 || d >= chunks) return;     // nothing to balance
+    c->wire_direct = psk_wire_split_next(chunks, d, t_pcie, t_widen, &c->wire_pcie_us, &c->wire_widen_us);
 }
 
 // The running statistics and the error flags (d_stats: u64[4] | i32) into the pinned mailbox, as a

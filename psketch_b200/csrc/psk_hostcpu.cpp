@@ -140,6 +140,31 @@ void PskWidenPool::finish() {
     while (done_.load(std::memory_order_acquire) < t) _mm_pause();
 }
 
+int psk_wire_split_next(int chunks, int d, double t_pcie_us, double t_widen_us, double *p_us, double *w_us) {
+    if (d < 0) d = 0;
+    if (chunks < 2 || d >= chunks || t_pcie_us <= 0.0 || t_widen_us <= 0.0)
+        return d < chunks ? d : (chunks > 0 ? chunks - 1 : 0);          // nothing to balance
+    const double p = t_pcie_us / (chunks + 3.0 * d), w = t_widen_us / (chunks - d);
+    *p_us = *p_us > 0 ? 0.5 * (*p_us + p) : p;
+    *w_us = *w_us > 0 ? 0.5 * (*w_us + w) : w;
+    const double ps = *p_us, ws = *w_us;
+    // 0.8: an f32 chunk costs the host more than its wire time — its DMA writes compete with the threads'
+    // stores for the same DRAM (measured: where the plain balance said d = 1 the step was 4 % slower than
+    // with d = 0).  Rounded down, and half a chunk of hysteresis on the way back.
+    const double best = ws > ps ? 0.8 * chunks * (ws - ps) / (ws + 3.0 * ps) : 0.0;
+    int nd = static_cast<int>(best);
+    if (nd > chunks - 1) nd = chunks - 1;
+    if (nd > d) return nd;
+    if (best < d - 0.5) return nd;
+    return d;
+}
+
+extern "C" int psk_debug_wire_split_next(int chunks, int d, double t_pcie_us, double t_widen_us, double *p_us,
+                                         double *w_us) {
+    if (!p_us || !w_us) return -1;
+    return psk_wire_split_next(chunks, d, t_pcie_us, t_widen_us, p_us, w_us);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // C ABI (include/psk_craft.h): the widening on its own, for callers that take PSK_FEATURES_U8 frames
 // and want f32 later.  No CUDA call: usable (and tested) on a box without a GPU.

@@ -150,6 +150,48 @@ def test_c_host_runs_rollouts(tmp_path):
     assert out.strip().endswith("teacher: 3 3 4 5 3 3 4 5"), out
 
 
+def test_wire_split_rule_converges_and_holds():
+    """The split-frame rule of PSK_FEATURES_F32_WIRE_U8 (psk_debug_wire_split_next; no CUDA call): on a
+    simulated box where a byte chunk costs p on the wire (an f32 chunk 4 p) and w on the host threads, the
+    number of chunks sent as f32 settles within a few calls just below 0.8 C (w - p) / (w + 3 p), stays
+    there under 5 % timing noise (moves of at most one chunk), returns to 0 when the host is the faster
+    side, and never leaves [0, C - 1]."""
+    import ctypes
+    from psketch_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(3)
+
+    def simulate(C, p, w, calls=40, d=0, noise=0.0):
+        ps, ws = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        hist = []
+        for _ in range(calls):
+            jp, jw = 1 + noise * rng.uniform(-1, 1), 1 + noise * rng.uniform(-1, 1)
+            t_pcie = (C + 3 * d) * p * jp + 30.0                  # + start-up latency
+            t_widen = (C - d) * max(w, p) * jw + 30.0             # threads cannot finish before the bytes land
+            d = lib.psk_debug_wire_split_next(C, d, t_pcie, t_widen, ctypes.byref(ps), ctypes.byref(ws))
+            assert 0 <= d <= C - 1
+            hist.append(d)
+        return hist
+
+    for C, p, w in [(16, 29.6, 75.0), (16, 29.6, 34.0), (16, 29.6, 20.0), (5, 10.0, 80.0), (64, 8.0, 12.0),
+                    (16, 60.0, 61.0), (2, 10.0, 100.0)]:
+        ideal = min(max(0.0, 0.8 * C * (w - p) / (w + 3 * p)), C - 1)       # the rule aims below the balance
+        hist = simulate(C, p, w)
+        assert len(set(hist[6:])) == 1, (C, p, w, hist)                     # settled, no oscillation
+        assert ideal - 1.6 <= hist[-1] <= ideal + 0.6, (C, p, w, hist, ideal)
+        noisy = simulate(C, p, w, calls=200, noise=0.05)
+        assert max(noisy[10:]) - min(noisy[10:]) <= 1 + (C >= 64), (C, p, w, noisy)
+        assert ideal - 1.6 <= np.mean(noisy[10:]) <= ideal + 1.0, (C, p, w, noisy, ideal)
+    # the host became the faster side (e.g. the caller gave the library more threads): back to bytes only
+    assert simulate(16, 29.6, 20.0, d=7)[-1] == 0
+    # degenerate calls leave the split alone
+    ps, ws = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    assert lib.psk_debug_wire_split_next(1, 0, 50.0, 50.0, ctypes.byref(ps), ctypes.byref(ws)) == 0
+    assert lib.psk_debug_wire_split_next(0, 0, 0.0, 0.0, ctypes.byref(ps), ctypes.byref(ws)) == 0
+    assert lib.psk_debug_wire_split_next(4, 9, 50.0, 50.0, ctypes.byref(ps), ctypes.byref(ws)) == 3
+    assert lib.psk_debug_wire_split_next(4, 2, 0.0, 50.0, ctypes.byref(ps), ctypes.byref(ws)) == 2
+
+
 def test_host_widening_of_byte_frames():
     """psk_host_widen_u8_f32 (the host half of PSK_FEATURES_F32_WIRE_U8): dst[i] == src[i] for every
     length and alignment, single-threaded and through the thread pool.  No CUDA call: runs here."""
